@@ -1,0 +1,512 @@
+// C ABI (include/tp3.h) over the sm_100a kernels: context, seeding tables, launches.
+// No CPU fallback lives here: without a usable device every compute entry point fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jump_tables.hpp"
+#include "kernels.cuh"
+
+using namespace tp3;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceSlot {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint32_t* d_ranf_table = nullptr;
+    uint64_t* d_xo_digit_polys = nullptr;
+    uint64_t* d_xo_thread_polys = nullptr;
+    uint64_t* d_xo_states = nullptr;
+    size_t xo_states_cap = 0;
+    tp3_acc* d_out = nullptr;
+    size_t out_cap = 0;
+    tp3_acc* d_merged = nullptr;
+    // last launch
+    uint64_t last_first = 0, last_n = 0;
+};
+
+}  // namespace
+
+struct tp3_ctx {
+    tp3_params params;
+    std::vector<DeviceSlot> devs;
+    std::string err;
+    uint64_t launches = 0;
+    // host copies of the seeding data
+    uint32_t ranf_base[kRanfLag];
+    std::vector<uint32_t> ranf_table;
+    std::vector<uint64_t> xo_digit_polys;   // [n_digits][256][4]
+    std::vector<uint64_t> xo_thread_polys;  // [kThreads][4]
+    uint64_t xo_base[4];
+    int xo_digits = 0;
+};
+
+namespace {
+
+#define TP3_CUDA(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+            return TP3_E_CUDA;                                                                           \
+        }                                                                                                \
+    } while (0)
+
+template <class F> PhysParams<F> phys_params(const tp3_params& p) {
+    PhysParams<F> q;
+    q.e_total = (F)p.e_total;
+    q.acut = (F)p.acut;
+    q.bcut = (F)p.bcut;
+    q.e_min = (F)p.e_min;
+    q.sincut = (F)p.sincut;
+    q.g_a = (F)p.g_a;
+    q.g_beta_p = (F)p.g_beta_p;
+    q.g_beta_m = (F)p.g_beta_m;
+    for (int k = 0; k < 5; ++k) q.sigma_contribs[k] = (F)p.sigma_contribs[k];
+    return q;
+}
+
+template <class F, int RNG, bool SORT, bool LITERAL>
+void launch_sim(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
+    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)a.n_batches, kThreads, 0, st>>>(a, phys_params<F>(p));
+}
+template <class F, int RNG, bool SORT, bool LITERAL>
+void launch_dump(const SimArgs& a, const tp3_params& p, const DumpArgs& d, cudaStream_t st) {
+    dump_kernel<F, RNG, SORT, LITERAL><<<1, kThreads, 0, st>>>(a, phys_params<F>(p), d);
+}
+
+using SimFn = void (*)(const SimArgs&, const tp3_params&, cudaStream_t);
+using DumpFn = void (*)(const SimArgs&, const tp3_params&, const DumpArgs&, cudaStream_t);
+
+template <class F, int RNG> SimFn pick_sim2(bool sort, bool literal) {
+    if (sort) return literal ? launch_sim<F, RNG, true, true> : launch_sim<F, RNG, true, false>;
+    return literal ? launch_sim<F, RNG, false, true> : launch_sim<F, RNG, false, false>;
+}
+template <class F, int RNG> DumpFn pick_dump2(bool sort, bool literal) {
+    if (sort) return literal ? launch_dump<F, RNG, true, true> : launch_dump<F, RNG, true, false>;
+    return literal ? launch_dump<F, RNG, false, true> : launch_dump<F, RNG, false, false>;
+}
+SimFn pick_sim(const tp3_params& p) {
+    const bool f32 = p.flags & TP3_F32, xo = p.flags & TP3_STANDARD_RANDOM;
+    const bool sort = !(p.flags & TP3_NO_PHOTON_SORTING), lit = p.kernel == TP3_KERNEL_LITERAL;
+    if (f32) return xo ? pick_sim2<float, RNG_XOSHIRO>(sort, lit) : pick_sim2<float, RNG_RANF>(sort, lit);
+    return xo ? pick_sim2<double, RNG_XOSHIRO>(sort, lit) : pick_sim2<double, RNG_RANF>(sort, lit);
+}
+DumpFn pick_dump(const tp3_params& p) {
+    const bool f32 = p.flags & TP3_F32, xo = p.flags & TP3_STANDARD_RANDOM;
+    const bool sort = !(p.flags & TP3_NO_PHOTON_SORTING), lit = p.kernel == TP3_KERNEL_LITERAL;
+    if (f32) return xo ? pick_dump2<float, RNG_XOSHIRO>(sort, lit) : pick_dump2<float, RNG_RANF>(sort, lit);
+    return xo ? pick_dump2<double, RNG_XOSHIRO>(sort, lit) : pick_dump2<double, RNG_RANF>(sort, lit);
+}
+
+// Seeding tables for the xoshiro streams (host, once per context).
+void build_xoshiro_tables(tp3_ctx* c) {
+    const bool f32 = c->params.flags & TP3_F32;
+    const bool jump = c->params.flags & TP3_FASTER_THREADING;
+    const int deg = f32 ? 128 : 256;
+    Gf2Mod mod;
+    if (f32) {
+        Xoshiro128 g = xoshiro128_seed(12345);  // standard.rs:23
+        for (int i = 0; i < 4; ++i) c->xo_base[i] = g.s[i];
+        mod = xoshiro_min_poly(g, 128);
+    } else {
+        Xoshiro256 g = xoshiro256_seed(12345);
+        for (int i = 0; i < 4; ++i) c->xo_base[i] = g.s[i];
+        mod = xoshiro_min_poly(g, 256);
+    }
+    // per-batch generator: G = x^(12 * 10000) (sequential stream) or jump() = x^(2^(deg/2))
+    Gf2Poly G = jump ? gf2_x_pow(1, deg / 2, mod) : gf2_x_pow((uint64_t)kDrawsPerEvent * kBatch, 0, mod);
+    c->xo_digits = 5;  // 2^40 batches
+    c->xo_digit_polys.assign((size_t)c->xo_digits * 256 * 4, 0);
+    Gf2Poly unit = G;
+    for (int k = 0; k < c->xo_digits; ++k) {
+        Gf2Poly cur;
+        cur.w[0] = 1;
+        for (int d = 0; d < 256; ++d) {
+            std::memcpy(&c->xo_digit_polys[((size_t)k * 256 + d) * 4], cur.w, 32);
+            cur = gf2_mul_mod(cur, unit, mod);
+        }
+        unit = cur;
+    }
+    c->xo_thread_polys.assign((size_t)kThreads * 4, 0);
+    for (int t = 0; t < kThreads; ++t) {
+        const uint64_t off = (uint64_t)kDrawsPerEvent * ((t / 32) * kWarpEvents + (t % 32) * kLaneEvents);
+        Gf2Poly p = gf2_x_pow(off, 0, mod);
+        std::memcpy(&c->xo_thread_polys[(size_t)t * 4], p.w, 32);
+    }
+}
+
+int ensure_out(tp3_ctx* c, DeviceSlot& s, uint64_t n) {
+    if (s.out_cap < n) {
+        if (s.d_out) TP3_CUDA(c, cudaFree(s.d_out));
+        s.d_out = nullptr;
+        s.out_cap = 0;
+        TP3_CUDA(c, cudaMalloc(&s.d_out, n * sizeof(tp3_acc)));
+        s.out_cap = n;
+    }
+    if ((c->params.flags & TP3_STANDARD_RANDOM) && s.xo_states_cap < n) {
+        if (s.d_xo_states) TP3_CUDA(c, cudaFree(s.d_xo_states));
+        s.d_xo_states = nullptr;
+        s.xo_states_cap = 0;
+        TP3_CUDA(c, cudaMalloc(&s.d_xo_states, n * 4 * sizeof(uint64_t)));
+        s.xo_states_cap = n;
+    }
+    return TP3_OK;
+}
+
+SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len) {
+    SimArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.first_batch = first;
+    a.n_batches = n;
+    a.last_batch_len = last_len;
+    a.jump_seeding = (c->params.flags & TP3_FASTER_THREADING) ? 1u : 0u;
+    a.ranf_table = s.d_ranf_table;
+    a.xo_batch_states = s.d_xo_states;
+    a.xo_thread_polys = s.d_xo_thread_polys;
+    a.out = s.d_out;
+    std::memcpy(a.ranf_base, c->ranf_base, sizeof a.ranf_base);
+    a.ranf_seed = RANF_DEFAULT_SEED;
+    return a;
+}
+
+// Enqueue seeding (xoshiro) + the fused kernel for [first, first+n) on one device slot.
+int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len) {
+    TP3_CUDA(c, cudaSetDevice(s.dev));
+    int rc = ensure_out(c, s, n);
+    if (rc) return rc;
+    if (n > 0x7fffffffull) {
+        c->err = "too many batches in one launch";
+        return TP3_E_INVALID;
+    }
+    if (!(c->params.flags & TP3_STANDARD_RANDOM) && (c->params.flags & TP3_FASTER_THREADING)) {
+        // ranf.rs:136-140 reseeds with seed + 123456*b in i32; beyond b = 6199 the seed leaves [0, 1e9)
+        // and the reference itself produces out-of-range words. Refuse rather than imitate that.
+        if (first + n > 6200) {
+            c->err = "RANF jump() seeding is only defined for the first 6200 batches (seed < 1e9)";
+            return TP3_E_INVALID;
+        }
+    }
+    SimArgs a = make_args(c, s, first, n, last_len);
+    if (c->params.flags & TP3_STANDARD_RANDOM) {
+        const unsigned blocks = (unsigned)((n + 127) / 128);
+        if (c->params.flags & TP3_F32)
+            xoshiro_seed_kernel<Xoshiro128Lane><<<blocks, 128, 0, s.stream>>>(first, n, s.d_xo_digit_polys, c->xo_digits,
+                                                                              c->xo_base[0], c->xo_base[1], c->xo_base[2],
+                                                                              c->xo_base[3], s.d_xo_states);
+        else
+            xoshiro_seed_kernel<Xoshiro256Lane><<<blocks, 128, 0, s.stream>>>(first, n, s.d_xo_digit_polys, c->xo_digits,
+                                                                              c->xo_base[0], c->xo_base[1], c->xo_base[2],
+                                                                              c->xo_base[3], s.d_xo_states);
+        ++c->launches;
+    }
+    pick_sim(c->params)(a, c->params, s.stream);
+    ++c->launches;
+    TP3_CUDA(c, cudaGetLastError());
+    s.last_first = first;
+    s.last_n = n;
+    return TP3_OK;
+}
+
+// Contiguous split of [0, n) over the device slots: slot g gets [n*g/G, n*(g+1)/G).
+void split(uint64_t n, size_t G, size_t g, uint64_t& off, uint64_t& cnt) {
+    off = n * g / G;
+    cnt = n * (g + 1) / G - off;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tp3_abi_version(void) { return TP3_ABI_VERSION; }
+
+const char* tp3_last_error(const tp3_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx** out) {
+    if (!params || !out || n_dev < 1) {
+        g_create_error = "tp3_create: bad arguments";
+        return TP3_E_INVALID;
+    }
+    if (params->flags & TP3_FASTER_EVGEN) {
+        g_create_error = "faster-evgen is not available on the GPU path yet";
+        return TP3_E_INVALID;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+        return TP3_E_NO_DEVICE;
+    }
+    tp3_ctx* c = new tp3_ctx;
+    c->params = *params;
+    ranf_seed_state(RANF_DEFAULT_SEED, c->ranf_base);
+    const bool xo = params->flags & TP3_STANDARD_RANDOM;
+    if (xo) build_xoshiro_tables(c);
+    else c->ranf_table = ranf_round_jump_table();
+    auto fail = [&](int code, const std::string& msg) {
+        g_create_error = msg;
+        tp3_destroy(c);
+        return code;
+    };
+    for (int i = 0; i < n_dev; ++i) {
+        DeviceSlot s;
+        s.dev = dev_ids ? dev_ids[i] : i;
+        if (s.dev < 0 || s.dev >= count) return fail(TP3_E_NO_DEVICE, "device id out of range");
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, s.dev)) != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
+        if (prop.major != 10) return fail(TP3_E_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+        if ((e = cudaSetDevice(s.dev)) != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return fail(TP3_E_CUDA, cudaGetErrorString(e));
+        s.own_stream = true;
+        auto up = [&](const void* h, size_t bytes, void** d) {
+            cudaError_t r = cudaMalloc(d, bytes);
+            if (r == cudaSuccess) r = cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+            return r;
+        };
+        if (xo) {
+            e = up(c->xo_digit_polys.data(), c->xo_digit_polys.size() * 8, (void**)&s.d_xo_digit_polys);
+            if (e == cudaSuccess) e = up(c->xo_thread_polys.data(), c->xo_thread_polys.size() * 8, (void**)&s.d_xo_thread_polys);
+        } else {
+            e = up(c->ranf_table.data(), c->ranf_table.size() * 4, (void**)&s.d_ranf_table);
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_merged, sizeof(tp3_acc));
+        c->devs.push_back(s);
+        if (e != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
+    }
+    *out = c;
+    return TP3_OK;
+}
+
+void tp3_destroy(tp3_ctx* c) {
+    if (!c) return;
+    for (auto& s : c->devs) {
+        cudaSetDevice(s.dev);
+        if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
+        cudaFree(s.d_ranf_table);
+        cudaFree(s.d_xo_digit_polys);
+        cudaFree(s.d_xo_thread_polys);
+        cudaFree(s.d_xo_states);
+        cudaFree(s.d_out);
+        cudaFree(s.d_merged);
+    }
+    delete c;
+}
+
+int tp3_set_stream(tp3_ctx* c, int slot, void* stream) {
+    if (!c || slot < 0 || slot >= (int)c->devs.size()) return TP3_E_INVALID;
+    DeviceSlot& s = c->devs[slot];
+    if (s.own_stream && s.stream) {
+        cudaSetDevice(s.dev);
+        cudaStreamDestroy(s.stream);
+    }
+    s.stream = (cudaStream_t)stream;
+    s.own_stream = false;
+    return TP3_OK;
+}
+
+uint64_t tp3_launch_count(const tp3_ctx* c) { return c ? c->launches : 0; }
+
+int tp3_synchronize(tp3_ctx* c) {
+    if (!c) return TP3_E_INVALID;
+    for (auto& s : c->devs) {
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+    }
+    return TP3_OK;
+}
+
+int tp3_simulate_batches_device(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len) {
+    if (!c || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE) {
+        if (c) c->err = "tp3_simulate_batches: bad range";
+        return TP3_E_INVALID;
+    }
+    const size_t G = c->devs.size();
+    for (size_t g = 0; g < G; ++g) {
+        uint64_t off, cnt;
+        split(n, G, g, off, cnt);
+        c->devs[g].last_n = 0;
+        if (!cnt) continue;
+        const uint32_t ll = (off + cnt == n) ? last_len : TP3_EVENT_BATCH_SIZE;
+        int rc = enqueue_range(c, c->devs[g], first + off, cnt, ll);
+        if (rc) return rc;
+    }
+    return TP3_OK;
+}
+
+int tp3_fetch(tp3_ctx* c, tp3_acc* out, uint64_t n) {
+    if (!c || !out) return TP3_E_INVALID;
+    uint64_t done = 0;
+    for (auto& s : c->devs) {
+        if (!s.last_n) continue;
+        if (done + s.last_n > n) {
+            c->err = "tp3_fetch: output array too small";
+            return TP3_E_INVALID;
+        }
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        TP3_CUDA(c, cudaMemcpyAsync(out + done, s.d_out, s.last_n * sizeof(tp3_acc), cudaMemcpyDeviceToHost, s.stream));
+        done += s.last_n;
+    }
+    return tp3_synchronize(c);
+}
+
+int tp3_simulate_batches(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
+    if (!out) return TP3_E_INVALID;
+    int rc = tp3_simulate_batches_device(c, first, n, last_len);
+    if (rc) return rc;
+    return tp3_fetch(c, out, n);
+}
+
+int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
+    if (!out) return TP3_E_INVALID;
+    int rc = tp3_simulate_batches_device(c, first, n, last_len);
+    if (rc) return rc;
+    std::vector<tp3_acc> parts;
+    for (auto& s : c->devs) {
+        if (!s.last_n) continue;
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        if (c->params.flags & TP3_F32) merge_kernel<float><<<1, 32, 0, s.stream>>>(s.d_out, s.last_n, s.d_merged);
+        else merge_kernel<double><<<1, 32, 0, s.stream>>>(s.d_out, s.last_n, s.d_merged);
+        ++c->launches;
+        TP3_CUDA(c, cudaGetLastError());
+    }
+    for (auto& s : c->devs) {
+        if (!s.last_n) continue;
+        tp3_acc h;
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        TP3_CUDA(c, cudaMemcpyAsync(&h, s.d_merged, sizeof h, cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        parts.push_back(h);
+    }
+    *out = parts[0];
+    for (size_t i = 1; i < parts.size(); ++i) tp3_merge(out, &parts[i], c->params.flags);
+    return TP3_OK;
+}
+
+static int run_dump(tp3_ctx* c, uint64_t batch, uint32_t n_events, uint64_t* words, double* momenta, int32_t* kept,
+                    double* m2) {
+    DeviceSlot& s = c->devs[0];
+    TP3_CUDA(c, cudaSetDevice(s.dev));
+    int rc = ensure_out(c, s, 1);
+    if (rc) return rc;
+    SimArgs a = make_args(c, s, batch, 1, TP3_EVENT_BATCH_SIZE);
+    if (c->params.flags & TP3_STANDARD_RANDOM) {
+        if (c->params.flags & TP3_F32)
+            xoshiro_seed_kernel<Xoshiro128Lane><<<1, 32, 0, s.stream>>>(batch, 1, s.d_xo_digit_polys, c->xo_digits, c->xo_base[0],
+                                                                        c->xo_base[1], c->xo_base[2], c->xo_base[3], s.d_xo_states);
+        else
+            xoshiro_seed_kernel<Xoshiro256Lane><<<1, 32, 0, s.stream>>>(batch, 1, s.d_xo_digit_polys, c->xo_digits, c->xo_base[0],
+                                                                        c->xo_base[1], c->xo_base[2], c->xo_base[3], s.d_xo_states);
+        ++c->launches;
+    }
+    DumpArgs d;
+    std::memset(&d, 0, sizeof d);
+    d.n_events = n_events;
+    if (words) TP3_CUDA(c, cudaMalloc(&d.words, (size_t)n_events * 12 * 8));
+    if (momenta) {
+        TP3_CUDA(c, cudaMalloc(&d.momenta, (size_t)n_events * 12 * 8));
+        TP3_CUDA(c, cudaMalloc(&d.kept, (size_t)n_events * 4));
+        TP3_CUDA(c, cudaMalloc(&d.m2, (size_t)n_events * 5 * 8));
+    }
+    pick_dump(c->params)(a, c->params, d, s.stream);
+    ++c->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    if (e == cudaSuccess && words) e = cudaMemcpy(words, d.words, (size_t)n_events * 12 * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && momenta) {
+        e = cudaMemcpy(momenta, d.momenta, (size_t)n_events * 12 * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(kept, d.kept, (size_t)n_events * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(m2, d.m2, (size_t)n_events * 5 * 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d.words);
+    cudaFree(d.momenta);
+    cudaFree(d.kept);
+    cudaFree(d.m2);
+    if (e != cudaSuccess) {
+        c->err = std::string("dump: ") + cudaGetErrorString(e);
+        return TP3_E_CUDA;
+    }
+    return TP3_OK;
+}
+
+int tp3_rng_dump(tp3_ctx* c, uint64_t batch, uint32_t n_words, uint64_t* out) {
+    if (!c || !out || n_words == 0 || n_words > 12u * TP3_EVENT_BATCH_SIZE) return TP3_E_INVALID;
+    const uint32_t n_events = (n_words + 11) / 12;
+    std::vector<uint64_t> tmp((size_t)n_events * 12);
+    int rc = run_dump(c, batch, n_events, tmp.data(), nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    std::memcpy(out, tmp.data(), (size_t)n_words * 8);
+    return TP3_OK;
+}
+
+int tp3_events_dump(tp3_ctx* c, uint64_t batch, uint32_t n, double* momenta, int32_t* kept, double* m2) {
+    if (!c || !momenta || !kept || !m2 || n == 0 || n > TP3_EVENT_BATCH_SIZE) return TP3_E_INVALID;
+    return run_dump(c, batch, n, nullptr, momenta, kept, m2);
+}
+
+int tp3_peak_probe(tp3_ctx* c, int which, double* tflops) {
+    if (!c || !tflops) return TP3_E_INVALID;
+    DeviceSlot& s = c->devs[0];
+    TP3_CUDA(c, cudaSetDevice(s.dev));
+    cudaDeviceProp prop;
+    TP3_CUDA(c, cudaGetDeviceProperties(&prop, s.dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    const int iters = which == 0 ? 4096 : 8192;
+    void* buf = nullptr;
+    TP3_CUDA(c, cudaMalloc(&buf, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    TP3_CUDA(c, cudaEventCreate(&e0));
+    TP3_CUDA(c, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        TP3_CUDA(c, cudaEventRecord(e0, s.stream));
+        if (which == 0) fma_probe_kernel<double><<<blocks, threads, 0, s.stream>>>((double*)buf, iters, 0.999999, 1e-6);
+        else fma_probe_kernel<float><<<blocks, threads, 0, s.stream>>>((float*)buf, iters, 0.999999f, 1e-6f);
+        ++c->launches;
+        TP3_CUDA(c, cudaEventRecord(e1, s.stream));
+        TP3_CUDA(c, cudaEventSynchronize(e1));
+        float ms;
+        TP3_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    const double fma = (double)blocks * threads * (double)iters * 64.0;
+    *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
+    return TP3_OK;
+}
+
+int tp3_host_ranf_round(int32_t seed, uint64_t round, uint32_t* out55) {
+    if (!out55 || seed <= 0 || seed >= (int32_t)RANF_MOD) return TP3_E_INVALID;
+    static const std::vector<uint32_t> table = ranf_round_jump_table();
+    ranf_round_at(table, seed, round, out55);
+    return TP3_OK;
+}
+
+int tp3_host_xoshiro_state(int f32, uint64_t n_steps, uint64_t n_jumps, uint64_t* out4) {
+    if (!out4) return TP3_E_INVALID;
+    if (f32) {
+        Xoshiro128 g = xoshiro128_seed(12345);
+        Gf2Mod mod = xoshiro_min_poly(g, 128);
+        Gf2Poly p = gf2_mul_mod(gf2_x_pow(n_steps, 0, mod), gf2_pow(gf2_x_pow(1, 64, mod), n_jumps, mod), mod);
+        xoshiro_apply(g, p, 128);
+        for (int i = 0; i < 4; ++i) out4[i] = g.s[i];
+    } else {
+        Xoshiro256 g = xoshiro256_seed(12345);
+        Gf2Mod mod = xoshiro_min_poly(g, 256);
+        Gf2Poly p = gf2_mul_mod(gf2_x_pow(n_steps, 0, mod), gf2_pow(gf2_x_pow(1, 128, mod), n_jumps, mod), mod);
+        xoshiro_apply(g, p, 256);
+        for (int i = 0; i < 4; ++i) out4[i] = g.s[i];
+    }
+    return TP3_OK;
+}
+
+}  // extern "C"

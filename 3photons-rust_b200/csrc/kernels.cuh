@@ -1,0 +1,336 @@
+// The fused per-batch kernel (replaces the closure of src/main.rs:103-128 and everything it
+// calls) plus the small parity/seeding kernels.  One CTA = one batch of <= 10 000 events
+// (src/scheduling/mod.rs:21); warp w of the CTA owns events [w*1280, (w+1)*1280) of the batch.
+#pragma once
+
+#include <cstdint>
+
+#include "../../include/tp3.h"
+#include "physics.cuh"
+#include "rng.cuh"
+
+namespace tp3 {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kBatch = TP3_EVENT_BATCH_SIZE;
+constexpr int kWarpEvents = 1280;  // ceil32(10000 / 8): events of a batch owned by one warp
+constexpr int kLaneEvents = kWarpEvents / 32;  // xoshiro: contiguous events per lane
+static_assert(kWarpEvents * kWarps >= kBatch, "partition must cover a batch");
+
+enum RngKind { RNG_RANF = 0, RNG_XOSHIRO = 1 };
+
+struct SimArgs {
+    uint64_t first_batch;      // index of the first batch of this launch within the run
+    uint64_t n_batches;        // batches in this launch (grid size)
+    uint32_t last_batch_len;   // events in the last batch of the launch
+    uint32_t jump_seeding;     // TP3_FASTER_THREADING: batch b starts after b rng.jump()s
+    const uint32_t* ranf_table;        // [kRanfDigits][256][55]
+    const uint64_t* xo_batch_states;   // [n_batches][4] from the seeding kernel
+    const uint64_t* xo_thread_polys;   // [kThreads][4] jump polynomial of each thread's offset in the batch
+    tp3_acc* out;                      // [n_batches]
+    uint32_t ranf_base[kRanfLag];      // seeded round 0 (ranf.rs:28-66), slot order
+    int32_t ranf_seed;
+};
+
+struct DumpArgs {
+    uint32_t n_events;   // events of the batch to dump
+    uint64_t* words;     // [n_events][12] raw stream words (may be null)
+    double* momenta;     // [n_events][3][4]             (may be null)
+    int32_t* kept;       // [n_events]
+    double* m2;          // [n_events][5]
+};
+
+template <class F, int RNG> struct RawWord;
+template <class F> struct RawWord<F, RNG_RANF> { using type = uint32_t; };
+template <> struct RawWord<double, RNG_XOSHIRO> { using type = uint64_t; };
+template <> struct RawWord<float, RNG_XOSHIRO> { using type = uint32_t; };
+
+// raw stream word -> uniform in [0,1): ranf.rs:99 / rand 0.8.5 Standard distribution (Appendix B.3)
+__device__ __forceinline__ double to_uniform(uint32_t n, double*, int) { return (double)(int)n * 1e-9; }
+__device__ __forceinline__ float to_uniform_ranf(uint32_t n) { return (float)(int)n * 1e-9f; }
+__device__ __forceinline__ double to_uniform_xo(uint64_t x) { return (double)(x >> 11) * (1.0 / 9007199254740992.0); }
+__device__ __forceinline__ float to_uniform_xo(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// Per-warp random source: hands each lane the 12 raw words of "its" event of iteration `it`.
+template <class F, int RNG> struct WarpRng;
+
+template <class F> struct WarpRng<F, RNG_RANF> {
+    RanfWarpStream s;
+    int lo, hi;
+    __device__ void init(const SimArgs& a, RanfWarpSmem* sm, uint32_t* blk_base, uint64_t batch, int n_ev, int warp,
+                         int lane) {
+        lo = warp * kWarpEvents;
+        hi = min(n_ev, lo + kWarpEvents);
+        if (lo >= hi) return;
+        if (a.jump_seeding)
+            s.init(sm, blk_base, (uint64_t)kDrawsPerEvent * lo, a.ranf_table, lane);
+        else
+            s.init(sm, a.ranf_base, (uint64_t)kDrawsPerEvent * (batch * kBatch + lo), a.ranf_table, lane);
+    }
+    __device__ int iterations() const { return lo < hi ? (hi - lo + 31) / 32 : 0; }
+    __device__ int event_of(int it, int lane) const {
+        const int e = lo + 32 * it + lane;
+        return e < hi ? e : -1;
+    }
+    __device__ void raw(int it, int lane, uint32_t w[12]) {
+        s.ensure((it + 1) * kWarpDraws, lane);
+        s.draws(it, lane, w);
+    }
+    __device__ static F uniform(uint32_t w) {
+        if (sizeof(F) == 8) return (F)((double)(int)w * 1e-9);
+        return (F)to_uniform_ranf(w);
+    }
+};
+
+template <> struct WarpRng<double, RNG_XOSHIRO> {
+    Xoshiro256Lane g;
+    int lo, hi;
+    __device__ void init(const SimArgs& a, RanfWarpSmem*, uint32_t*, uint64_t batch, int n_ev, int warp, int lane) {
+        lo = warp * kWarpEvents + lane * kLaneEvents;
+        hi = min(min(n_ev, (warp + 1) * kWarpEvents), lo + kLaneEvents);
+        const uint64_t* st = a.xo_batch_states + 4 * (batch - a.first_batch);
+        g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
+        const bool any = __any_sync(0xffffffffu, lo < hi);
+        if (any && (warp | lane)) g.apply(a.xo_thread_polys + 4 * (warp * 32 + lane));
+    }
+    __device__ int iterations() const {
+        const int n = lo < hi ? hi - lo : 0;
+        return __reduce_max_sync(0xffffffffu, n);
+    }
+    __device__ int event_of(int it, int) const { return lo + it < hi ? lo + it : -1; }
+    __device__ void raw(int, int, uint64_t w[12]) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) w[j] = g.next();
+    }
+    __device__ static double uniform(uint64_t w) { return to_uniform_xo(w); }
+};
+
+template <> struct WarpRng<float, RNG_XOSHIRO> {
+    Xoshiro128Lane g;
+    int lo, hi;
+    __device__ void init(const SimArgs& a, RanfWarpSmem*, uint32_t*, uint64_t batch, int n_ev, int warp, int lane) {
+        lo = warp * kWarpEvents + lane * kLaneEvents;
+        hi = min(min(n_ev, (warp + 1) * kWarpEvents), lo + kLaneEvents);
+        const uint64_t* st = a.xo_batch_states + 4 * (batch - a.first_batch);
+        g.s0 = (uint32_t)st[0]; g.s1 = (uint32_t)st[1]; g.s2 = (uint32_t)st[2]; g.s3 = (uint32_t)st[3];
+        const bool any = __any_sync(0xffffffffu, lo < hi);
+        if (any && (warp | lane)) g.apply(a.xo_thread_polys + 4 * (warp * 32 + lane));
+    }
+    __device__ int iterations() const {
+        const int n = lo < hi ? hi - lo : 0;
+        return __reduce_max_sync(0xffffffffu, n);
+    }
+    __device__ int event_of(int it, int) const { return lo + it < hi ? lo + it : -1; }
+    __device__ void raw(int, int, uint32_t w[12]) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) w[j] = g.next();
+    }
+    __device__ static float uniform(uint32_t w) { return to_uniform_xo(w); }
+};
+
+template <class F> struct LaneAcc {
+    F spm2[5], vars[5], sigma, variance;
+    uint32_t selected;
+    __device__ void clear() {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) spm2[k] = vars[k] = 0;
+        sigma = variance = 0;
+        selected = 0;
+    }
+    // resacc.rs:121-129
+    __device__ __forceinline__ void integrate(const F m[5], const F sc[5]) {
+        selected += 1;
+        F w = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            spm2[k] += m[k];
+            vars[k] += m[k] * m[k];
+            w += m[k] * sc[k];
+        }
+        sigma += w;
+        variance += w * w;
+    }
+};
+
+template <class F> __device__ __forceinline__ F shfl_xor_t(F v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+struct BlockSmem {
+    RanfWarpSmem ranf[kWarps];
+    uint32_t seed_y[kRanfLag + 1];
+    uint32_t seed_tmp[kRanfLag + 1];
+    double red[kWarps][12];
+    uint32_t red_n[kWarps];
+};
+
+// Shared prologue: batch geometry + per-warp random source.
+template <class F, int RNG>
+__device__ __forceinline__ void setup_batch(const SimArgs& a, BlockSmem& sm, WarpRng<F, RNG>& rng, uint64_t& batch,
+                                            int& n_ev) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t b = blockIdx.x;
+    batch = a.first_batch + b;
+    n_ev = (b + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
+    if (RNG == RNG_RANF && a.jump_seeding) {
+        // rng.jump() = reseed with seed + 123456 per batch (ranf.rs:136-140), i32 wrapping
+        if (warp == 0)
+            ranf_seed_warp(sm.seed_y, sm.seed_tmp, (int32_t)((uint32_t)a.ranf_seed + 123456u * (uint32_t)batch), lane);
+        __syncthreads();
+    }
+    rng.init(a, &sm.ranf[warp], sm.seed_y, batch, n_ev, warp, lane);
+}
+
+template <class F, int RNG, bool SORT, bool LITERAL>
+__global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
+    __shared__ BlockSmem sm;
+    using Word = typename RawWord<F, RNG>::type;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpRng<F, RNG> rng;
+    uint64_t batch;
+    int n_ev;
+    setup_batch<F, RNG>(a, sm, rng, batch, n_ev);
+
+    LaneAcc<F> acc;
+    acc.clear();
+    const int n_it = rng.iterations();
+    for (int it = 0; it < n_it; ++it) {
+        Word w[12];
+        rng.raw(it, lane, w);
+        if (rng.event_of(it, lane) < 0) continue;
+        F u[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
+        F p[3][4];
+        gen_event<F, SORT, LITERAL>(u, P.e_total, p);
+        if (keep_event<F, SORT>(p, P)) {
+            F m[5];
+            if (LITERAL) me_literal<F>(p, P, m);
+            else me_fast<F>(p, P, m);
+            acc.integrate(m, P.sigma_contribs);
+        }
+    }
+
+    // resacc.rs:133-139 within the batch: warp shuffle tree, then warps in fixed order
+    F v[12];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        v[k] = acc.spm2[k];
+        v[5 + k] = acc.vars[k];
+    }
+    v[10] = acc.sigma;
+    v[11] = acc.variance;
+    uint32_t n = acc.selected;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v[k] += shfl_xor_t(v[k], off);
+        n += __shfl_xor_sync(0xffffffffu, n, off);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) sm.red[warp][k] = (double)v[k];
+        sm.red_n[warp] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x < 13) {
+        tp3_acc* o = a.out + blockIdx.x;
+        if (threadIdx.x == 12) {
+            uint64_t t = 0;
+            for (int w2 = 0; w2 < kWarps; ++w2) t += sm.red_n[w2];
+            o->selected_events = t;
+        } else {
+            F t = (F)sm.red[0][threadIdx.x];
+            for (int w2 = 1; w2 < kWarps; ++w2) t += (F)sm.red[w2][threadIdx.x];
+            double* dst = threadIdx.x < 5 ? &o->spm2[threadIdx.x]
+                          : threadIdx.x < 10 ? &o->vars[threadIdx.x - 5]
+                          : threadIdx.x == 10 ? &o->sigma : &o->variance;
+            *dst = (double)t;
+        }
+    }
+}
+
+// Parity hook: same streams, same partition, per-event outputs instead of sums.
+template <class F, int RNG, bool SORT, bool LITERAL>
+__global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const PhysParams<F> P, const DumpArgs d) {
+    __shared__ BlockSmem sm;
+    using Word = typename RawWord<F, RNG>::type;
+    const int lane = threadIdx.x & 31;
+    WarpRng<F, RNG> rng;
+    uint64_t batch;
+    int n_ev;
+    setup_batch<F, RNG>(a, sm, rng, batch, n_ev);
+    const int n_it = rng.iterations();
+    for (int it = 0; it < n_it; ++it) {
+        Word w[12];
+        rng.raw(it, lane, w);
+        const int e = rng.event_of(it, lane);
+        if (e < 0 || e >= (int)d.n_events) continue;
+        if (d.words)
+            for (int j = 0; j < 12; ++j) d.words[(size_t)e * 12 + j] = (uint64_t)w[j];
+        if (!d.momenta) continue;
+        F u[12];
+        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
+        F p[3][4];
+        gen_event<F, SORT, LITERAL>(u, P.e_total, p);
+        const bool k = keep_event<F, SORT>(p, P);
+        F m[5] = {0, 0, 0, 0, 0};
+        if (k) {
+            if (LITERAL) me_literal<F>(p, P, m);
+            else me_fast<F>(p, P, m);
+        }
+        for (int q = 0; q < 3; ++q)
+            for (int c = 0; c < 4; ++c) d.momenta[((size_t)e * 3 + q) * 4 + c] = (double)p[q][c];
+        d.kept[e] = k;
+        for (int c = 0; c < 5; ++c) d.m2[(size_t)e * 5 + c] = (double)m[c];
+    }
+}
+
+// xoshiro seeding kernel: state at the start of each batch of the launch.
+//   sequential stream: base advanced by 120000 * batch outputs; faster-threading: batch jump()s.
+// digit_polys[k][d] = G^(d * 256^k), G = x^120000 or the jump() polynomial; words per poly = 4.
+template <class Lane>
+__global__ void xoshiro_seed_kernel(uint64_t first_batch, uint64_t n_batches, const uint64_t* __restrict__ digit_polys,
+                                    int n_digits, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3, uint64_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_batches) return;
+    const uint64_t batch = first_batch + i;
+    Lane g;
+    g.s0 = (decltype(g.s0))b0; g.s1 = (decltype(g.s0))b1; g.s2 = (decltype(g.s0))b2; g.s3 = (decltype(g.s0))b3;
+    for (int k = 0; k < n_digits; ++k) {
+        const unsigned dgt = (unsigned)((batch >> (8 * k)) & 0xffu);
+        if (dgt) g.apply(digit_polys + ((size_t)k * 256 + dgt) * 4);
+    }
+    out[4 * i + 0] = g.s0; out[4 * i + 1] = g.s1; out[4 * i + 2] = g.s2; out[4 * i + 3] = g.s3;
+}
+
+// ResultsAccumulator::merge (resacc.rs:133-139) as a left fold in batch order: lane k owns field k.
+template <class F> __global__ void merge_kernel(const tp3_acc* __restrict__ in, uint64_t n, tp3_acc* out) {
+    const int k = threadIdx.x;
+    if (k > 12) return;
+    if (k == 12) {
+        uint64_t t = 0;
+        for (uint64_t b = 0; b < n; ++b) t += in[b].selected_events;
+        out->selected_events = t;
+        return;
+    }
+    const size_t off = 1 + k;  // doubles after the u64
+    const double* base = reinterpret_cast<const double*>(in);
+    F t = (F)base[off];
+    for (uint64_t b = 1; b < n; ++b) t += (F)base[b * 13 + off];
+    reinterpret_cast<double*>(out)[off] = (double)t;
+}
+
+// Peak probes: 8 independent FMA chains per thread.
+template <class F> __global__ void fma_probe_kernel(F* out, int iters, F a, F b) {
+    F x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma_t(x0, a, b); x1 = fma_t(x1, a, b); x2 = fma_t(x2, a, b); x3 = fma_t(x3, a, b);
+            x4 = fma_t(x4, a, b); x5 = fma_t(x5, a, b); x6 = fma_t(x6, a, b); x7 = fma_t(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace tp3

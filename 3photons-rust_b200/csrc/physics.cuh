@@ -1,0 +1,309 @@
+// Per-event physics of e+e- -> 3 photons, register resident, templated on the run's Float.
+//
+//   gen_event      RAMBO for 3 massless photons       src/evgen.rs:89-132,174-207
+//   keep_event     the four cuts as a predicate        src/evcut.rs:42-96
+//   me_literal     spinor products + helicity amps     src/spinor.rs:31-162, src/matelems.rs:53-86
+//   me_fast        the same five helicity sums after algebraic reduction:
+//                  |s_ij|^2 = 2 p_i.p_j turns the A and B+ sums into real dot products, the mixed
+//                  term needs only s_jk^2 and u_k = s_0k s_1k, and no square root is left
+//                  (one reciprocal per photon + one for the common denominator).
+#pragma once
+
+#include <cstdint>
+
+namespace tp3 {
+
+template <class F> struct Num;
+template <> struct Num<double> {
+    static constexpr double MIN_POSITIVE = 2.2250738585072014e-308;
+    static constexpr double TWO_PI = 6.283185307179586476925286766559;
+    static constexpr double RAC8 = 2.8284271247461900976033774484194;
+};
+template <> struct Num<float> {
+    static constexpr float MIN_POSITIVE = 1.17549435e-38f;
+    static constexpr float TWO_PI = 2.0f * 3.14159265358979323846f;
+    static constexpr float RAC8 = 2.0f * 1.41421356237309504880f;
+};
+
+__device__ __forceinline__ void sincospi_t(double x, double* s, double* c) { sincospi(x, s, c); }
+__device__ __forceinline__ void sincospi_t(float x, float* s, float* c) { sincospif(x, s, c); }
+__device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ double log_t(double x) { return log(x); }
+__device__ __forceinline__ float log_t(float x) { return logf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
+__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double abs_t(double x) { return fabs(x); }
+__device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
+
+// Reciprocal without the IEEE-division slow path: MUFU seed + 2 Newton steps (operands here are
+// always finite, normal and far from overflow). ~1 ulp.
+__device__ __forceinline__ double rcp_t(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ float rcp_t(float x) { return __frcp_rn(x); }
+
+// Kernel-side view of tp3_params in the run's Float.
+template <class F> struct PhysParams {
+    F e_total, acut, bcut, e_min, sincut;
+    F g_a, g_beta_p, g_beta_m;
+    F sigma_contribs[5];
+};
+
+// ------------------------------------------------------------------ event generation
+// u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187).
+// p[k] = (X, Y, Z, E) of photon k, optionally sorted by decreasing E (evgen.rs:109-118).
+template <class F, bool SORT, bool LITERAL>
+__device__ __forceinline__ void gen_event(const F u[12], F e_total, F p[3][4]) {
+    F q[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const F c = (F)2 * u[4 * k] - (F)1;
+        F sphi, cphi;
+        if (LITERAL)
+            sincos_t(Num<F>::TWO_PI * u[4 * k + 1], &sphi, &cphi);
+        else
+            sincospi_t((F)2 * u[4 * k + 1], &sphi, &cphi);
+        const F e = u[4 * k + 2] * u[4 * k + 3];
+        const F st = sqrt_t((F)1 - c * c);
+        const F en = -log_t(e + Num<F>::MIN_POSITIVE);
+        q[k][0] = en * (st * sphi);
+        q[k][1] = en * (st * cphi);
+        q[k][2] = en * c;
+        q[k][3] = en;
+    }
+    F r[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r[c] = (q[0][c] + q[1][c]) + q[2][c];
+    const F m2 = r[3] * r[3] - ((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
+    F alpha, m, beta;
+    if (LITERAL) {
+        alpha = e_total / m2;
+        m = sqrt_t(m2);
+        beta = (F)1 / (m + r[3]);
+    } else {
+        const F rs = rsqrt_t(m2);
+        m = m2 * rs;
+        alpha = e_total * (rs * rs);
+        beta = rcp_t(m + r[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const F rq = (q[k][0] * r[0] + q[k][1] * r[1]) + q[k][2] * r[2];
+        p[k][3] = alpha * (r[3] * q[k][3] - rq);
+        const F b = beta * rq - q[k][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[k][c] = alpha * (m * q[k][c] + b * r[c]);
+    }
+    if (SORT) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = a + 1; b < 3; ++b) {
+                const bool sw = p[b][3] > p[a][3];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const F x = p[a][c], y = p[b][c];
+                    p[a][c] = sw ? y : x;
+                    p[b][c] = sw ? x : y;
+                }
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------ cuts
+// The beam is along X: p(e-) = (-E/2, 0, 0, E/2) (evgen.rs:66-69), so p_gamma . p_e = -X E/2 and
+// the common factor E/2 drops out of evcut.rs:52-62 and :80-92.
+template <class F, bool SORT>
+__device__ __forceinline__ bool keep_event(const F p[3][4], const PhysParams<F>& P) {
+    F emin;
+    if (SORT) emin = p[2][3];
+    else emin = fmin(p[0][3], fmin(p[1][3], p[2][3]));
+    bool ok = !(emin < P.e_min);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ok = ok && !(abs_t(p[k][0]) > P.acut * p[k][3]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 3; ++b) {
+            const F num = (p[a][0] * p[b][0] + p[a][1] * p[b][1]) + p[a][2] * p[b][2];
+            ok = ok && !(num > P.bcut * (p[a][3] * p[b][3]));
+        }
+    if (P.sincut > (F)0) {  // |n_x| < sincut |n|  (uniform branch; the default sincut is 0)
+        const F nx = p[0][1] * p[1][2] - p[0][2] * p[1][1];
+        const F ny = p[0][2] * p[1][0] - p[0][0] * p[1][2];
+        const F nz = p[0][0] * p[1][1] - p[0][1] * p[1][0];
+        const F nn = sqrt_t((nx * nx + ny * ny) + nz * nz);
+        ok = ok && !(abs_t(nx) < P.sincut * nn);
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------ matrix elements
+template <class F> struct Cplx {
+    F re, im;
+};
+template <class F> __device__ __forceinline__ Cplx<F> cmul(Cplx<F> a, Cplx<F> b) {
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+template <class F> __device__ __forceinline__ Cplx<F> csqr(Cplx<F> a) { return cmul(a, a); }
+template <class F> __device__ __forceinline__ Cplx<F> cadd(Cplx<F> a, Cplx<F> b) { return {a.re + b.re, a.im + b.im}; }
+template <class F> __device__ __forceinline__ Cplx<F> csub(Cplx<F> a, Cplx<F> b) { return {a.re - b.re, a.im - b.im}; }
+template <class F> __device__ __forceinline__ Cplx<F> cscale(Cplx<F> a, F s) { return {a.re * s, a.im * s}; }
+template <class F> __device__ __forceinline__ Cplx<F> cdiv(Cplx<F> a, Cplx<F> b) {  // num-complex 0.4.4
+    const F n = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / n, (a.im * b.re - a.re * b.im) / n};
+}
+template <class F> __device__ __forceinline__ F cnorm(Cplx<F> a) { return a.re * a.re + a.im * a.im; }
+
+// Operation-for-operation transcription (spinor.rs:31-162, matelems.rs:53-86). m[5] = helicity sums.
+template <class F> __device__ void me_literal(const F p[3][4], const PhysParams<F>& P, F m[5]) {
+    F ev[5][4];
+    const F half = P.e_total / (F)2;
+    ev[0][0] = -half; ev[0][1] = 0; ev[0][2] = 0; ev[0][3] = half;
+    ev[1][0] = half;  ev[1][1] = 0; ev[1][2] = 0; ev[1][3] = half;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ev[2 + k][c] = p[k][c];
+    F xx[5];
+    Cplx<F> fx[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        xx[i] = sqrt_t(ev[i][3] + ev[i][2]);
+        if (xx[i] > Num<F>::MIN_POSITIVE) fx[i] = {ev[i][0] / xx[i], ev[i][1] / xx[i]};
+        else fx[i] = {sqrt_t((F)2 * ev[i][3]), (F)0};
+    }
+    Cplx<F> s[5][5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s[i][j] = csub(cscale(fx[i], xx[j]), cscale(fx[j], xx[i]));
+    auto S = [&](int i, int j) { return s[i][j]; };
+    auto T = [&](int i, int j) { return Cplx<F>{-s[i][j].re, s[i][j].im}; };
+    const F mr8 = -Num<F>::RAC8;
+    auto a_ppm = [&](int k1, int k2, int k3) {
+        return cdiv(cmul(cscale(S(0, 1), mr8), csqr(S(0, k3))), cmul(cmul(cmul(S(0, k1), S(0, k2)), S(1, k1)), S(1, k2)));
+    };
+    auto a_pmm = [&](int k1, int k2, int k3) {
+        return cdiv(cmul(cscale(T(0, 1), mr8), csqr(T(1, k1))), cmul(cmul(cmul(T(1, k2), T(1, k3)), T(0, k2)), T(0, k3)));
+    };
+    auto bp_ppm = [&](int k1, int k2, int k3) { return cmul(cscale(T(0, 1), mr8), csqr(cmul(T(k1, k2), S(k3, 0)))); };
+    auto bp_pmm = [&](int k1, int k2, int k3) { return cmul(cscale(S(0, 1), mr8), csqr(cmul(T(k1, 1), S(k2, k3)))); };
+    auto bm_ppp = [&](int k1, int k2, int k3) {
+        return cmul(cscale(S(0, 1), mr8),
+                    cadd(cadd(csqr(cmul(T(k1, k2), T(k3, 1))), csqr(cmul(T(k1, k3), T(k2, 1)))), csqr(cmul(T(k2, k3), T(k1, 1)))));
+    };
+    auto bm_mmm = [&](int k1, int k2, int k3) {
+        return cmul(cscale(T(0, 1), mr8),
+                    cadd(cadd(csqr(cmul(S(k1, 0), S(k2, k3))), csqr(cmul(S(k2, 0), S(k1, k3)))), csqr(cmul(S(k3, 0), S(k1, k2)))));
+    };
+    const Cplx<F> zero = {0, 0};
+    Cplx<F> a[8] = {zero, a_pmm(4, 2, 3), a_pmm(3, 2, 4), a_ppm(3, 4, 2), a_pmm(2, 3, 4), a_ppm(2, 4, 3), a_ppm(2, 3, 4), zero};
+    Cplx<F> bp[8] = {zero, bp_pmm(4, 2, 3), bp_pmm(3, 2, 4), bp_ppm(3, 4, 2), bp_pmm(2, 3, 4), bp_ppm(2, 4, 3), bp_ppm(2, 3, 4), zero};
+    Cplx<F> bm[8] = {bm_mmm(2, 3, 4), zero, zero, zero, zero, zero, zero, bm_ppp(2, 3, 4)};
+    m[0] = m[1] = m[2] = m[3] = m[4] = 0;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        const Cplx<F> A = cscale(a[h], P.g_a), Bp = cscale(bp[h], P.g_beta_p), Bm = cscale(bm[h], P.g_beta_m);
+        const Cplx<F> mix = cmul(cscale(A, (F)2), Cplx<F>{Bp.re, -Bp.im});
+        m[0] += cnorm(A);
+        m[1] += cnorm(Bp);
+        m[2] += cnorm(Bm);
+        m[3] += mix.re;
+        m[4] += mix.im;
+    }
+}
+
+// Algebraically reduced form.  With e = e_total, h^2 = e/2 and, per photon k,
+//   A_k = E_k + Z_k,  c_k = X_k + i Y_k,  g_k = c_k^2 / A_k  (= fx_k^2),
+//   s_0k^2 = h^2 (A_k + 2 c_k + g_k),  s_1k^2 = h^2 (A_k - 2 c_k + g_k),  u_k = s_0k s_1k = -h^2 (A_k - g_k),
+//   P_k = |s_0k|^2 = e (E_k + X_k),  Q_k = |s_1k|^2 = e (E_k - X_k),
+// per pair  s_ij^2 = g_i A_j - 2 c_i c_j + g_j A_i,  R_ij = |s_ij|^2 = 2 (E_i E_j - p_i.p_j),
+// and D = prod_k P_k Q_k = |u_0 u_1 u_2|^2, the helicity sums of matelems.rs:72-86 are
+//   m0 = g_a^2  8 e^2 / D * sum_k P_k Q_k (P_k^2 + Q_k^2)
+//   m1 = g_b+^2 8 e^2     * sum_k R_ij^2 (P_k^2 + Q_k^2)
+//   m2 = g_b-^2 8 e^2     * ( |sum_k s_0k^2 s_ij^2|^2 + |sum_k s_1k^2 s_ij^2|^2 )
+//   m3 + i m4 = -16 e^2 g_a g_b+ * sum_k ( P_k^2 W_k + Q_k^2 conj W_k ),  W_k = s_ij^2 u_k conj(U) / D, U = u_0 u_1 u_2
+// (ij = the two photons other than k).  The common powers of h^2 are pulled out of the sums.
+template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], const PhysParams<F>& P, F m[5]) {
+    const F e = P.e_total;
+    F A[3], Ep[3], Em[3];       // A_k, E_k + X_k, E_k - X_k
+    Cplx<F> g[3], sp[3], sm[3], ub[3];  // g_k, (A+2c+g), (A-2c+g), (A-g)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const F X = p[k][0], Y = p[k][1], Z = p[k][2], E = p[k][3];
+        A[k] = E + Z;
+        const F iA = rcp_t(A[k]);
+        g[k].re = (X * X - Y * Y) * iA;
+        g[k].im = ((X + X) * Y) * iA;
+        Ep[k] = E + X;
+        Em[k] = E - X;
+        const F t = A[k] + g[k].re;
+        sp[k] = {t + (X + X), g[k].im + (Y + Y)};
+        sm[k] = {t - (X + X), g[k].im - (Y + Y)};
+        ub[k] = {A[k] - g[k].re, -g[k].im};
+    }
+    // pairs, indexed by the photon k they exclude: (i,j) = (1,2), (0,2), (0,1)
+    Cplx<F> s2[3];
+    F R[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = (k == 0) ? 1 : 0, j = (k == 2) ? 1 : 2;
+        const Cplx<F> cc = cmul(Cplx<F>{p[i][0], p[i][1]}, Cplx<F>{p[j][0], p[j][1]});
+        s2[k].re = g[i].re * A[j] + g[j].re * A[i] - (cc.re + cc.re);
+        s2[k].im = g[i].im * A[j] + g[j].im * A[i] - (cc.im + cc.im);
+        const F dot = (p[i][0] * p[j][0] + p[i][1] * p[j][1]) + p[i][2] * p[j][2];
+        R[k] = (F)2 * (p[i][3] * p[j][3] - dot);
+    }
+    // T_k = (E+X)(E-X), PQ2_k = (E+X)^2 + (E-X)^2, DPQ_k = (E+X)^2 - (E-X)^2   (units of e^2 pulled out)
+    F T[3], S2[3], D2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T[k] = Ep[k] * Em[k];
+        const F a = Ep[k] * Ep[k], b = Em[k] * Em[k];
+        S2[k] = a + b;
+        D2[k] = a - b;
+    }
+    const F Dn = (T[0] * T[1]) * T[2];  // D = e^6 * Dn
+    const F iDn = rcp_t(Dn);
+    const F e2 = e * e;
+    // m0 = g_a^2 * 8 e^2 * e^4 sum(T S2) / (e^6 Dn)
+    m[0] = (P.g_a * P.g_a) * (F)8 * ((T[0] * S2[0] + T[1] * S2[1] + T[2] * S2[2]) * iDn);
+    // m1 = g_b+^2 * 8 e^2 * e^2 sum(R^2 S2)
+    m[1] = (P.g_beta_p * P.g_beta_p) * ((F)8 * e2 * e2) * (R[0] * R[0] * S2[0] + R[1] * R[1] * S2[1] + R[2] * R[2] * S2[2]);
+    // m2: s_0k^2 = (e/2) sp_k, s_1k^2 = (e/2) sm_k
+    Cplx<F> bm0 = cmul(sp[0], s2[0]), bm1 = cmul(sm[0], s2[0]);
+#pragma unroll
+    for (int k = 1; k < 3; ++k) {
+        bm0 = cadd(bm0, cmul(sp[k], s2[k]));
+        bm1 = cadd(bm1, cmul(sm[k], s2[k]));
+    }
+    m[2] = (P.g_beta_m * P.g_beta_m) * ((F)2 * e2 * e2) * (cnorm(bm0) + cnorm(bm1));
+    // mixed: u_k = -(e/2) ub_k, U = -(e/2)^3 Ub, W_k = s2_k u_k conj(U) / D = s2_k ub_k conj(Ub) (e/2)^4 / (e^6 Dn)
+    const Cplx<F> Ub = cmul(cmul(ub[0], ub[1]), ub[2]);
+    const Cplx<F> Uc = {Ub.re, -Ub.im};
+    F re = 0, im = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const Cplx<F> w = cmul(cmul(s2[k], ub[k]), Uc);
+        re += S2[k] * w.re;
+        im += D2[k] * w.im;
+    }
+    // P_k^2 = e^2 (E+X)^2: total factor -16 e^2 g_a g_b+ * e^2 * (e/2)^4 / e^6 = -g_a g_b+ e^2
+    const F cm = -(P.g_a * P.g_beta_p) * e2 * iDn;
+    m[3] = cm * re;
+    m[4] = cm * im;
+}
+
+}  // namespace tp3

@@ -1,0 +1,170 @@
+/* include/tp3.h — C ABI of the B200-native 3photons hot path (libtp3.so).
+ *
+ * The reference (HadrienG2/3photons-rust) has no FFI: its narrowest seam is the
+ * kernel closure handed to the scheduler,
+ *     scheduling::run_simulation(num_events, simulate_events)      src/scheduling/mod.rs:31-34
+ *     simulate_events = |num_events, &mut rng| -> ResultsAccumulator  src/main.rs:103-128
+ * This header is what a Rust `-sys` crate would bind in place of that closure
+ * (see INTEGRATION.md for the extern "C" block).  Plain pointers and sizes only;
+ * no C++/torch types; every entry point returns 0 on success or a TP3_E_* code and
+ * never throws or aborts across the boundary.  A context is not re-entrant: one
+ * host thread drives it.
+ *
+ * There is NO CPU fallback: every compute entry point fails with TP3_E_CUDA /
+ * TP3_E_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef TP3_H
+#define TP3_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TP3_ABI_VERSION 1
+
+/* Size of an event batch — src/scheduling/mod.rs:21 (EVENT_BATCH_SIZE) */
+#define TP3_EVENT_BATCH_SIZE 10000u
+
+/* Feature flags: the reference's cargo features (Cargo.toml:9-21), as run-time flags */
+#define TP3_F32               (1u << 0) /* numeric.rs:6-13        single precision           */
+#define TP3_FASTER_EVGEN      (1u << 1) /* evgen.rs:143-173       unit-disc rejection evgen   */
+#define TP3_FASTER_THREADING  (1u << 2) /* multi_threading.rs:66-69  per-batch rng.jump()     */
+#define TP3_MULTI_THREADING   (1u << 3) /* scheduling/mod.rs:4-7  (host scheduling only)      */
+#define TP3_NO_PHOTON_SORTING (1u << 4) /* evgen.rs:109, event.rs:96                          */
+#define TP3_STANDARD_RANDOM   (1u << 5) /* random/standard.rs     xoshiro256+ / xoshiro128+   */
+
+/* Kernel variants (tp3_params.kernel) */
+#define TP3_KERNEL_FAST    0u /* algebraically reduced amplitudes, FMA, survivor compaction */
+#define TP3_KERNEL_LITERAL 1u /* operation-for-operation transcription of spinor.rs/matelems.rs */
+
+/* Error codes */
+#define TP3_OK            0
+#define TP3_E_INVALID     1 /* bad argument / unsupported combination */
+#define TP3_E_NO_DEVICE   2 /* no usable sm_100 CUDA device */
+#define TP3_E_CUDA        3 /* CUDA runtime error, see tp3_last_error() */
+#define TP3_E_CONFIG      4 /* `valeurs` parse / validation error (config.rs:57-128) */
+#define TP3_E_IO          5
+
+/* Everything the per-event kernel reads.  Replaces the closure's captured state
+ * (&cfg, &couplings, &evgen; main.rs:103-115).  All constants are computed by the
+ * host in the run's Float precision and widened exactly to double. */
+typedef struct tp3_params {
+    uint64_t num_events_total;   /* cfg.num_events (config.rs:10); only for bookkeeping */
+    double   e_total;            /* config.rs:13                                        */
+    double   acut, bcut, e_min, sincut; /* EventCut, evcut.rs:11-23                     */
+    double   g_a, g_beta_p, g_beta_m;   /* Couplings, coupling.rs:10-19                 */
+    double   sigma_contribs[5];  /* ResultsAccumulator::new, resacc.rs:94-100           */
+    uint32_t flags;              /* TP3_F32 | TP3_FASTER_EVGEN | ...                    */
+    uint32_t kernel;             /* TP3_KERNEL_*                                        */
+} tp3_params;
+
+/* One ResultsAccumulator (resacc.rs:16-34): 13 scalars, 104 bytes.
+ * Under TP3_F32 the device accumulates in f32 and widens exactly. */
+typedef struct tp3_acc {
+    uint64_t selected_events;
+    double   spm2[5];
+    double   vars[5];
+    double   sigma;
+    double   variance;
+} tp3_acc;
+
+typedef struct tp3_ctx tp3_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+int  tp3_abi_version(void);
+/* n_dev devices (dev_ids may be NULL = 0..n_dev-1) driven from this one host thread. */
+int  tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx** out);
+void tp3_destroy(tp3_ctx* ctx);
+const char* tp3_last_error(const tp3_ctx* ctx); /* ctx may be NULL: last create error */
+/* Launch on a caller-owned CUDA stream (cudaStream_t cast to void*) of device slot i. */
+int  tp3_set_stream(tp3_ctx* ctx, int dev_slot, void* cuda_stream);
+
+/* ---- the hot path: replaces simulate_events over a RANGE of batches ---------------- */
+/* Simulates batches [first_batch, first_batch+n_batches) of the run; every batch has
+ * TP3_EVENT_BATCH_SIZE events except the last of the range, which has last_batch_len
+ * (1..10000; pass 10000 for a full one).  Batch b's random stream is positioned exactly
+ * where the sequential reference has it (sequential.rs:24-36), or after b jump()s under
+ * TP3_FASTER_THREADING (multi_threading.rs:66-69).  Writes one accumulator per batch to
+ * the caller-owned HOST array (device->host copy included).  With several devices the
+ * range is split into contiguous sub-ranges, one per device. */
+int  tp3_simulate_batches(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
+                          uint32_t last_batch_len, tp3_acc* out_per_batch);
+/* Same launch, but results stay in device memory (asynchronous; for HBM-resident timing). */
+int  tp3_simulate_batches_device(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
+                                 uint32_t last_batch_len);
+/* Copy the accumulators of the last *_device launch to the host and synchronise. */
+int  tp3_fetch(tp3_ctx* ctx, tp3_acc* out_per_batch, uint64_t n_batches);
+/* Same range, but the per-batch accumulators are left-folded in batch order ON DEVICE
+ * (ResultsAccumulator::merge, resacc.rs:133-139) and only the merged one comes back. */
+int  tp3_simulate_merged(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
+                         uint32_t last_batch_len, tp3_acc* out_merged);
+int  tp3_synchronize(tp3_ctx* ctx);
+/* Number of kernel launches issued by this context so far. */
+uint64_t tp3_launch_count(const tp3_ctx* ctx);
+
+/* ---- parity hooks ------------------------------------------------------------------ */
+/* Raw integer random stream of batch `batch`, in the order the reference consumes it,
+ * produced by the SAME per-warp/per-lane stream code the simulation kernel uses.
+ * RANF words are the i32 values (ranf.rs:95-101) zero-extended; xoshiro words are the
+ * raw u64 (f64) / u32 (f32) outputs.  n_words <= 12 * TP3_EVENT_BATCH_SIZE. */
+int  tp3_rng_dump(tp3_ctx* ctx, uint64_t batch, uint32_t n_words, uint64_t* out_words);
+/* Per-event outputs of the first n events of batch `batch`: sorted photon momenta
+ * [n][3][4] (X,Y,Z,E), cut decision [n], helicity-summed matrix elements [n][5]. */
+int  tp3_events_dump(tp3_ctx* ctx, uint64_t batch, uint32_t n, double* momenta, int32_t* kept,
+                     double* m2_sums);
+
+/* ---- measurement ------------------------------------------------------------------- */
+/* Sustained FMA throughput of the FP64 (which=0) or FP32 (which=1) pipe, TFLOP/s. */
+int  tp3_peak_probe(tp3_ctx* ctx, int which, double* tflops);
+
+/* ---- host side of the reference surface (config.rs, coupling.rs, resacc.rs, resfin.rs,
+ *      output.rs), so a caller can go valeurs -> res.data without the Rust crate ----- */
+typedef struct tp3_config {        /* Configuration, config.rs:8-53 (values widened to double) */
+    uint64_t num_events;
+    double   e_total, beam_photons_cut, photon_photon_cut, e_min, beam_photon_plane_cut;
+    double   alpha, alpha_z, gev2_to_picobarn, m_z0, g_z0, sin2_weinberg, branching_ep_em;
+    double   beta_plus, beta_minus;
+    int32_t  num_bins;
+    int32_t  impr, plot;
+} tp3_config;
+
+typedef struct tp3_final {         /* FinalResults, resfin.rs:26-62 */
+    uint64_t selected_events;
+    double   spm2[2][5], vars[2][5];
+    double   sigma, prec, variance, beta_min, ss_p, inc_ss_p, ss_m, inc_ss_m;
+} tp3_final;
+
+/* Parse the text of a `valeurs` file (config.rs:57-128). err_buf receives the message. */
+int  tp3_config_parse(const char* valeurs_text, uint32_t flags, tp3_config* out, char* err_buf,
+                      size_t err_cap);
+/* Couplings::new + EventGenerator::new + ResultsAccumulator::new -> kernel parameters. */
+int  tp3_params_from_config(const tp3_config* cfg, uint32_t flags, uint32_t kernel, tp3_params* out);
+/* ResultsAccumulator::merge (resacc.rs:133-139), in the run's Float precision. */
+int  tp3_merge(tp3_acc* into, const tp3_acc* other, uint32_t flags);
+/* ResultsAccumulator::finalize (resacc.rs:142-223). */
+int  tp3_finalize(const tp3_config* cfg, uint32_t flags, const tp3_acc* merged, tp3_final* out);
+/* Text of res.data (output.rs:64-142) and of the stdout report (config.rs:131-155,
+ * evgen.rs:47, resfin.rs:66-194).  Return the number of bytes needed (excl. NUL). */
+size_t tp3_format_res_data(const tp3_config* cfg, uint32_t flags, const tp3_final* fin, char* buf,
+                           size_t cap);
+size_t tp3_format_stdout(const tp3_config* cfg, uint32_t flags, const tp3_final* fin, char* buf,
+                         size_t cap);
+/* The whole program (main.rs:75-145) on n_dev GPUs: reads valeurs_path, writes res.data,
+ * res.times and appends pil.mc in out_dir, returns the stdout text in stdout_buf. */
+int  tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint32_t kernel, int n_dev,
+             char* stdout_buf, size_t stdout_cap, double* elapsed_seconds);
+
+/* Host mirror of the device RANF jump-ahead (no GPU needed): state of the generator's
+ * 55-word round `round` (0 = after seeding + warm-up), numbers[1..55] -> out[0..54]. */
+int  tp3_host_ranf_round(int32_t seed, uint64_t round, uint32_t* out55);
+/* Host mirror of the xoshiro jump-ahead: state after `n_steps` outputs from
+ * seed_from_u64(12345); f32 != 0 selects xoshiro128+ (4 x u32 widened). */
+int  tp3_host_xoshiro_state(int f32, uint64_t n_steps, uint64_t n_jumps, uint64_t* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TP3_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so). TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+
+F32, FASTER_EVGEN, FASTER_THREADING, MULTI_THREADING, NO_PHOTON_SORTING, STANDARD_RANDOM = 1, 2, 4, 8, 16, 32
+BITS = {"f32": F32, "faster-evgen": FASTER_EVGEN, "faster-threading": FASTER_THREADING,
+        "multi-threading": MULTI_THREADING, "no-photon-sorting": NO_PHOTON_SORTING, "standard-random": STANDARD_RANDOM}
+
+
+def mask(features):
+    if isinstance(features, int):
+        return features
+    m = 0
+    for f in (features.split(",") if isinstance(features, str) else features):
+        if f:
+            m |= BITS[f]
+    return m
+
+
+class Acc(C.Structure):
+    _fields_ = [("selected_events", C.c_uint64), ("spm2", C.c_double * 5), ("vars", C.c_double * 5),
+                ("sigma", C.c_double), ("variance", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.oracle_run.restype = C.c_int
+        L.oracle_run.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_uint64, C.POINTER(Acc), C.POINTER(C.c_uint64),
+                                 C.POINTER(Acc), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_double)]
+        L.oracle_rng_words.restype = C.c_int
+        L.oracle_rng_words.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.oracle_events.restype = C.c_int
+        L.oracle_events.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_double)]
+        L.oracle_constants.restype = C.c_int
+        L.oracle_constants.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+class Run:
+    def __init__(self, per_batch, merged, res_data, stdout, seconds):
+        self.per_batch, self.merged, self.res_data, self.stdout, self.seconds = per_batch, merged, res_data, stdout, seconds
+
+
+def run(valeurs_text, features="", threads=1, num_events=0, want_batches=True, want_text=True):
+    """Whole run through the oracle. num_events=0 keeps the file's value."""
+    m = mask(features)
+    cap = 0
+    per_batch = None
+    if want_batches:
+        n = num_events or int(valeurs_text.split()[0])
+        cap = n // 10000 + 2
+        per_batch = (Acc * cap)()
+    nb = C.c_uint64(cap)
+    merged = Acc()
+    rd = C.create_string_buffer(1 << 14) if want_text else None
+    so = C.create_string_buffer(1 << 14) if want_text else None
+    secs = C.c_double()
+    rc = lib().oracle_run(valeurs_text.encode(), m, threads, num_events, per_batch, C.byref(nb), C.byref(merged),
+                          rd, len(rd) if rd else 0, so, len(so) if so else 0, C.byref(secs))
+    if rc != 0:
+        raise RuntimeError("oracle_run failed: " + (so.value.decode() if so else ""))
+    batches = [per_batch[i] for i in range(nb.value)] if want_batches else None
+    return Run(batches, merged, rd.value.decode() if rd else None, so.value.decode() if so else None, secs.value)
+
+
+def rng_words(features, batch, n_words):
+    out = (C.c_uint64 * n_words)()
+    lib().oracle_rng_words(mask(features), batch, n_words, out)
+    return list(out)
+
+
+def events(valeurs_text, features, n):
+    mom = (C.c_double * (n * 12))()
+    kept = (C.c_int32 * n)()
+    m2 = (C.c_double * (n * 5))()
+    rc = lib().oracle_events(valeurs_text.encode(), mask(features), n, mom, kept, m2)
+    assert rc == 0
+    return list(mom), list(kept), list(m2)
+
+
+def constants(valeurs_text, features=""):
+    out = (C.c_double * 10)()
+    rc = lib().oracle_constants(valeurs_text.encode(), mask(features), out)
+    assert rc == 0
+    return list(out)

@@ -1,0 +1,144 @@
+"""CPU tests of the product's host side (no GPU, no compute): the C-ABI library loads and exports
+every symbol of include/tp3.h, `valeurs` parsing follows config.rs, the kernel constants match the
+oracle's, and finalize + res.data/stdout formatting reproduce the goldens when fed the oracle's
+merged sums (the GPU tests feed them the GPU's sums)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, golden
+from numdiff import compare
+
+
+def test_library_exports_every_declared_symbol(tp3):
+    header = open(os.path.join(ROOT, "include", "tp3.h")).read()
+    declared = set(re.findall(r"\b(tp3_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(tp3.ABI_SYMBOLS)
+    lib = tp3.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.tp3_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tp3):
+    assert C.sizeof(tp3.Acc) == 104  # 13 scalars (resacc.rs:19-34)
+    assert C.sizeof(tp3.Params) == 8 + 13 * 8 + 8
+    assert C.sizeof(tp3.Config) == 8 + 14 * 8 + 3 * 4 + 4
+    assert C.sizeof(tp3.Final) == 8 + 20 * 8 + 8 * 8
+
+
+def test_no_gpu_fails_loudly(tp3, valeurs_text):
+    """No CPU fallback: without a B200 the context cannot be created."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg = tp3.Configuration.parse(valeurs_text)
+    with pytest.raises(tp3.Tp3Error) as e:
+        tp3.Simulator(cfg)
+    assert e.value.code == tp3.E_NO_DEVICE
+
+
+def test_config_parse_default(tp3, valeurs_text):
+    cfg = tp3.Configuration.parse(valeurs_text)
+    r = cfg.raw
+    assert (r.num_events, r.e_total, r.beam_photons_cut, r.photon_photon_cut, r.e_min, r.beam_photon_plane_cut) == (
+        10_000_000, 91.187, 0.9, 0.9396, 4.559, 0.0)
+    assert (r.alpha, r.alpha_z, r.gev2_to_picobarn, r.m_z0, r.g_z0) == (7.297353079644818e-3, 7.8125e-3, 0.38937966e9, 91.187, 2.49)
+    assert (r.sin2_weinberg, r.branching_ep_em, r.beta_plus, r.beta_minus, r.num_bins, r.impr, r.plot) == (
+        0.2319, 0.03367, 1.0, 1.0, 200, 0, 0)
+
+
+def test_config_parse_f32_rounds_text_directly(tp3, valeurs_text):
+    import numpy as np
+    cfg = tp3.Configuration.parse(valeurs_text, "f32")
+    assert cfg.raw.alpha == float(np.float32("7.297353079644818e-3"))
+    assert cfg.raw.gev2_to_picobarn == float(np.float32("0.38937966e9"))
+
+
+@pytest.mark.parametrize("mutate,message", [
+    (lambda t: "\n".join(t.splitlines()[:10]), "missing configuration of g_z0"),
+    (lambda t: t.replace("10000000 ", "0 ", 1), "Please simulate at least one event"),
+    (lambda t: t.replace("91.187e0", "abc", 1), "could not parse configuration of e_total"),
+    (lambda t: re.sub(r"\.false\.(\s+'HBook)", r".true.\1", t), "Plotting is not supported"),
+    (lambda t: re.sub(r"\.false\.(\s+'Impression)", r".TRUE.\1", t), "Individual result printing is not supported"),
+    (lambda t: re.sub(r"\.false\.(\s+'Impression)", r"maybe\1", t), "could not parse configuration of impr"),
+])
+def test_config_errors(tp3, valeurs_text, mutate, message):
+    with pytest.raises(tp3.Tp3Error) as e:
+        tp3.Configuration.parse(mutate(valeurs_text))
+    assert e.value.code == tp3.E_CONFIG and message in str(e.value)
+
+
+def test_config_blank_lines_and_first_token_rule(tp3, valeurs_text):
+    """config.rs:69-71: only the first whitespace-delimited token of each non-blank line counts."""
+    lines = valeurs_text.splitlines()
+    shuffled = "\n\n   \n".join("   " + l for l in lines[:18]) + "\n\n"
+    a, b = tp3.Configuration.parse(valeurs_text).raw, tp3.Configuration.parse(shuffled).raw
+    assert bytes(a) == bytes(b)
+
+
+@pytest.mark.parametrize("features", ["", "f32"])
+def test_kernel_constants_match_oracle(tp3, oracle, valeurs_text, features):
+    p = tp3.Configuration.parse(valeurs_text, features).params()
+    c = oracle.constants(valeurs_text, features)
+    assert (p.g_a, p.g_beta_p, p.g_beta_m) == tuple(c[0:3])
+    assert list(p.sigma_contribs) == c[5:10]
+    assert p.num_events_total == 10_000_000
+
+
+@pytest.mark.parametrize("features,suffix,tol", [
+    ("", "", {}),
+    ("f32", "f32", dict(abs_=1.1e-8)),
+    ("standard-random", "standard-random", {}),
+    ("multi-threading,faster-threading", "multi-threading,faster-threading", {}),
+])
+def test_finalize_and_text_from_oracle_sums(tp3, oracle, valeurs_text, features, suffix, tol):
+    """Product finalize/formatters (host.cpp) on the oracle's per-batch sums == golden files."""
+    run = oracle.run(valeurs_text, features, threads=8, want_text=False)
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    accs = (tp3.Acc * len(run.per_batch))()
+    for i, b in enumerate(run.per_batch):
+        C.memmove(C.byref(accs[i]), C.byref(b), C.sizeof(tp3.Acc))
+    fin = tp3.finalize(cfg, tp3.fold(accs, cfg.flags))
+    assert fin.selected_events == run.merged.selected_events
+    assert compare(fin.res_data(), golden("res.data-features_" + suffix), **tol) == []
+    out_tol = dict(rel=1.9e-5) if "f32" in features else {}
+    assert compare(fin.stdout(), golden("stdout.log-features_" + suffix), **out_tol) == []
+
+
+def test_batch_layout_and_sharding(tp3):
+    assert tp3.batch_layout(10_000_000) == (1000, 10000)
+    assert tp3.batch_layout(10_001) == (2, 1)
+    assert tp3.batch_layout(1) == (1, 1)
+    for n, w in [(1000, 8), (7, 4), (1, 2), (10**6, 3)]:
+        parts = [tp3.shard_range(n, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+        for (lo, cnt), (lo2, _) in zip(parts, parts[1:]):
+            assert lo + cnt == lo2
+
+
+def test_host_ranf_jump_matches_oracle_stream(tp3, oracle):
+    """Round r of the seeded generator via polynomial jump-ahead == the oracle stepped there.
+    The reference hands out slots 55..1 of each round (ranf.rs:95-101)."""
+    words = oracle.rng_words("", 0, 55 * 40)
+    out = (C.c_uint32 * 55)()
+    for r in (0, 1, 2, 39):
+        assert tp3.lib().tp3_host_ranf_round(234612947, r, out) == 0
+        assert list(out)[::-1] == words[55 * r: 55 * (r + 1)]
+    # far jump: batch 999 starts at draw 119 880 000 = round 2 179 636, offset 20
+    assert tp3.lib().tp3_host_ranf_round(234612947, 119_880_000 // 55, out) == 0
+    off = 119_880_000 % 55
+    assert list(out)[::-1][off:off + 4] == oracle.rng_words("", 999, 4)
+
+
+@pytest.mark.parametrize("f32,features", [(0, "standard-random"), (1, "standard-random,f32")])
+def test_host_xoshiro_jump_matches_oracle_stream(tp3, oracle, f32, features):
+    st = (C.c_uint64 * 4)()
+    mask = (1 << 32) - 1 if f32 else (1 << 64) - 1
+    for batch in (0, 1, 7):
+        assert tp3.lib().tp3_host_xoshiro_state(f32, 120_000 * batch, 0, st) == 0
+        assert (st[0] + st[3]) & mask == oracle.rng_words(features, batch, 1)[0]
+        assert tp3.lib().tp3_host_xoshiro_state(f32, 0, batch, st) == 0
+        assert (st[0] + st[3]) & mask == oracle.rng_words(features + ",multi-threading,faster-threading", batch, 1)[0]

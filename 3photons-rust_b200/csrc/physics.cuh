@@ -240,15 +240,27 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
     const F e = P.e_total;
     F A[3], Ep[3], Em[3];       // A_k, E_k + X_k, E_k - X_k
     Cplx<F> g[3], sp[3], sm[3], ub[3];  // g_k, (A+2c+g), (A-2c+g), (A-g)
+    F cx[3], cy[3];                     // c_k = X_k + i Y_k
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const F X = p[k][0], Y = p[k][1], Z = p[k][2], E = p[k][3];
+        F X = p[k][0], Y = p[k][1];
+        const F Z = p[k][2], E = p[k][3];
+        Ep[k] = E + X;
+        Em[k] = E - X;
         A[k] = E + Z;
         const F iA = rcp_t(A[k]);
         g[k].re = (X * X - Y * Y) * iA;
         g[k].im = ((X + X) * Y) * iA;
-        Ep[k] = E + X;
-        Em[k] = E - X;
+        // photon along -Z (spinor.rs:42-46): xx = 0, fx = sqrt(2E)  =>  A = 0, c = 0, g = 2E.
+        // Reached in f32 (E + Z rounds to 0 about once per 1e7 events), never observed in f64.
+        if (!(A[k] > Num<F>::MIN_POSITIVE)) {
+            A[k] = 0;
+            g[k] = {E + E, (F)0};
+            X = 0;
+            Y = 0;
+        }
+        cx[k] = X;
+        cy[k] = Y;
         const F t = A[k] + g[k].re;
         sp[k] = {t + (X + X), g[k].im + (Y + Y)};
         sm[k] = {t - (X + X), g[k].im - (Y + Y)};
@@ -260,7 +272,7 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int i = (k == 0) ? 1 : 0, j = (k == 2) ? 1 : 2;
-        const Cplx<F> cc = cmul(Cplx<F>{p[i][0], p[i][1]}, Cplx<F>{p[j][0], p[j][1]});
+        const Cplx<F> cc = cmul(Cplx<F>{cx[i], cy[i]}, Cplx<F>{cx[j], cy[j]});
         s2[k].re = g[i].re * A[j] + g[j].re * A[i] - (cc.re + cc.re);
         s2[k].im = g[i].im * A[j] + g[j].im * A[i] - (cc.im + cc.im);
         const F dot = (p[i][0] * p[j][0] + p[i][1] * p[j][1]) + p[i][2] * p[j][2];

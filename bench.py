@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — events/s of the 3photons hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle restatement)
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): the default
+`valeurs` with num_events = 10^10, i.e. 10^6 batches of 10 000 events (scheduling/mod.rs:21),
+default features (f64, RANF, sorted photons).  The batch range is sharded contiguously over the
+ranks (strong scaling: total work fixed), no data-path collective; per-batch accumulators are
+gathered and left-folded in batch order on rank 0 for the end-to-end number.
+
+A "step" is one pass of the fused kernel over this rank's batch range.
+  value : whole-job events/s, device time (CUDA events on the launching stream, max over ranks),
+          everything the kernel reads (jump table, parameters) already resident in HBM.
+  e2e   : same metric through the C ABI call with HOST buffers (tp3_simulate_batches: launch +
+          device->host copy of the per-batch accumulators), plus gather + ordered fold + finalize.
+  roofline: the path is FP64-pipe bound (no tensor cores, ~0.01 B/event of HBM traffic), so the
+          roofline is achieved algorithmic FP64 TFLOP/s (833 flop per generated event, SURVEY.md
+          §8d) over the DFMA peak measured live on this GPU by tp3_peak_probe (MEASURED_PEAKS.json
+          carries no FP64 figure).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FLOP_PER_EVENT = 833.0  # 203 (generation + cuts) + 0.7082 * 890 (matrix elements)
+REFERENCE_FEATURES = "multi-threading"  # the reference's reproducible multi-threaded build
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--events", type=float, default=1e10, help="total events per step (all GPUs)")
+    ap.add_argument("--features", default="", help="cargo-style feature list, e.g. f32,standard-random")
+    ap.add_argument("--kernel", default="fast", choices=["fast", "literal"])
+    ap.add_argument("--cpu-sample-events", type=float, default=5e7)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def valeurs_text():
+    with open(os.path.join(ROOT, "tests", "golden", "valeurs")) as f:
+        return f.read()
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(n_events, threads):
+    """events/s of the CPU oracle run with the reference's `multi-threading` semantics (one task
+    per batch, scheduler thread pre-advances the RNG, ordered merge) on `threads` host threads."""
+    import oracle_lib  # CPU baseline leg: the only place bench.py executes oracle/
+    run = oracle_lib.run(valeurs_text(), REFERENCE_FEATURES, threads=threads, num_events=int(n_events),
+                         want_batches=False, want_text=False)
+    return n_events / run.seconds, run.seconds
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
+        power = max(float(r[2]) for r in rows if r[2].replace(".", "").isdigit())
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": power}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    if rank != 0:
+        return
+    threads = host_threads()
+    sample = args.cpu_sample_events
+    for _ in range(args.warmup):
+        cpu_reference_rate(min(sample, 2e6), threads)
+    t = 0.0
+    for _ in range(args.steps):
+        _, s = cpu_reference_rate(sample, threads)
+        t += s
+    rate = sample * args.steps / t
+    unit = "events/s"
+    desc = (f"{sample:.3g} events of the default valeurs per step (bounded sample of the 1e10-event workload), "
+            f"C++ restatement of the reference's `multi-threading` build (oracle/), {threads} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "events/sec", "value": rate, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "default valeurs shape, 1e10 events (configs[4]); CPU arm times a bounded sample",
+                   "features": REFERENCE_FEATURES},
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    pkg = entry.package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_events = int(args.events)
+    cfg = pkg.Configuration.parse(valeurs_text(), args.features).with_num_events(n_events)
+    kernel = pkg.KERNEL_FAST if args.kernel == "fast" else pkg.KERNEL_LITERAL
+    nb, last = pkg.batch_layout(n_events)
+    lo, cnt = pkg.shard_range(nb, world, rank)
+    my_last = last if lo + cnt == nb else pkg.EVENT_BATCH_SIZE
+    my_events = (cnt - 1) * pkg.EVENT_BATCH_SIZE + my_last if cnt else 0
+
+    sim = pkg.Simulator(cfg, kernel, devices=[local_rank])
+    stream = torch.cuda.current_stream()
+    sim.set_stream(stream.cuda_stream)
+    peak_tflops = sim.peak_probe(1 if "f32" in args.features else 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing ("value") --------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        sim.simulate_batches_device(lo, cnt, my_last)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sim.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sim.simulate_batches_device(lo, cnt, my_last)
+    ev1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(sum_over_ranks(sim.launch_count - launches0))
+    clocks = sampler.stop()
+    value = n_events * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ("e2e") -----------------------------
+    acc_bytes = ctypes.sizeof(pkg.Acc)
+
+    def e2e_step():
+        ctypes_out = sim.simulate_batches(lo, cnt, my_last)  # launch + D2H of 104 B per batch into host memory
+        if world > 1:
+            mine = torch.frombuffer(ctypes_out, dtype=torch.uint8).cuda()
+            sizes = [pkg.shard_range(nb, world, r)[1] * acc_bytes for r in range(world)]
+            parts = [torch.empty(s, dtype=torch.uint8, device="cuda") for s in sizes] if rank == 0 else None
+            dist.gather(mine, parts, dst=0)
+            if rank != 0:
+                return None
+            raw = torch.cat(parts).cpu().numpy().tobytes()
+            accs = (pkg.Acc * nb).from_buffer_copy(raw)
+        else:
+            accs = ctypes_out
+        total = merge_all(accs)
+        return pkg.finalize(cfg, total)
+
+    def merge_all(accs):
+        # left fold in batch order (sequential.rs:24-36), vectorised per field with the same order
+        import numpy as np
+        arr = np.frombuffer(accs, dtype=np.dtype([("n", "<u8"), ("f", "<f8", (12,))]))
+        total = pkg.Acc()
+        total.selected_events = int(arr["n"].sum())
+        f = np.add.accumulate(arr["f"], axis=0)[-1] if len(arr) else np.zeros(12)  # sequential left fold per field
+        for k in range(5):
+            total.spm2[k] = f[k]
+            total.vars[k] = f[5 + k]
+        total.sigma, total.variance = f[10], f[11]
+        return total
+
+    fin = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fin = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_events * args.steps / e2e_s
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        rate, secs = cpu_reference_rate(args.cpu_sample_events, threads)
+        cpu = {"value": rate, "unit": "events/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_sample_events:.3g} events of the default valeurs ({secs:.2f} s), C++ restatement of "
+                         f"the reference's `multi-threading` build, {threads} threads"}
+
+    if rank == 0:
+        achieved = value / world * FLOP_PER_EVENT / 1e12  # per GPU, to compare with a per-GPU peak
+        f32 = "f32" in args.features
+        line = {
+            "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if f32 else "f64", "data": "synthetic",
+            "config": {"workload": f"default valeurs, num_events={n_events:.3g} ({nb} batches of 10000; BASELINE configs[4], "
+                                   "the shape of configs[1]); contiguous batch ranges per GPU",
+                       "features": args.features or "default (f64, RANF, photon sorting)", "kernel": args.kernel,
+                       "l2": "not applicable: no input tensors; the kernel reads a 281 KB jump table and writes 104 B per batch"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": nb * acc_bytes,
+                    "note": "C-ABI call with host output array; parameters travel as kernel arguments"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp64" if not f32 else "fp32", "achieved": achieved, "peak": peak_tflops,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+                         "peak_source": "measured live: tp3_peak_probe (8 independent FMA chains per thread, all SMs)",
+                         "flop_per_event": FLOP_PER_EVENT},
+            "cpu_baseline": cpu,
+            "check": {"selected_events": fin.selected_events, "sigma_pb": fin.sigma},
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,7 @@ def lib() -> C.CDLL:
         "tp3_rng_dump": (C.c_int, [vp, u64, u32, P(u64)]),
         "tp3_events_dump": (C.c_int, [vp, u64, u32, P(dbl), P(i32), P(dbl)]),
         "tp3_peak_probe": (C.c_int, [vp, C.c_int, P(dbl)]),
+        "tp3_fastmath_probe": (C.c_int, [vp, C.c_int, u32, P(dbl), P(dbl)]),
         "tp3_config_parse": (C.c_int, [C.c_char_p, u32, P(Config), C.c_char_p, C.c_size_t]),
         "tp3_params_from_config": (C.c_int, [P(Config), u32, u32, P(Params)]),
         "tp3_merge": (C.c_int, [P(Acc), P(Acc), u32]),
@@ -192,7 +193,7 @@ def lib() -> C.CDLL:
 ABI_SYMBOLS = [
     "tp3_abi_version", "tp3_create", "tp3_destroy", "tp3_last_error", "tp3_set_stream", "tp3_simulate_batches",
     "tp3_simulate_batches_device", "tp3_fetch", "tp3_simulate_merged", "tp3_synchronize", "tp3_launch_count",
-    "tp3_rng_dump", "tp3_events_dump", "tp3_peak_probe", "tp3_config_parse", "tp3_params_from_config", "tp3_merge",
+    "tp3_rng_dump", "tp3_events_dump", "tp3_peak_probe", "tp3_fastmath_probe", "tp3_config_parse", "tp3_params_from_config", "tp3_merge",
     "tp3_finalize", "tp3_format_res_data", "tp3_format_stdout", "tp3_run", "tp3_host_ranf_round",
     "tp3_host_xoshiro_state",
 ]
@@ -376,6 +377,13 @@ class Simulator:
         m2 = (C.c_double * (n * 5))()
         self._check(lib().tp3_events_dump(self._h, batch, n, mom, kept, m2))
         return list(mom), list(kept), list(m2)
+
+    def fastmath_probe(self, which: int, xs):
+        n = len(xs)
+        a = (C.c_double * n)(*xs)
+        out = (C.c_double * n)()
+        self._check(lib().tp3_fastmath_probe(self._h, which, n, a, out))
+        return list(out)
 
     def peak_probe(self, which: int = 0) -> float:
         t = C.c_double()

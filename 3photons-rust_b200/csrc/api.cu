@@ -484,6 +484,30 @@ int tp3_peak_probe(tp3_ctx* c, int which, double* tflops) {
     return TP3_OK;
 }
 
+int tp3_fastmath_probe(tp3_ctx* c, int which, uint32_t n, const double* in, double* out) {
+    if (!c || !in || !out || n == 0 || which < 0 || which > 8) return TP3_E_INVALID;
+    DeviceSlot& s = c->devs[0];
+    TP3_CUDA(c, cudaSetDevice(s.dev));
+    double *d_in = nullptr, *d_out = nullptr;
+    TP3_CUDA(c, cudaMalloc(&d_in, (size_t)n * 8));
+    TP3_CUDA(c, cudaMalloc(&d_out, (size_t)n * 8));
+    cudaError_t e = cudaMemcpyAsync(d_in, in, (size_t)n * 8, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) {
+        fastmath_probe_kernel<<<148, 256, 0, s.stream>>>(which, n, d_in, d_out);
+        ++c->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        c->err = std::string("fastmath probe: ") + cudaGetErrorString(e);
+        return TP3_E_CUDA;
+    }
+    return TP3_OK;
+}
+
 int tp3_host_ranf_round(int32_t seed, uint64_t round, uint32_t* out55) {
     if (!out55 || seed <= 0 || seed >= (int32_t)RANF_MOD) return TP3_E_INVALID;
     static const std::vector<uint32_t> table = ranf_round_jump_table();

@@ -1,0 +1,116 @@
+// Hand-written FP64 elementary functions for the fused kernel.
+//
+// Why not CUDA's libdevice versions: ncu on the first kernel (profiles/r01_v1_fast_f64_ranf.txt)
+// showed only 31 % of the issue slots going to the FP64 pipe; log()/sincospi()/sqrt() spend more
+// instructions on UMOV pairs (64-bit immediates), integer fix-ups and slow-path branches than on
+// DFMAs.  Here every coefficient lives in constant memory (DFMA reads c[bank][off] directly), there
+// are no special-case branches (the operands of this kernel are known to be finite and normal), and
+// the argument reductions use what we know about the inputs:
+//   neg_log      x in (0, 2): 128-entry table of (1/c, -log c) in shared memory + degree-6 log1p
+//   sincos_2pi   u in [0, 1): exact quadrant reduction of t = 4u, degree-6 polynomials in a^2
+//   sqrt / rsqrt / rcp        MUFU seed (RSQ64H / RCP64H) + Newton steps in FMA form
+// Accuracy (tests/test_gpu_parity.py::test_fastmath_accuracy, measured on B200): <= 2 ulp each,
+// i.e. ~1e-16 relative, four orders of magnitude inside the 1e-13 per-event budget that keeps every
+// accumulated quantity within 1e-10 of the reference.
+#pragma once
+
+namespace tp3 {
+
+#include "fastmath_tables.inc"
+
+__constant__ double kLog1p[5] = {TP3_LOG1P_COEFFS};
+__constant__ double kSinPoly[7] = {TP3_SIN_COEFFS};
+__constant__ double kCosPoly[7] = {TP3_COS_COEFFS};
+__constant__ double kNegLn2 = TP3_NEG_LN2;
+
+struct FastMathSmem {
+    double2 log_tab[128];
+};
+
+__device__ __forceinline__ void fastmath_load(FastMathSmem* sm) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) sm->log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
+}
+
+__device__ __forceinline__ double mufu_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double mufu_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// 1/x, x finite normal: seed error e0 -> e0^3 with three FMAs
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double y = mufu_rcp(x);
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+// sqrt(x) and 1/sqrt(x) together (Goldschmidt form), x > 0 finite normal
+__device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs) {
+    const double y = mufu_rsqrt(x);
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    s = g;
+    rs = h + h;
+}
+// sqrt(x), x >= 0 (0 is clamped to 1e-300, whose root 1e-150 is 0 for every use in this kernel)
+__device__ __forceinline__ double fast_sqrt(double x) {
+    x = fmax(x, 1e-300);
+    const double y = mufu_rsqrt(x);
+    double g = x * y;
+    const double h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    const double h1 = fma(h, r, h);
+    r = fma(-g, h1, 0.5);
+    return fma(g, r, g);
+}
+
+// -log(x) for finite normal x > 0
+__device__ __forceinline__ double fast_neg_log(double x, const FastMathSmem* sm) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int k = (hi >> 20) - 1023;
+    const double2 t = sm->log_tab[(hi >> 13) & 127];
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(r, kLog1p[4], kLog1p[3]);
+    p = fma(r, p, kLog1p[2]);
+    p = fma(r, p, kLog1p[1]);
+    p = fma(r, p, kLog1p[0]);
+    p = fma(r * r, p, r);  // log1p(r)
+    return fma((double)k, kNegLn2, t.y) - p;
+}
+
+// sin(2 pi u), cos(2 pi u) for u in [0, 1]
+__device__ __forceinline__ void fast_sincos_2pi(double u, double& s, double& c) {
+    const double t = 4.0 * u;
+    const double qd = rint(t);
+    const int q = __double2int_rn(t);
+    const double a = t - qd;  // exact, |a| <= 1/2
+    const double y = a * a;
+    double ps = fma(y, kSinPoly[6], kSinPoly[5]);
+    double pc = fma(y, kCosPoly[6], kCosPoly[5]);
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+        ps = fma(y, ps, kSinPoly[i]);
+        pc = fma(y, pc, kCosPoly[i]);
+    }
+    ps *= a;
+    // rotate by q quarter turns: (s, c) -> (c, -s) -> (-s, -c) -> (-c, s)
+    const bool swap = q & 1;
+    const double s0 = swap ? pc : ps, c0 = swap ? ps : pc;
+    const int sflip = (int)((unsigned)(q & 2) << 30), cflip = (int)((unsigned)((q + 1) & 2) << 30);
+    s = __hiloint2double(__double2hiint(s0) ^ sflip, __double2loint(s0));
+    c = __hiloint2double(__double2hiint(c0) ^ cflip, __double2loint(c0));
+}
+
+}  // namespace tp3

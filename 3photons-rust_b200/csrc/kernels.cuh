@@ -47,7 +47,6 @@ template <> struct RawWord<double, RNG_XOSHIRO> { using type = uint64_t; };
 template <> struct RawWord<float, RNG_XOSHIRO> { using type = uint32_t; };
 
 // raw stream word -> uniform in [0,1): ranf.rs:99 / rand 0.8.5 Standard distribution (Appendix B.3)
-__device__ __forceinline__ double to_uniform(uint32_t n, double*, int) { return (double)(int)n * 1e-9; }
 __device__ __forceinline__ float to_uniform_ranf(uint32_t n) { return (float)(int)n * 1e-9f; }
 __device__ __forceinline__ double to_uniform_xo(uint64_t x) { return (double)(x >> 11) * (1.0 / 9007199254740992.0); }
 __device__ __forceinline__ float to_uniform_xo(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
@@ -74,8 +73,8 @@ template <class F> struct WarpRng<F, RNG_RANF> {
         return e < hi ? e : -1;
     }
     __device__ void raw(int it, int lane, uint32_t w[12]) {
-        s.ensure((it + 1) * kWarpDraws, lane);
-        s.draws(it, lane, w);
+        if (it > 0) s.advance(lane);
+        s.draws(lane, w);
     }
     __device__ static F uniform(uint32_t w) {
         if (sizeof(F) == 8) return (F)((double)(int)w * 1e-9);
@@ -156,6 +155,7 @@ template <class F> struct LaneAcc {
 template <class F> __device__ __forceinline__ F shfl_xor_t(F v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 struct BlockSmem {
+    FastMathSmem fm;
     RanfWarpSmem ranf[kWarps];
     uint32_t seed_y[kRanfLag + 1];
     uint32_t seed_tmp[kRanfLag + 1];
@@ -169,6 +169,8 @@ __device__ __forceinline__ void setup_batch(const SimArgs& a, BlockSmem& sm, War
                                             int& n_ev) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t b = blockIdx.x;
+    fastmath_load(&sm.fm);
+    __syncthreads();
     batch = a.first_batch + b;
     n_ev = (b + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
     if (RNG == RNG_RANF && a.jump_seeding) {
@@ -200,9 +202,15 @@ __global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, con
         F u[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
+        // The fast kernel never needs the sorted order: the energy cut is min(E_1,E_2,E_3) either way, the
+        // plane normal p_a x p_b is the same direction for any photon pair (momenta sum to zero), and the
+        // helicity sums are symmetric under photon permutations (the reference's no-photon-sorting golden
+        // is a symlink to the default one). The sort (evgen.rs:109-118) stays in the literal kernel and in
+        // the per-event dump.
+        constexpr bool kSort = SORT && LITERAL;
         F p[3][4];
-        gen_event<F, SORT, LITERAL>(u, P.e_total, p);
-        if (keep_event<F, SORT>(p, P)) {
+        gen_event<F, kSort, LITERAL>(u, P.e_total, &sm.fm, p);
+        if (keep_event<F, kSort>(p, P)) {
             F m[5];
             if (LITERAL) me_literal<F>(p, P, m);
             else me_fast<F>(p, P, m);
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
         F u[12];
         for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
         F p[3][4];
-        gen_event<F, SORT, LITERAL>(u, P.e_total, p);
+        gen_event<F, SORT, LITERAL>(u, P.e_total, &sm.fm, p);
         const bool k = keep_event<F, SORT>(p, P);
         F m[5] = {0, 0, 0, 0, 0};
         if (k) {
@@ -318,6 +326,29 @@ template <class F> __global__ void merge_kernel(const tp3_acc* __restrict__ in, 
     F t = (F)base[off];
     for (uint64_t b = 1; b < n; ++b) t += (F)base[b * 13 + off];
     reinterpret_cast<double*>(out)[off] = (double)t;
+}
+
+// Parity hook for the hand-written FP64 functions (fastmath.cuh): out[i] = f_which(in[i]).
+__global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __restrict__ in, double* __restrict__ out) {
+    __shared__ FastMathSmem fm;
+    fastmath_load(&fm);
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double x = in[i];
+        double a = 0, b = 0;
+        switch (which) {
+            case 0: a = fast_neg_log(x, &fm); break;
+            case 1: fast_sincos_2pi(x, a, b); break;
+            case 2: fast_sincos_2pi(x, b, a); break;
+            case 3: a = fast_sqrt(x); break;
+            case 4: a = fast_rcp(x); break;
+            case 5: fast_sqrt_rsqrt(x, b, a); break;
+            case 6: fast_sqrt_rsqrt(x, a, b); break;
+            case 7: a = mufu_rcp(x); break;
+            case 8: a = mufu_rsqrt(x); break;
+        }
+        out[i] = a;
+    }
 }
 
 // Peak probes: 8 independent FMA chains per thread.

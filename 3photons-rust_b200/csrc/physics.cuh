@@ -11,6 +11,8 @@
 
 #include <cstdint>
 
+#include "fastmath.cuh"
+
 namespace tp3 {
 
 template <class F> struct Num;
@@ -40,18 +42,20 @@ __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(
 __device__ __forceinline__ double abs_t(double x) { return fabs(x); }
 __device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
 
-// Reciprocal without the IEEE-division slow path: MUFU seed + 2 Newton steps (operands here are
-// always finite, normal and far from overflow). ~1 ulp.
-__device__ __forceinline__ double rcp_t(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
-}
+// Fast-path math: hand-written FP64 (fastmath.cuh); f32 keeps libdevice (MUFU based, already lean).
+__device__ __forceinline__ double rcp_t(double x) { return fast_rcp(x); }
 __device__ __forceinline__ float rcp_t(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double neg_log_t(double x, const FastMathSmem* sm) { return fast_neg_log(x, sm); }
+__device__ __forceinline__ float neg_log_t(float x, const FastMathSmem*) { return -logf(x); }
+__device__ __forceinline__ void sincos_2pi_t(double u, double* s, double* c) { fast_sincos_2pi(u, *s, *c); }
+__device__ __forceinline__ void sincos_2pi_t(float u, float* s, float* c) { sincospif(2.0f * u, s, c); }
+__device__ __forceinline__ double sqrt_pos_t(double x) { return fast_sqrt(x); }
+__device__ __forceinline__ float sqrt_pos_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ void sqrt_rsqrt_t(double x, double* s, double* rs) { fast_sqrt_rsqrt(x, *s, *rs); }
+__device__ __forceinline__ void sqrt_rsqrt_t(float x, float* s, float* rs) {
+    *rs = rsqrtf(x);
+    *s = x * *rs;
+}
 
 // Kernel-side view of tp3_params in the run's Float.
 template <class F> struct PhysParams {
@@ -64,19 +68,22 @@ template <class F> struct PhysParams {
 // u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187).
 // p[k] = (X, Y, Z, E) of photon k, optionally sorted by decreasing E (evgen.rs:109-118).
 template <class F, bool SORT, bool LITERAL>
-__device__ __forceinline__ void gen_event(const F u[12], F e_total, F p[3][4]) {
+__device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMathSmem* fm, F p[3][4]) {
     F q[3][4];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const F c = (F)2 * u[4 * k] - (F)1;
-        F sphi, cphi;
-        if (LITERAL)
-            sincos_t(Num<F>::TWO_PI * u[4 * k + 1], &sphi, &cphi);
-        else
-            sincospi_t((F)2 * u[4 * k + 1], &sphi, &cphi);
         const F e = u[4 * k + 2] * u[4 * k + 3];
-        const F st = sqrt_t((F)1 - c * c);
-        const F en = -log_t(e + Num<F>::MIN_POSITIVE);
+        F sphi, cphi, st, en;
+        if (LITERAL) {
+            sincos_t(Num<F>::TWO_PI * u[4 * k + 1], &sphi, &cphi);
+            st = sqrt_t((F)1 - c * c);
+            en = -log_t(e + Num<F>::MIN_POSITIVE);
+        } else {
+            sincos_2pi_t(u[4 * k + 1], &sphi, &cphi);
+            st = sqrt_pos_t((F)1 - c * c);
+            en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
+        }
         q[k][0] = en * (st * sphi);
         q[k][1] = en * (st * cphi);
         q[k][2] = en * c;
@@ -92,8 +99,8 @@ __device__ __forceinline__ void gen_event(const F u[12], F e_total, F p[3][4]) {
         m = sqrt_t(m2);
         beta = (F)1 / (m + r[3]);
     } else {
-        const F rs = rsqrt_t(m2);
-        m = m2 * rs;
+        F rs;
+        sqrt_rsqrt_t(m2, &m, &rs);
         alpha = e_total * (rs * rs);
         beta = rcp_t(m + r[3]);
     }

@@ -9,8 +9,11 @@
 //     gives every new slot as a +-combination of <= 4 OLD slots, so one round = 55 independent
 //     lanes of work (2 passes of a 32-wide warp);
 //   * layout: draws are stored in CONSUMPTION order (the reference hands out slots 55,54,..,1,
-//     ranf.rs:95-101) in a 512-word shared-memory ring, so the 12 draws of one event are three
-//     aligned 128-bit shared loads, bank-conflict free across the warp (stride 48 B).
+//     ranf.rs:95-101) in a linear 8-round buffer per warp (440 draws >= 54 + the 384 one warp
+//     iteration consumes); a refill keeps the unconsumed tail at the front and regenerates 7
+//     rounds with compile-time shared-memory offsets (no ring arithmetic): ~17 warp instructions
+//     per round of 55 numbers (ncu on the first version, which used a masked ring: 29 issue slots
+//     per number, 20 % of the kernel).
 //
 // xoshiro256+/128+ (src/random/standard.rs): per-lane state in registers; each lane owns a
 // contiguous run of events.  Batch start states come from a seeding kernel (GF(2) jump
@@ -24,48 +27,50 @@ namespace tp3 {
 constexpr int kRanfLag = 55;
 constexpr int kRanfDigits = 5;
 constexpr uint32_t kRanfMod = 1000000000u;
-constexpr int kRing = 512;       // words per warp ring
-constexpr int kRingBias = 64;    // ring position of consumption coordinate 0 (keeps 16 B alignment)
 constexpr int kDrawsPerEvent = 12;
-constexpr int kWarpDraws = 32 * kDrawsPerEvent;  // draws consumed by one warp iteration
+constexpr int kWarpDraws = 32 * kDrawsPerEvent;   // draws consumed by one warp iteration (384)
+constexpr int kBufRounds = 8;                     // rounds held per warp: 440 draws >= 54 + 384
+constexpr int kBufWords = kBufRounds * kRanfLag;
 
 struct RanfWarpSmem {
-    uint32_t ring[kRing];
-    uint32_t win[2 * kRanfLag + 2];
+    uint32_t buf[kBufWords];           // rounds rho .. rho+7 in CONSUMPTION order (draw r of a round = slot 55 - r)
+    uint32_t win[2 * kRanfLag + 2];    // jump-ahead window (slot order), used by init only
 };
 
-__device__ __forceinline__ int ring_pos(int c) { return (c + kRingBias) & (kRing - 1); }
-
-__device__ __forceinline__ uint32_t ranf_norm(int v) {
-    // v in (-2e9, 2e9) -> [0, 1e9)
-    v += (v < 0) ? (int)kRanfMod : 0;
-    v += (v < 0) ? (int)kRanfMod : 0;
-    v -= (v >= (int)kRanfMod) ? (int)kRanfMod : 0;
-    return (uint32_t)v;
+// a - b for a, b in [0, 1e9): add 1e9 back if the difference is negative (unsigned min trick)
+__device__ __forceinline__ uint32_t ranf_sub(uint32_t a, uint32_t b) {
+    const uint32_t v = a - b;
+    return min(v, v + kRanfMod);
+}
+// a + b for a, b in [0, 1e9): subtract 1e9 if the sum reaches it
+__device__ __forceinline__ uint32_t ranf_add(uint32_t a, uint32_t b) {
+    const uint32_t v = a + b;
+    return min(v, v - kRanfMod);
 }
 
-// Next round in slot order: y[0..54] = numbers[1..55] -> out (may not alias)
+// Next round in slot order: y[0..54] = numbers[1..55] (ranf.rs:106-119 with the in-place updates
+// substituted: every new slot is a +- combination of at most four OLD slots)
 __device__ __forceinline__ uint32_t ranf_next_slot(const uint32_t* y, int i /*1..55*/) {
-    int v;
-    if (i <= 24) v = (int)y[i - 1] - (int)y[i + 31 - 1];
-    else if (i <= 48) v = (int)y[i - 1] - (int)y[i - 24 - 1] + (int)y[i + 7 - 1];
-    else v = (int)y[i - 1] - (int)y[i - 24 - 1] + (int)y[i - 48 - 1] - (int)y[i - 17 - 1];
-    return ranf_norm(v);
+    if (i <= 24) return ranf_sub(y[i - 1], y[i + 31 - 1]);
+    if (i <= 48) return ranf_add(ranf_sub(y[i - 1], y[i - 24 - 1]), y[i + 7 - 1]);
+    return ranf_add(ranf_sub(y[i - 1], y[i - 24 - 1]), ranf_sub(y[i - 48 - 1], y[i - 17 - 1]));
 }
 
+// One warp regenerates the reference's stream for a contiguous range of events.
+// The buffer is linear (no ring arithmetic): all shared-memory offsets inside a refill are
+// compile-time immediates relative to three per-lane pointers.
 struct RanfWarpStream {
-    uint32_t* ring;
-    int round_base;  // consumption coordinate of the first draw of the newest generated round
-    int gen_end;     // one past the newest generated draw
+    uint32_t* buf;
+    int p0;  // offset in buf of the first draw of the current warp iteration (warp-uniform)
 
     // base_y: round 0 of the generator (55 words, slot order) in shared or global memory;
     // d0: index of this warp's first draw in that generator's stream.
     __device__ void init(RanfWarpSmem* sm, const uint32_t* base_y, uint64_t d0,
                          const uint32_t* __restrict__ jump_table, int lane) {
-        ring = sm->ring;
+        buf = sm->buf;
         uint32_t* win = sm->win;
         const uint64_t rho0 = d0 / kRanfLag;
-        const int q0 = (int)(d0 - rho0 * kRanfLag);
+        p0 = (int)(d0 - rho0 * kRanfLag);
         for (int i = lane; i < kRanfLag; i += 32) win[i] = base_y[i];
         __syncwarp();
         for (int k = 0; k < kRanfDigits; ++k) {
@@ -96,48 +101,61 @@ struct RanfWarpStream {
             __syncwarp();
         }
         // slot order -> consumption order: draw r of the round is slot 55 - r
-        for (int r = lane; r < kRanfLag; r += 32) ring[ring_pos(-q0 + r)] = win[kRanfLag - 1 - r];
-        round_base = -q0;
-        gen_end = -q0 + kRanfLag;
+        for (int r = lane; r < kRanfLag; r += 32) buf[r] = win[kRanfLag - 1 - r];
         __syncwarp();
+        refill(1, lane);
     }
 
-    // One new round from the newest one, in consumption order (r = 55 - slot).
-    __device__ __forceinline__ uint32_t next_draw(int r) const {
-        const int b = round_base;
-        const int k1 = (r >= 31) ? r - 31 : r + 24;
-        const int k2 = (r >= 7) ? r - 7 : r + 48;
-        int v = (int)ring[ring_pos(b + r)] - (int)ring[ring_pos(b + k1)];
-        if (r < 31) v += (int)ring[ring_pos(b + k2)];
-        if (r < 7) v -= (int)ring[ring_pos(b + r + 17)];
-        return ranf_norm(v);
-    }
-
-    // Make draws [.., need_end) available.
-    __device__ __forceinline__ void ensure(int need_end, int lane) {
-        __syncwarp();
-        while (gen_end < need_end) {
-            const uint32_t v0 = next_draw(lane);
-            const uint32_t v1 = (lane + 32 < kRanfLag) ? next_draw(lane + 32) : 0u;
-            ring[ring_pos(round_base + kRanfLag + lane)] = v0;
-            if (lane + 32 < kRanfLag) ring[ring_pos(round_base + kRanfLag + lane + 32)] = v1;
-            round_base += kRanfLag;
-            gen_end += kRanfLag;
-            __syncwarp();
+    // Round K of the buffer from round K-1, in consumption order r = 55 - slot:
+    //   r in [31,54]: z'[r] = z[r] - z[r-31]
+    //   r in [ 7,30]: z'[r] = z[r] - z[r+24] + z[r-7]
+    //   r in [ 0, 6]: z'[r] = z[r] - z[r+24] + z[r+48] - z[r+17]
+    template <int K> __device__ __forceinline__ void gen_round(int lane) {
+        const uint32_t* pl = buf + lane + (K - 1) * kRanfLag;
+        const uint32_t* pa = pl + (lane == 31 ? -31 : 24);
+        const uint32_t* pb = pl + (lane >= 7 ? -7 : 48);
+        uint32_t v = ranf_sub(pl[0], pa[0]);
+        if (lane < 31) {
+            uint32_t c = pb[0];
+            if (lane < 7) c = ranf_sub(c, pl[17]);
+            v = ranf_add(v, c);
         }
+        uint32_t w = 0;
+        if (lane < kRanfLag - 32) w = ranf_sub(pl[32], pl[1]);
+        buf[K * kRanfLag + lane] = v;
+        if (lane < kRanfLag - 32) buf[K * kRanfLag + 32 + lane] = w;
+        __syncwarp();
     }
 
-    // The 12 raw draws of event slot `lane` of warp iteration `it` (consumption coordinates).
-    __device__ __forceinline__ void draws(int it, int lane, uint32_t out[kDrawsPerEvent]) const {
-        const int c0 = it * kWarpDraws + lane * kDrawsPerEvent;
+    // Generate rounds first..7 of the buffer (first is 1 or 2, warp-uniform).
+    __device__ __forceinline__ void refill(int first, int lane) {
+        if (first <= 1) gen_round<1>(lane);
+        gen_round<2>(lane);
+        gen_round<3>(lane);
+        gen_round<4>(lane);
+        gen_round<5>(lane);
+        gen_round<6>(lane);
+        gen_round<7>(lane);
+    }
+
+    // Step to the next warp iteration: drop the 384 consumed draws, keep the round(s) that still
+    // hold unconsumed ones at the front, regenerate the rest.
+    __device__ __forceinline__ void advance(int lane) {
+        __syncwarp();
+        p0 += kWarpDraws;                      // in [384, 438]
+        const int k = (p0 >= 7 * kRanfLag) ? 7 : 6;
+        const int src = k * kRanfLag;
+        for (int r = lane; r < kBufWords - src; r += 32) buf[r] = buf[src + r];
+        p0 -= src;
+        __syncwarp();
+        refill(8 - k, lane);
+    }
+
+    // The 12 raw draws of event slot `lane` of the current warp iteration.
+    __device__ __forceinline__ void draws(int lane, uint32_t out[kDrawsPerEvent]) const {
+        const uint32_t* p = buf + p0 + lane * kDrawsPerEvent;
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            const uint4 v = *reinterpret_cast<const uint4*>(&ring[ring_pos(c0 + 4 * g)]);
-            out[4 * g + 0] = v.x;
-            out[4 * g + 1] = v.y;
-            out[4 * g + 2] = v.z;
-            out[4 * g + 3] = v.w;
-        }
+        for (int j = 0; j < kDrawsPerEvent; ++j) out[j] = p[j];
     }
 };
 

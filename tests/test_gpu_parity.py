@@ -79,6 +79,53 @@ def test_rng_stream_far_batches(sims, oracle):
         assert sims("standard-random").rng_dump(batch, 24) == oracle.rng_words("standard-random", batch, 24)
 
 
+# ------------------------------------------------------------ hand-written FP64 functions
+def test_fastmath_accuracy(sims):
+    """fastmath.cuh vs correctly rounded references (mpmath, 40 digits): a few ulp at most."""
+    import random
+    import mpmath as mp
+    mp.mp.dps = 40
+    sim = sims("")
+    rnd = random.Random(1234)
+    n = 20000
+
+    def ulp_err(got, want_mp):
+        want = float(want_mp)
+        if want == 0.0:
+            return abs(got) / 5e-324
+        import math
+        return abs(mp.mpf(got) - want_mp) / mp.mpf(math.ulp(want))
+
+    # -log x on the kernel's domain: products of two RANF uniforms (down to 1e-18) + MIN_POSITIVE, and x near 1
+    xs = [rnd.randrange(1, 10**9) * 1e-9 * (rnd.randrange(1, 10**9) * 1e-9) for _ in range(n)]
+    xs += [1.0 - 2.0**-k for k in range(1, 53)] + [2.2250738585072014e-308, 1e-18, 0.5, 1.0, 0.999999999 * 0.999999999]
+    got = sim.fastmath_probe(0, xs)
+    for x, g in zip(xs, got):
+        want = -mp.log(mp.mpf(x))
+        assert abs(mp.mpf(g) - want) <= 3e-16 * max(abs(want), 1), (x, g)
+    # sin / cos (2 pi u), u = n * 1e-9 and u = k * 2^-53
+    us = [rnd.randrange(0, 10**9) * 1e-9 for _ in range(n)] + [rnd.getrandbits(53) * 2.0**-53 for _ in range(n)]
+    us += [0.0, 0.125, 0.25, 0.375, 0.5, 0.625, 0.75, 0.875, 0.999999999, 1e-9]
+    s_got, c_got = sim.fastmath_probe(1, us), sim.fastmath_probe(2, us)
+    for u, sg, cg in zip(us, s_got, c_got):
+        ang = 2 * mp.pi * mp.mpf(u)
+        assert abs(mp.mpf(sg) - mp.sin(ang)) <= 2.5e-16, (u, sg)
+        assert abs(mp.mpf(cg) - mp.cos(ang)) <= 2.5e-16, (u, cg)
+    # sqrt, 1/x, 1/sqrt x
+    xs = [rnd.uniform(1e-12, 1.0) for _ in range(n)] + [rnd.uniform(1.0, 1e6) for _ in range(n)]
+    for which, f in ((3, mp.sqrt), (6, mp.sqrt), (4, lambda v: 1 / v), (5, lambda v: 1 / mp.sqrt(v))):
+        got = sim.fastmath_probe(which, xs)
+        worst = max(ulp_err(g, f(mp.mpf(x))) for x, g in zip(xs, got))
+        assert worst <= 2.0, (which, float(worst))
+    assert sim.fastmath_probe(3, [0.0])[0] < 1e-149  # clamped root of zero
+    # the MUFU seeds the Newton steps start from (documented in DESIGN.md): at least 20 good bits
+    for which, f in ((7, lambda v: 1 / v), (8, lambda v: 1 / mp.sqrt(v))):
+        got = sim.fastmath_probe(which, xs[:2000])
+        worst = max(abs(mp.mpf(g) / f(mp.mpf(x)) - 1) for x, g in zip(xs, got))
+        print(f"MUFU seed {which}: max relative error 2^{float(mp.log(worst, 2)):.2f}")
+        assert worst < 2.0**-20
+
+
 # ------------------------------------------------------------------------ per-event parity
 @pytest.mark.parametrize("kernel", [0, 1], ids=["fast", "literal"])
 @pytest.mark.parametrize("features", ["", "no-photon-sorting", "standard-random"])

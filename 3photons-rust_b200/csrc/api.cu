@@ -22,7 +22,7 @@ struct DeviceSlot {
     bool own_stream = false;
     uint32_t* d_ranf_table = nullptr;
     uint64_t* d_xo_digit_polys = nullptr;
-    uint64_t* d_xo_thread_polys = nullptr;
+    uint64_t* d_xo_lane_polys = nullptr;
     uint64_t* d_xo_states = nullptr;
     size_t xo_states_cap = 0;
     tp3_acc* d_out = nullptr;
@@ -43,7 +43,7 @@ struct tp3_ctx {
     uint32_t ranf_base[kRanfLag];
     std::vector<uint32_t> ranf_table;
     std::vector<uint64_t> xo_digit_polys;   // [n_digits][256][4]
-    std::vector<uint64_t> xo_thread_polys;  // [kThreads][4]
+    std::vector<uint64_t> xo_lane_polys;    // [32][4]
     uint64_t xo_base[4];
     int xo_digits = 0;
 };
@@ -75,7 +75,7 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
 
 template <class F, int RNG, bool SORT, bool LITERAL>
 void launch_sim(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
-    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)a.n_batches, kThreads, 0, st>>>(a, phys_params<F>(p));
+    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + kWarps - 1) / kWarps), kThreads, 0, st>>>(a, phys_params<F>(p));
 }
 template <class F, int RNG, bool SORT, bool LITERAL>
 void launch_dump(const SimArgs& a, const tp3_params& p, const DumpArgs& d, cudaStream_t st) {
@@ -135,11 +135,10 @@ void build_xoshiro_tables(tp3_ctx* c) {
         }
         unit = cur;
     }
-    c->xo_thread_polys.assign((size_t)kThreads * 4, 0);
-    for (int t = 0; t < kThreads; ++t) {
-        const uint64_t off = (uint64_t)kDrawsPerEvent * ((t / 32) * kWarpEvents + (t % 32) * kLaneEvents);
-        Gf2Poly p = gf2_x_pow(off, 0, mod);
-        std::memcpy(&c->xo_thread_polys[(size_t)t * 4], p.w, 32);
+    c->xo_lane_polys.assign((size_t)32 * 4, 0);
+    for (int l = 0; l < 32; ++l) {  // lane l starts kLaneEvents * l events into the batch
+        Gf2Poly p = gf2_x_pow((uint64_t)kDrawsPerEvent * kLaneEvents * l, 0, mod);
+        std::memcpy(&c->xo_lane_polys[(size_t)l * 4], p.w, 32);
     }
 }
 
@@ -170,7 +169,7 @@ SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     a.jump_seeding = (c->params.flags & TP3_FASTER_THREADING) ? 1u : 0u;
     a.ranf_table = s.d_ranf_table;
     a.xo_batch_states = s.d_xo_states;
-    a.xo_thread_polys = s.d_xo_thread_polys;
+    a.xo_lane_polys = s.d_xo_lane_polys;
     a.out = s.d_out;
     std::memcpy(a.ranf_base, c->ranf_base, sizeof a.ranf_base);
     a.ranf_seed = RANF_DEFAULT_SEED;
@@ -273,7 +272,7 @@ int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx*
         };
         if (xo) {
             e = up(c->xo_digit_polys.data(), c->xo_digit_polys.size() * 8, (void**)&s.d_xo_digit_polys);
-            if (e == cudaSuccess) e = up(c->xo_thread_polys.data(), c->xo_thread_polys.size() * 8, (void**)&s.d_xo_thread_polys);
+            if (e == cudaSuccess) e = up(c->xo_lane_polys.data(), c->xo_lane_polys.size() * 8, (void**)&s.d_xo_lane_polys);
         } else {
             e = up(c->ranf_table.data(), c->ranf_table.size() * 4, (void**)&s.d_ranf_table);
         }
@@ -292,7 +291,7 @@ void tp3_destroy(tp3_ctx* c) {
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_ranf_table);
         cudaFree(s.d_xo_digit_polys);
-        cudaFree(s.d_xo_thread_polys);
+        cudaFree(s.d_xo_lane_polys);
         cudaFree(s.d_xo_states);
         cudaFree(s.d_out);
         cudaFree(s.d_merged);

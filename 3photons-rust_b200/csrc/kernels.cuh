@@ -1,6 +1,12 @@
 // The fused per-batch kernel (replaces the closure of src/main.rs:103-128 and everything it
-// calls) plus the small parity/seeding kernels.  One CTA = one batch of <= 10 000 events
-// (src/scheduling/mod.rs:21); warp w of the CTA owns events [w*1280, (w+1)*1280) of the batch.
+// calls) plus the small parity/seeding kernels.
+//
+// Work decomposition: ONE WARP = ONE BATCH of <= 10 000 events (src/scheduling/mod.rs:21), four
+// batches per 128-thread CTA.  A warp regenerates its batch's random stream from one jump-ahead
+// (rng.cuh), runs generation + cuts on 32 events per iteration, compacts the survivors (70.8 % at
+// the default cuts) into a shared-memory queue and evaluates the matrix elements only on full
+// warps, then folds its 13 sums with shuffles and writes one 104-byte accumulator.  There is no
+// CTA-level barrier after the prologue, so warps never wait for each other.
 #pragma once
 
 #include <cstdint>
@@ -11,23 +17,22 @@
 
 namespace tp3 {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;                // batches per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kBatch = TP3_EVENT_BATCH_SIZE;
-constexpr int kWarpEvents = 1280;  // ceil32(10000 / 8): events of a batch owned by one warp
-constexpr int kLaneEvents = kWarpEvents / 32;  // xoshiro: contiguous events per lane
-static_assert(kWarpEvents * kWarps >= kBatch, "partition must cover a batch");
+constexpr int kLaneEvents = (kBatch + 31) / 32;  // xoshiro: contiguous events per lane (313)
+constexpr int kQueue = 64;               // survivor queue slots per warp (< 32 pending + <= 32 new)
 
 enum RngKind { RNG_RANF = 0, RNG_XOSHIRO = 1 };
 
 struct SimArgs {
     uint64_t first_batch;      // index of the first batch of this launch within the run
-    uint64_t n_batches;        // batches in this launch (grid size)
+    uint64_t n_batches;        // batches in this launch
     uint32_t last_batch_len;   // events in the last batch of the launch
     uint32_t jump_seeding;     // TP3_FASTER_THREADING: batch b starts after b rng.jump()s
     const uint32_t* ranf_table;        // [kRanfDigits][256][55]
     const uint64_t* xo_batch_states;   // [n_batches][4] from the seeding kernel
-    const uint64_t* xo_thread_polys;   // [kThreads][4] jump polynomial of each thread's offset in the batch
+    const uint64_t* xo_lane_polys;     // [32][4] jump polynomial of each lane's offset in the batch
     tp3_acc* out;                      // [n_batches]
     uint32_t ranf_base[kRanfLag];      // seeded round 0 (ranf.rs:28-66), slot order
     int32_t ranf_seed;
@@ -47,30 +52,40 @@ template <> struct RawWord<double, RNG_XOSHIRO> { using type = uint64_t; };
 template <> struct RawWord<float, RNG_XOSHIRO> { using type = uint32_t; };
 
 // raw stream word -> uniform in [0,1): ranf.rs:99 / rand 0.8.5 Standard distribution (Appendix B.3)
-__device__ __forceinline__ float to_uniform_ranf(uint32_t n) { return (float)(int)n * 1e-9f; }
 __device__ __forceinline__ double to_uniform_xo(uint64_t x) { return (double)(x >> 11) * (1.0 / 9007199254740992.0); }
 __device__ __forceinline__ float to_uniform_xo(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+template <class F> struct WarpSmem {
+    RanfWarpSmem ranf;
+    F queue[12][kQueue];  // survivors' momenta, component-major (conflict-free for consecutive slots)
+};
+template <class F> struct BlockSmem {
+    FastMathSmem fm;
+    WarpSmem<F> w[kWarps];
+};
 
 // Per-warp random source: hands each lane the 12 raw words of "its" event of iteration `it`.
 template <class F, int RNG> struct WarpRng;
 
+// RANF: lanes interleave (event = 32 it + lane); the warp regenerates the global stream cooperatively.
 template <class F> struct WarpRng<F, RNG_RANF> {
     RanfWarpStream s;
-    int lo, hi;
-    __device__ void init(const SimArgs& a, RanfWarpSmem* sm, uint32_t* blk_base, uint64_t batch, int n_ev, int warp,
-                         int lane) {
-        lo = warp * kWarpEvents;
-        hi = min(n_ev, lo + kWarpEvents);
-        if (lo >= hi) return;
-        if (a.jump_seeding)
-            s.init(sm, blk_base, (uint64_t)kDrawsPerEvent * lo, a.ranf_table, lane);
-        else
-            s.init(sm, a.ranf_base, (uint64_t)kDrawsPerEvent * (batch * kBatch + lo), a.ranf_table, lane);
+    int n;
+    __device__ void init(const SimArgs& a, WarpSmem<F>* sm, uint64_t batch, uint64_t /*slot*/, int n_ev, int lane) {
+        n = n_ev;
+        if (a.jump_seeding) {
+            // rng.jump() = reseed with seed + 123456 per batch (ranf.rs:136-140), i32 wrapping
+            uint32_t* y = reinterpret_cast<uint32_t*>(&sm->queue[0][0]);
+            ranf_seed_warp(y, y + 64, (int32_t)((uint32_t)a.ranf_seed + 123456u * (uint32_t)batch), lane);
+            s.init(&sm->ranf, y, 0, a.ranf_table, lane);
+        } else {
+            s.init(&sm->ranf, a.ranf_base, (uint64_t)kDrawsPerEvent * kBatch * batch, a.ranf_table, lane);
+        }
     }
-    __device__ int iterations() const { return lo < hi ? (hi - lo + 31) / 32 : 0; }
+    __device__ int iterations() const { return (n + 31) / 32; }
     __device__ int event_of(int it, int lane) const {
-        const int e = lo + 32 * it + lane;
-        return e < hi ? e : -1;
+        const int e = 32 * it + lane;
+        return e < n ? e : -1;
     }
     __device__ void raw(int it, int lane, uint32_t w[12]) {
         if (it > 0) s.advance(lane);
@@ -78,53 +93,33 @@ template <class F> struct WarpRng<F, RNG_RANF> {
     }
     __device__ static F uniform(uint32_t w) {
         if (sizeof(F) == 8) return (F)((double)(int)w * 1e-9);
-        return (F)to_uniform_ranf(w);
+        return (F)((float)(int)w * 1e-9f);
     }
 };
 
-template <> struct WarpRng<double, RNG_XOSHIRO> {
-    Xoshiro256Lane g;
-    int lo, hi;
-    __device__ void init(const SimArgs& a, RanfWarpSmem*, uint32_t*, uint64_t batch, int n_ev, int warp, int lane) {
-        lo = warp * kWarpEvents + lane * kLaneEvents;
-        hi = min(min(n_ev, (warp + 1) * kWarpEvents), lo + kLaneEvents);
-        const uint64_t* st = a.xo_batch_states + 4 * (batch - a.first_batch);
-        g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
-        const bool any = __any_sync(0xffffffffu, lo < hi);
-        if (any && (warp | lane)) g.apply(a.xo_thread_polys + 4 * (warp * 32 + lane));
+// xoshiro: per-lane state in registers, each lane owns a contiguous run of kLaneEvents events.
+template <class F, class Lane> struct XoshiroWarpRng {
+    Lane g;
+    int lo, hi, n;
+    __device__ void init(const SimArgs& a, WarpSmem<F>*, uint64_t, uint64_t slot, int n_ev, int lane) {
+        n = n_ev;
+        lo = lane * kLaneEvents;
+        hi = min(n_ev, lo + kLaneEvents);
+        const uint64_t* st = a.xo_batch_states + 4 * slot;
+        g.s0 = (decltype(g.s0))st[0]; g.s1 = (decltype(g.s0))st[1]; g.s2 = (decltype(g.s0))st[2]; g.s3 = (decltype(g.s0))st[3];
+        if (lane && lo < hi) g.apply(a.xo_lane_polys + 4 * lane);
     }
-    __device__ int iterations() const {
-        const int n = lo < hi ? hi - lo : 0;
-        return __reduce_max_sync(0xffffffffu, n);
-    }
+    __device__ int iterations() const { return min(n, kLaneEvents); }
     __device__ int event_of(int it, int) const { return lo + it < hi ? lo + it : -1; }
-    __device__ void raw(int, int, uint64_t w[12]) {
+    template <class W> __device__ void raw(int, int, W w[12]) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) w[j] = g.next();
     }
+};
+template <> struct WarpRng<double, RNG_XOSHIRO> : XoshiroWarpRng<double, Xoshiro256Lane> {
     __device__ static double uniform(uint64_t w) { return to_uniform_xo(w); }
 };
-
-template <> struct WarpRng<float, RNG_XOSHIRO> {
-    Xoshiro128Lane g;
-    int lo, hi;
-    __device__ void init(const SimArgs& a, RanfWarpSmem*, uint32_t*, uint64_t batch, int n_ev, int warp, int lane) {
-        lo = warp * kWarpEvents + lane * kLaneEvents;
-        hi = min(min(n_ev, (warp + 1) * kWarpEvents), lo + kLaneEvents);
-        const uint64_t* st = a.xo_batch_states + 4 * (batch - a.first_batch);
-        g.s0 = (uint32_t)st[0]; g.s1 = (uint32_t)st[1]; g.s2 = (uint32_t)st[2]; g.s3 = (uint32_t)st[3];
-        const bool any = __any_sync(0xffffffffu, lo < hi);
-        if (any && (warp | lane)) g.apply(a.xo_thread_polys + 4 * (warp * 32 + lane));
-    }
-    __device__ int iterations() const {
-        const int n = lo < hi ? hi - lo : 0;
-        return __reduce_max_sync(0xffffffffu, n);
-    }
-    __device__ int event_of(int it, int) const { return lo + it < hi ? lo + it : -1; }
-    __device__ void raw(int, int, uint32_t w[12]) {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) w[j] = g.next();
-    }
+template <> struct WarpRng<float, RNG_XOSHIRO> : XoshiroWarpRng<float, Xoshiro128Lane> {
     __device__ static float uniform(uint32_t w) { return to_uniform_xo(w); }
 };
 
@@ -154,71 +149,99 @@ template <class F> struct LaneAcc {
 
 template <class F> __device__ __forceinline__ F shfl_xor_t(F v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-struct BlockSmem {
-    FastMathSmem fm;
-    RanfWarpSmem ranf[kWarps];
-    uint32_t seed_y[kRanfLag + 1];
-    uint32_t seed_tmp[kRanfLag + 1];
-    double red[kWarps][12];
-    uint32_t red_n[kWarps];
-};
-
-// Shared prologue: batch geometry + per-warp random source.
+// Shared prologue. Returns false for warps beyond the last batch of the launch.
 template <class F, int RNG>
-__device__ __forceinline__ void setup_batch(const SimArgs& a, BlockSmem& sm, WarpRng<F, RNG>& rng, uint64_t& batch,
-                                            int& n_ev) {
+__device__ __forceinline__ bool setup_batch(const SimArgs& a, BlockSmem<F>& sm, WarpRng<F, RNG>& rng, int& n_ev) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t b = blockIdx.x;
     fastmath_load(&sm.fm);
     __syncthreads();
-    batch = a.first_batch + b;
-    n_ev = (b + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
-    if (RNG == RNG_RANF && a.jump_seeding) {
-        // rng.jump() = reseed with seed + 123456 per batch (ranf.rs:136-140), i32 wrapping
-        if (warp == 0)
-            ranf_seed_warp(sm.seed_y, sm.seed_tmp, (int32_t)((uint32_t)a.ranf_seed + 123456u * (uint32_t)batch), lane);
-        __syncthreads();
-    }
-    rng.init(a, &sm.ranf[warp], sm.seed_y, batch, n_ev, warp, lane);
+    const uint64_t slot = (uint64_t)blockIdx.x * kWarps + warp;  // batch index within the launch
+    if (slot >= a.n_batches) return false;
+    n_ev = (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
+    rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
+    return true;
 }
 
 template <class F, int RNG, bool SORT, bool LITERAL>
 __global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
-    __shared__ BlockSmem sm;
+    __shared__ BlockSmem<F> sm;
     using Word = typename RawWord<F, RNG>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpRng<F, RNG> rng;
-    uint64_t batch;
     int n_ev;
-    setup_batch<F, RNG>(a, sm, rng, batch, n_ev);
+    if (!setup_batch<F, RNG>(a, sm, rng, n_ev)) return;
+    F(*queue)[kQueue] = sm.w[warp].queue;
+
+    // The fast kernel never needs the sorted order: the energy cut is min(E_1,E_2,E_3) either way, the plane
+    // normal p_a x p_b has the same direction for any photon pair (momenta sum to zero), and the helicity sums
+    // are symmetric under photon permutations (the reference's no-photon-sorting golden is a symlink to the
+    // default one). The sort (evgen.rs:109-118) stays in the literal kernel and in the per-event dump.
+    constexpr bool kSort = SORT && LITERAL;
 
     LaneAcc<F> acc;
     acc.clear();
+    int q_head = 0, q_count = 0;  // survivor queue (warp-uniform)
     const int n_it = rng.iterations();
     for (int it = 0; it < n_it; ++it) {
         Word w[12];
         rng.raw(it, lane, w);
-        if (rng.event_of(it, lane) < 0) continue;
-        F u[12];
-#pragma unroll
-        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
-        // The fast kernel never needs the sorted order: the energy cut is min(E_1,E_2,E_3) either way, the
-        // plane normal p_a x p_b is the same direction for any photon pair (momenta sum to zero), and the
-        // helicity sums are symmetric under photon permutations (the reference's no-photon-sorting golden
-        // is a symlink to the default one). The sort (evgen.rs:109-118) stays in the literal kernel and in
-        // the per-event dump.
-        constexpr bool kSort = SORT && LITERAL;
+        bool keep = false;
         F p[3][4];
-        gen_event<F, kSort, LITERAL>(u, P.e_total, &sm.fm, p);
-        if (keep_event<F, kSort>(p, P)) {
+        if (rng.event_of(it, lane) >= 0) {
+            F u[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
+            gen_event<F, kSort, LITERAL>(u, P.e_total, &sm.fm, p);
+            keep = keep_event<F, kSort>(p, P);
+        }
+        if (LITERAL) {
+            if (keep) {
+                F m[5];
+                me_literal<F>(p, P, m);
+                acc.integrate(m, P.sigma_contribs);
+            }
+            continue;
+        }
+        // evcut.rs:42-96 as a predicate mask; survivors are compacted so that the matrix elements
+        // (75 % of the FP64 work) always run on full warps.
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int slot = (q_head + q_count + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) queue[4 * k + c][slot] = p[k][c];
+        }
+        q_count += __popc(mask);
+        __syncwarp();
+        if (q_count >= 32) {
+            const int slot = (q_head + lane) & (kQueue - 1);
+            F e[3][4];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) e[k][c] = queue[4 * k + c][slot];
+            __syncwarp();
+            q_head = (q_head + 32) & (kQueue - 1);
+            q_count -= 32;
             F m[5];
-            if (LITERAL) me_literal<F>(p, P, m);
-            else me_fast<F>(p, P, m);
+            me_fast<F>(e, P, m);
             acc.integrate(m, P.sigma_contribs);
         }
     }
+    if (!LITERAL && lane < q_count) {  // drain
+        const int slot = (q_head + lane) & (kQueue - 1);
+        F e[3][4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) e[k][c] = queue[4 * k + c][slot];
+        F m[5];
+        me_fast<F>(e, P, m);
+        acc.integrate(m, P.sigma_contribs);
+    }
 
-    // resacc.rs:133-139 within the batch: warp shuffle tree, then warps in fixed order
+    // ResultsAccumulator of the batch: xor-shuffle tree over the 32 lane-partials (deterministic)
     F v[12];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -235,38 +258,27 @@ __global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, con
         n += __shfl_xor_sync(0xffffffffu, n, off);
     }
     if (lane == 0) {
+        tp3_acc* o = a.out + ((uint64_t)blockIdx.x * kWarps + warp);
+        o->selected_events = n;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) sm.red[warp][k] = (double)v[k];
-        sm.red_n[warp] = n;
-    }
-    __syncthreads();
-    if (threadIdx.x < 13) {
-        tp3_acc* o = a.out + blockIdx.x;
-        if (threadIdx.x == 12) {
-            uint64_t t = 0;
-            for (int w2 = 0; w2 < kWarps; ++w2) t += sm.red_n[w2];
-            o->selected_events = t;
-        } else {
-            F t = (F)sm.red[0][threadIdx.x];
-            for (int w2 = 1; w2 < kWarps; ++w2) t += (F)sm.red[w2][threadIdx.x];
-            double* dst = threadIdx.x < 5 ? &o->spm2[threadIdx.x]
-                          : threadIdx.x < 10 ? &o->vars[threadIdx.x - 5]
-                          : threadIdx.x == 10 ? &o->sigma : &o->variance;
-            *dst = (double)t;
+        for (int k = 0; k < 5; ++k) {
+            o->spm2[k] = (double)v[k];
+            o->vars[k] = (double)v[5 + k];
         }
+        o->sigma = (double)v[10];
+        o->variance = (double)v[11];
     }
 }
 
-// Parity hook: same streams, same partition, per-event outputs instead of sums.
+// Parity hook: same streams, same event -> lane mapping, per-event outputs instead of sums.
 template <class F, int RNG, bool SORT, bool LITERAL>
 __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const PhysParams<F> P, const DumpArgs d) {
-    __shared__ BlockSmem sm;
+    __shared__ BlockSmem<F> sm;
     using Word = typename RawWord<F, RNG>::type;
     const int lane = threadIdx.x & 31;
     WarpRng<F, RNG> rng;
-    uint64_t batch;
     int n_ev;
-    setup_batch<F, RNG>(a, sm, rng, batch, n_ev);
+    if (!setup_batch<F, RNG>(a, sm, rng, n_ev)) return;
     const int n_it = rng.iterations();
     for (int it = 0; it < n_it; ++it) {
         Word w[12];

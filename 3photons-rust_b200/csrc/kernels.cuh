@@ -55,9 +55,15 @@ template <> struct RawWord<float, RNG_XOSHIRO> { using type = uint32_t; };
 __device__ __forceinline__ double to_uniform_xo(uint64_t x) { return (double)(x >> 11) * (1.0 / 9007199254740992.0); }
 __device__ __forceinline__ float to_uniform_xo(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
+template <class F> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+
 template <class F> struct WarpSmem {
     RanfWarpSmem ranf;
-    F queue[12][kQueue];  // survivors' momenta, component-major (conflict-free for consecutive slots)
+    // survivors' momenta as (X,Y) and (Z,E) pairs per photon, pair-major: consecutive slots are
+    // consecutive 16-byte (f64) words, so the 128-bit accesses of a warp are conflict free
+    alignas(16) typename Pair<F>::type queue[6][kQueue];
 };
 template <class F> struct BlockSmem {
     FastMathSmem fm;
@@ -75,7 +81,7 @@ template <class F> struct WarpRng<F, RNG_RANF> {
         n = n_ev;
         if (a.jump_seeding) {
             // rng.jump() = reseed with seed + 123456 per batch (ranf.rs:136-140), i32 wrapping
-            uint32_t* y = reinterpret_cast<uint32_t*>(&sm->queue[0][0]);
+            uint32_t* y = reinterpret_cast<uint32_t*>(&sm->queue[0][0]);  // the queue is idle during seeding
             ranf_seed_warp(y, y + 64, (int32_t)((uint32_t)a.ranf_seed + 123456u * (uint32_t)batch), lane);
             s.init(&sm->ranf, y, 0, a.ranf_table, lane);
         } else {
@@ -163,14 +169,14 @@ __device__ __forceinline__ bool setup_batch(const SimArgs& a, BlockSmem<F>& sm, 
 }
 
 template <class F, int RNG, bool SORT, bool LITERAL>
-__global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
+__global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
     __shared__ BlockSmem<F> sm;
     using Word = typename RawWord<F, RNG>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpRng<F, RNG> rng;
     int n_ev;
     if (!setup_batch<F, RNG>(a, sm, rng, n_ev)) return;
-    F(*queue)[kQueue] = sm.w[warp].queue;
+    typename Pair<F>::type(*queue)[kQueue] = sm.w[warp].queue;
 
     // The fast kernel never needs the sorted order: the energy cut is min(E_1,E_2,E_3) either way, the plane
     // normal p_a x p_b has the same direction for any photon pair (momenta sum to zero), and the helicity sums
@@ -208,9 +214,10 @@ __global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, con
         if (keep) {
             const int slot = (q_head + q_count + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1);
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) queue[4 * k + c][slot] = p[k][c];
+            for (int k = 0; k < 3; ++k) {
+                queue[2 * k][slot] = {p[k][0], p[k][1]};
+                queue[2 * k + 1][slot] = {p[k][2], p[k][3]};
+            }
         }
         q_count += __popc(mask);
         __syncwarp();
@@ -218,9 +225,10 @@ __global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, con
             const int slot = (q_head + lane) & (kQueue - 1);
             F e[3][4];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) e[k][c] = queue[4 * k + c][slot];
+            for (int k = 0; k < 3; ++k) {
+                const typename Pair<F>::type xy = queue[2 * k][slot], ze = queue[2 * k + 1][slot];
+                e[k][0] = xy.x; e[k][1] = xy.y; e[k][2] = ze.x; e[k][3] = ze.y;
+            }
             __syncwarp();
             q_head = (q_head + 32) & (kQueue - 1);
             q_count -= 32;
@@ -233,9 +241,10 @@ __global__ void __launch_bounds__(kThreads) simulate_kernel(const SimArgs a, con
         const int slot = (q_head + lane) & (kQueue - 1);
         F e[3][4];
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) e[k][c] = queue[4 * k + c][slot];
+        for (int k = 0; k < 3; ++k) {
+            const typename Pair<F>::type xy = queue[2 * k][slot], ze = queue[2 * k + 1][slot];
+            e[k][0] = xy.x; e[k][1] = xy.y; e[k][2] = ze.x; e[k][3] = ze.y;
+        }
         F m[5];
         me_fast<F>(e, P, m);
         acc.integrate(m, P.sigma_contribs);

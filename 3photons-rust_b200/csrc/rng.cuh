@@ -32,8 +32,10 @@ constexpr int kWarpDraws = 32 * kDrawsPerEvent;   // draws consumed by one warp 
 constexpr int kBufRounds = 8;                     // rounds held per warp: 440 draws >= 54 + 384
 constexpr int kBufWords = kBufRounds * kRanfLag;
 
-struct RanfWarpSmem {
-    uint32_t buf[kBufWords];           // rounds rho .. rho+7 in CONSUMPTION order (draw r of a round = slot 55 - r)
+struct alignas(16) RanfWarpSmem {
+    // rounds rho .. rho+7 in CONSUMPTION order (draw r of a round = slot 55 - r), starting at word
+    // `shift` (0..3) so that the first unconsumed draw is always 16-byte aligned
+    uint32_t buf[kBufWords + 4];
     uint32_t win[2 * kRanfLag + 2];    // jump-ahead window (slot order), used by init only
 };
 
@@ -58,10 +60,13 @@ __device__ __forceinline__ uint32_t ranf_next_slot(const uint32_t* y, int i /*1.
 
 // One warp regenerates the reference's stream for a contiguous range of events.
 // The buffer is linear (no ring arithmetic): all shared-memory offsets inside a refill are
-// compile-time immediates relative to three per-lane pointers.
+// compile-time immediates relative to per-lane pointers, and every lane keeps its own two values
+// of the newest round in registers (draws r = lane and r = lane + 32).
 struct RanfWarpStream {
     uint32_t* buf;
-    int p0;  // offset in buf of the first draw of the current warp iteration (warp-uniform)
+    int shift;     // word offset of round 0 in buf (0..3)
+    int p0;        // word offset in buf of the first draw of the current warp iteration; p0 % 4 == 0
+    uint32_t v, w; // this lane's draws r = lane and r = lane + 32 of the newest generated round
 
     // base_y: round 0 of the generator (55 words, slot order) in shared or global memory;
     // d0: index of this warp's first draw in that generator's stream.
@@ -70,7 +75,7 @@ struct RanfWarpStream {
         buf = sm->buf;
         uint32_t* win = sm->win;
         const uint64_t rho0 = d0 / kRanfLag;
-        p0 = (int)(d0 - rho0 * kRanfLag);
+        const int q0 = (int)(d0 - rho0 * kRanfLag);
         for (int i = lane; i < kRanfLag; i += 32) win[i] = base_y[i];
         __syncwarp();
         for (int k = 0; k < kRanfDigits; ++k) {
@@ -86,7 +91,7 @@ struct RanfWarpStream {
                 const int i = lane + 32 * h;
                 uint64_t acc = 0;
                 if (i < kRanfLag) {
-#pragma unroll 11
+#pragma unroll 5
                     for (int j = 0; j < kRanfLag; ++j) {
                         acc += (uint64_t)__ldg(c + j) * win[i + j];
                         if ((j % 16) == 15) acc %= kRanfMod;  // 16 products < 1.6e19 < 2^64
@@ -101,7 +106,12 @@ struct RanfWarpStream {
             __syncwarp();
         }
         // slot order -> consumption order: draw r of the round is slot 55 - r
-        for (int r = lane; r < kRanfLag; r += 32) buf[r] = win[kRanfLag - 1 - r];
+        shift = (-q0) & 3;
+        p0 = shift + q0;
+        v = win[kRanfLag - 1 - lane];
+        w = (lane < kRanfLag - 32) ? win[kRanfLag - 1 - 32 - lane] : 0u;
+        buf[shift + lane] = v;
+        if (lane < kRanfLag - 32) buf[shift + 32 + lane] = w;
         __syncwarp();
         refill(1, lane);
     }
@@ -110,52 +120,79 @@ struct RanfWarpStream {
     //   r in [31,54]: z'[r] = z[r] - z[r-31]
     //   r in [ 7,30]: z'[r] = z[r] - z[r+24] + z[r-7]
     //   r in [ 0, 6]: z'[r] = z[r] - z[r+24] + z[r+48] - z[r+17]
-    template <int K> __device__ __forceinline__ void gen_round(int lane) {
-        const uint32_t* pl = buf + lane + (K - 1) * kRanfLag;
-        const uint32_t* pa = pl + (lane == 31 ? -31 : 24);
-        const uint32_t* pb = pl + (lane >= 7 ? -7 : 48);
-        uint32_t v = ranf_sub(pl[0], pa[0]);
+    template <int K> __device__ __forceinline__ void gen_round(const uint32_t* pl, const uint32_t* pa, const uint32_t* pb,
+                                                               uint32_t* po, int lane) {
+        constexpr int B = (K - 1) * kRanfLag;
+        uint32_t nv = ranf_sub(v, pa[B]);
         if (lane < 31) {
-            uint32_t c = pb[0];
-            if (lane < 7) c = ranf_sub(c, pl[17]);
-            v = ranf_add(v, c);
+            uint32_t c = pb[B];
+            if (lane < 7) c = ranf_sub(c, pl[B + 17]);
+            nv = ranf_add(nv, c);
         }
-        uint32_t w = 0;
-        if (lane < kRanfLag - 32) w = ranf_sub(pl[32], pl[1]);
-        buf[K * kRanfLag + lane] = v;
-        if (lane < kRanfLag - 32) buf[K * kRanfLag + 32 + lane] = w;
+        uint32_t nw = 0;
+        if (lane < kRanfLag - 32) nw = ranf_sub(w, pl[B + 1]);
+        v = nv;
+        w = nw;
+        po[B + kRanfLag] = nv;
+        if (lane < kRanfLag - 32) po[B + kRanfLag + 32] = nw;
         __syncwarp();
     }
 
     // Generate rounds first..7 of the buffer (first is 1 or 2, warp-uniform).
     __device__ __forceinline__ void refill(int first, int lane) {
-        if (first <= 1) gen_round<1>(lane);
-        gen_round<2>(lane);
-        gen_round<3>(lane);
-        gen_round<4>(lane);
-        gen_round<5>(lane);
-        gen_round<6>(lane);
-        gen_round<7>(lane);
+        uint32_t* po = buf + shift + lane;
+        const uint32_t* pl = po;
+        const uint32_t* pa = pl + (lane == 31 ? -31 : 24);
+        const uint32_t* pb = pl + (lane >= 7 ? -7 : 48);
+        if (first <= 1) gen_round<1>(pl, pa, pb, po, lane);
+        gen_round<2>(pl, pa, pb, po, lane);
+        gen_round<3>(pl, pa, pb, po, lane);
+        gen_round<4>(pl, pa, pb, po, lane);
+        gen_round<5>(pl, pa, pb, po, lane);
+        gen_round<6>(pl, pa, pb, po, lane);
+        gen_round<7>(pl, pa, pb, po, lane);
     }
 
-    // Step to the next warp iteration: drop the 384 consumed draws, keep the round(s) that still
-    // hold unconsumed ones at the front, regenerate the rest.
+    // Step to the next warp iteration: drop the 384 consumed draws, move the round(s) that still
+    // hold unconsumed ones to the front (re-aligned to 16 bytes), regenerate the rest.
     __device__ __forceinline__ void advance(int lane) {
         __syncwarp();
-        p0 += kWarpDraws;                      // in [384, 438]
-        const int k = (p0 >= 7 * kRanfLag) ? 7 : 6;
-        const int src = k * kRanfLag;
-        for (int r = lane; r < kBufWords - src; r += 32) buf[r] = buf[src + r];
-        p0 -= src;
+        const int rel = p0 - shift + kWarpDraws;        // in [384, 438], relative to round 0
+        const int k = (rel >= 7 * kRanfLag) ? 7 : 6;    // round holding the next unconsumed draw
+        const int new_rel = rel - k * kRanfLag;
+        const int new_shift = (-new_rel) & 3;
+        if (k == 7) {  // the newest round is in registers
+            buf[new_shift + lane] = v;
+            if (lane < kRanfLag - 32) buf[new_shift + 32 + lane] = w;
+        } else {       // once every 55 iterations: two rounds stay
+            const uint32_t a = buf[shift + 6 * kRanfLag + lane];
+            const uint32_t b = (lane < kRanfLag - 32) ? buf[shift + 6 * kRanfLag + 32 + lane] : 0u;
+            __syncwarp();
+            buf[new_shift + lane] = a;
+            buf[new_shift + kRanfLag + lane] = v;
+            if (lane < kRanfLag - 32) {
+                buf[new_shift + 32 + lane] = b;
+                buf[new_shift + kRanfLag + 32 + lane] = w;
+            }
+        }
+        shift = new_shift;
+        p0 = new_shift + new_rel;
         __syncwarp();
         refill(8 - k, lane);
     }
 
-    // The 12 raw draws of event slot `lane` of the current warp iteration.
+    // The 12 raw draws of event slot `lane` of the current warp iteration: three aligned 128-bit
+    // loads, bank-conflict free across the warp (lane stride 48 bytes).
     __device__ __forceinline__ void draws(int lane, uint32_t out[kDrawsPerEvent]) const {
-        const uint32_t* p = buf + p0 + lane * kDrawsPerEvent;
+        const uint4* p = reinterpret_cast<const uint4*>(buf + p0 + lane * kDrawsPerEvent);
 #pragma unroll
-        for (int j = 0; j < kDrawsPerEvent; ++j) out[j] = p[j];
+        for (int g = 0; g < 3; ++g) {
+            const uint4 q = p[g];
+            out[4 * g + 0] = q.x;
+            out[4 * g + 1] = q.y;
+            out[4 * g + 2] = q.z;
+            out[4 * g + 3] = q.w;
+        }
     }
 };
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@ thread_local std::string g_create_error;
 
 struct DeviceSlot {
     int dev = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint32_t* d_ranf_table = nullptr;
@@ -75,7 +77,8 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
 
 template <class F, int RNG, bool SORT, bool LITERAL>
 void launch_sim(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
-    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + kWarps - 1) / kWarps), kThreads, 0, st>>>(a, phys_params<F>(p));
+    const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
+    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, 0, st>>>(a, phys_params<F>(p));
 }
 template <class F, int RNG, bool SORT, bool LITERAL>
 void launch_dump(const SimArgs& a, const tp3_params& p, const DumpArgs& d, cudaStream_t st) {
@@ -167,6 +170,18 @@ SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     a.n_batches = n;
     a.last_batch_len = last_len;
     a.jump_seeding = (c->params.flags & TP3_FASTER_THREADING) ? 1u : 0u;
+    // Consecutive batches per warp: the sequential RANF stream continues from one batch into the next, so the
+    // jump-ahead is paid once per warp. Keep at least ~8 warp-tasks per resident warp slot for load balance.
+    a.batches_per_warp = 1;
+    if (!(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING))) {
+        const uint64_t resident_warps = (uint64_t)s.sm_count * 16;
+        uint64_t nb = n / (resident_warps * 8);
+        a.batches_per_warp = (uint32_t)(nb < 1 ? 1 : nb > 8 ? 8 : nb);
+        if (const char* e = std::getenv("TP3_BATCHES_PER_WARP")) {  // test hook
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 64) a.batches_per_warp = (uint32_t)v;
+        }
+    }
     a.ranf_table = s.d_ranf_table;
     a.xo_batch_states = s.d_xo_states;
     a.xo_lane_polys = s.d_xo_lane_polys;
@@ -261,6 +276,7 @@ int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx*
         cudaDeviceProp prop;
         if ((e = cudaGetDeviceProperties(&prop, s.dev)) != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
         if (prop.major != 10) return fail(TP3_E_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+        s.sm_count = prop.multiProcessorCount;
         if ((e = cudaSetDevice(s.dev)) != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
         if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
             return fail(TP3_E_CUDA, cudaGetErrorString(e));

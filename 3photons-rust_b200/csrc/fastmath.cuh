@@ -62,9 +62,10 @@ __device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs)
     s = g;
     rs = h + h;
 }
-// sqrt(x), x >= 0 (0 is clamped to 1e-300, whose root 1e-150 is 0 for every use in this kernel)
+// sqrt(x), x >= 0; x is biased by 1e-300 so that 0 gives 1e-150 (0 for every use in this kernel) instead of
+// 0 * inf; the nonzero arguments here are >= 4e-9 and unchanged by the bias
 __device__ __forceinline__ double fast_sqrt(double x) {
-    x = fmax(x, 1e-300);
+    x += 1e-300;
     const double y = mufu_rsqrt(x);
     double g = x * y;
     const double h = 0.5 * y;

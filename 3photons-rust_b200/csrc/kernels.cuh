@@ -30,6 +30,7 @@ struct SimArgs {
     uint64_t n_batches;        // batches in this launch
     uint32_t last_batch_len;   // events in the last batch of the launch
     uint32_t jump_seeding;     // TP3_FASTER_THREADING: batch b starts after b rng.jump()s
+    uint32_t batches_per_warp; // consecutive batches handled by one warp (the RANF stream simply continues)
     const uint32_t* ranf_table;        // [kRanfDigits][256][55]
     const uint64_t* xo_batch_states;   // [n_batches][4] from the seeding kernel
     const uint64_t* xo_lane_polys;     // [32][4] jump polynomial of each lane's offset in the batch
@@ -94,8 +95,16 @@ template <class F> struct WarpRng<F, RNG_RANF> {
         return e < n ? e : -1;
     }
     __device__ void raw(int it, int lane, uint32_t w[12]) {
-        if (it > 0) s.advance(lane);
+        if (it > 0) s.advance(kWarpDraws, lane);
         s.draws(lane, w);
+    }
+    // The next batch of the sequential stream starts right after this batch's last draw: step past
+    // the (possibly partial) last warp iteration instead of jumping again.
+    __device__ bool next_batch(const SimArgs& a, int n_next, int lane) {
+        if (a.jump_seeding) return false;
+        s.advance(kDrawsPerEvent * (n - 32 * (iterations() - 1)), lane);
+        n = n_next;
+        return true;
     }
     __device__ static F uniform(uint32_t w) {
         if (sizeof(F) == 8) return (F)((double)(int)w * 1e-9);
@@ -117,6 +126,7 @@ template <class F, class Lane> struct XoshiroWarpRng {
     }
     __device__ int iterations() const { return min(n, kLaneEvents); }
     __device__ int event_of(int it, int) const { return lo + it < hi ? lo + it : -1; }
+    __device__ bool next_batch(const SimArgs&, int, int) { return false; }  // re-seeded from the batch state
     template <class W> __device__ void raw(int, int, W w[12]) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) w[j] = g.next();
@@ -155,17 +165,9 @@ template <class F> struct LaneAcc {
 
 template <class F> __device__ __forceinline__ F shfl_xor_t(F v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// Shared prologue. Returns false for warps beyond the last batch of the launch.
-template <class F, int RNG>
-__device__ __forceinline__ bool setup_batch(const SimArgs& a, BlockSmem<F>& sm, WarpRng<F, RNG>& rng, int& n_ev) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    fastmath_load(&sm.fm);
-    __syncthreads();
-    const uint64_t slot = (uint64_t)blockIdx.x * kWarps + warp;  // batch index within the launch
-    if (slot >= a.n_batches) return false;
-    n_ev = (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
-    rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
-    return true;
+// Number of events of batch `slot` of the launch.
+__device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
+    return (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
 }
 
 template <class F, int RNG, bool SORT, bool LITERAL>
@@ -173,9 +175,8 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(con
     __shared__ BlockSmem<F> sm;
     using Word = typename RawWord<F, RNG>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpRng<F, RNG> rng;
-    int n_ev;
-    if (!setup_batch<F, RNG>(a, sm, rng, n_ev)) return;
+    fastmath_load(&sm.fm);
+    __syncthreads();
     typename Pair<F>::type(*queue)[kQueue] = sm.w[warp].queue;
 
     // The fast kernel never needs the sorted order: the energy cut is min(E_1,E_2,E_3) either way, the plane
@@ -183,6 +184,14 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(con
     // are symmetric under photon permutations (the reference's no-photon-sorting golden is a symlink to the
     // default one). The sort (evgen.rs:109-118) stays in the literal kernel and in the per-event dump.
     constexpr bool kSort = SORT && LITERAL;
+
+    WarpRng<F, RNG> rng;
+    const uint64_t slot0 = ((uint64_t)blockIdx.x * kWarps + warp) * a.batches_per_warp;
+  for (uint32_t bi = 0; bi < a.batches_per_warp; ++bi) {
+    const uint64_t slot = slot0 + bi;
+    if (slot >= a.n_batches) break;
+    const int n_ev = batch_len(a, slot);
+    if (bi == 0 || !rng.next_batch(a, n_ev, lane)) rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
 
     LaneAcc<F> acc;
     acc.clear();
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(con
         n += __shfl_xor_sync(0xffffffffu, n, off);
     }
     if (lane == 0) {
-        tp3_acc* o = a.out + ((uint64_t)blockIdx.x * kWarps + warp);
+        tp3_acc* o = a.out + slot;
         o->selected_events = n;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -277,6 +286,8 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(con
         o->sigma = (double)v[10];
         o->variance = (double)v[11];
     }
+    __syncwarp();
+  }
 }
 
 // Parity hook: same streams, same event -> lane mapping, per-event outputs instead of sums.
@@ -285,9 +296,11 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
     __shared__ BlockSmem<F> sm;
     using Word = typename RawWord<F, RNG>::type;
     const int lane = threadIdx.x & 31;
+    fastmath_load(&sm.fm);
+    __syncthreads();
+    if (threadIdx.x >= 32) return;  // one warp = one batch; the dump is for a single batch
     WarpRng<F, RNG> rng;
-    int n_ev;
-    if (!setup_batch<F, RNG>(a, sm, rng, n_ev)) return;
+    rng.init(a, &sm.w[0], a.first_batch, 0, batch_len(a, 0), lane);
     const int n_it = rng.iterations();
     for (int it = 0; it < n_it; ++it) {
         Word w[12];

@@ -133,10 +133,9 @@ __device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMa
 // the common factor E/2 drops out of evcut.rs:52-62 and :80-92.
 template <class F, bool SORT>
 __device__ __forceinline__ bool keep_event(const F p[3][4], const PhysParams<F>& P) {
-    F emin;
-    if (SORT) emin = p[2][3];
-    else emin = fmin(p[0][3], fmin(p[1][3], p[2][3]));
-    bool ok = !(emin < P.e_min);
+    bool ok;
+    if (SORT) ok = !(p[2][3] < P.e_min);
+    else ok = !(p[0][3] < P.e_min) && !(p[1][3] < P.e_min) && !(p[2][3] < P.e_min);  // event.rs:96-105
 #pragma unroll
     for (int k = 0; k < 3; ++k) ok = ok && !(abs_t(p[k][0]) > P.acut * p[k][3]);
 #pragma unroll

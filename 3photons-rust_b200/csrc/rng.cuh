@@ -35,7 +35,7 @@ constexpr int kBufWords = kBufRounds * kRanfLag;
 struct alignas(16) RanfWarpSmem {
     // rounds rho .. rho+7 in CONSUMPTION order (draw r of a round = slot 55 - r), starting at word
     // `shift` (0..3) so that the first unconsumed draw is always 16-byte aligned
-    uint32_t buf[kBufWords + 4];
+    uint32_t buf[kBufWords + 8];
     uint32_t win[2 * kRanfLag + 2];    // jump-ahead window (slot order), used by init only
 };
 
@@ -120,65 +120,67 @@ struct RanfWarpStream {
     //   r in [31,54]: z'[r] = z[r] - z[r-31]
     //   r in [ 7,30]: z'[r] = z[r] - z[r+24] + z[r-7]
     //   r in [ 0, 6]: z'[r] = z[r] - z[r+24] + z[r+48] - z[r+17]
+    // Branch free: every lane loads all four operands from valid addresses and masks the terms its
+    // class does not have (a - 0 and a + 0 pass through ranf_sub / ranf_add unchanged).
     template <int K> __device__ __forceinline__ void gen_round(const uint32_t* pl, const uint32_t* pa, const uint32_t* pb,
-                                                               uint32_t* po, int lane) {
+                                                               uint32_t* po, uint32_t m7, uint32_t m31, bool p23) {
         constexpr int B = (K - 1) * kRanfLag;
-        uint32_t nv = ranf_sub(v, pa[B]);
-        if (lane < 31) {
-            uint32_t c = pb[B];
-            if (lane < 7) c = ranf_sub(c, pl[B + 17]);
-            nv = ranf_add(nv, c);
-        }
-        uint32_t nw = 0;
-        if (lane < kRanfLag - 32) nw = ranf_sub(w, pl[B + 1]);
-        v = nv;
-        w = nw;
-        po[B + kRanfLag] = nv;
-        if (lane < kRanfLag - 32) po[B + kRanfLag + 32] = nw;
+        const uint32_t b = pa[B], c = pb[B], d = pl[B + 17], e = pl[B + 1];
+        const uint32_t t1 = ranf_sub(v, b);
+        const uint32_t t2 = ranf_sub(c, d & m7) & m31;
+        v = ranf_add(t1, t2);
+        w = ranf_sub(w, e);
+        po[B + kRanfLag] = v;
+        if (p23) po[B + kRanfLag + 32] = w;
         __syncwarp();
     }
 
-    // Generate rounds first..7 of the buffer (first is 1 or 2, warp-uniform).
+    // Generate rounds first..7 of the buffer (warp-uniform first >= 1).
     __device__ __forceinline__ void refill(int first, int lane) {
         uint32_t* po = buf + shift + lane;
         const uint32_t* pl = po;
         const uint32_t* pa = pl + (lane == 31 ? -31 : 24);
         const uint32_t* pb = pl + (lane >= 7 ? -7 : 48);
-        if (first <= 1) gen_round<1>(pl, pa, pb, po, lane);
-        gen_round<2>(pl, pa, pb, po, lane);
-        gen_round<3>(pl, pa, pb, po, lane);
-        gen_round<4>(pl, pa, pb, po, lane);
-        gen_round<5>(pl, pa, pb, po, lane);
-        gen_round<6>(pl, pa, pb, po, lane);
-        gen_round<7>(pl, pa, pb, po, lane);
+        const uint32_t m7 = lane < 7 ? 0xffffffffu : 0u, m31 = lane < 31 ? 0xffffffffu : 0u;
+        const bool p23 = lane < kRanfLag - 32;
+        if (first <= 1) gen_round<1>(pl, pa, pb, po, m7, m31, p23);
+        if (first <= 2) gen_round<2>(pl, pa, pb, po, m7, m31, p23);
+        if (first <= 3) gen_round<3>(pl, pa, pb, po, m7, m31, p23);
+        if (first <= 4) gen_round<4>(pl, pa, pb, po, m7, m31, p23);
+        if (first <= 5) gen_round<5>(pl, pa, pb, po, m7, m31, p23);
+        if (first <= 6) gen_round<6>(pl, pa, pb, po, m7, m31, p23);
+        gen_round<7>(pl, pa, pb, po, m7, m31, p23);
     }
 
-    // Step to the next warp iteration: drop the 384 consumed draws, move the round(s) that still
-    // hold unconsumed ones to the front (re-aligned to 16 bytes), regenerate the rest.
-    __device__ __forceinline__ void advance(int lane) {
+    // Step past `consumed` draws (384 after a full warp iteration, 12 * n after a partial one at the
+    // end of a batch): the rounds that still hold unconsumed draws move to the front (re-aligned to
+    // 16 bytes), the rest is regenerated.
+    __device__ __forceinline__ void advance(int consumed, int lane) {
         __syncwarp();
-        const int rel = p0 - shift + kWarpDraws;        // in [384, 438], relative to round 0
-        const int k = (rel >= 7 * kRanfLag) ? 7 : 6;    // round holding the next unconsumed draw
+        const int rel = p0 - shift + consumed;          // relative to round 0, < 440
+        const int k = rel / kRanfLag;                   // round holding the next unconsumed draw
         const int new_rel = rel - k * kRanfLag;
         const int new_shift = (-new_rel) & 3;
-        if (k == 7) {  // the newest round is in registers
+        if (k == 7) {  // the usual case: only the newest round stays, and it is in registers
             buf[new_shift + lane] = v;
             if (lane < kRanfLag - 32) buf[new_shift + 32 + lane] = w;
-        } else {       // once every 55 iterations: two rounds stay
-            const uint32_t a = buf[shift + 6 * kRanfLag + lane];
-            const uint32_t b = (lane < kRanfLag - 32) ? buf[shift + 6 * kRanfLag + 32 + lane] : 0u;
-            __syncwarp();
-            buf[new_shift + lane] = a;
-            buf[new_shift + kRanfLag + lane] = v;
-            if (lane < kRanfLag - 32) {
-                buf[new_shift + 32 + lane] = b;
-                buf[new_shift + kRanfLag + 32 + lane] = w;
+        } else {
+            // Batch boundary (consumed = 192 for full batches, so k is 3 or 4): forward copy in chunks of 32.
+            // Needs k >= 1: the destination then starts below the source and a chunk never overwrites
+            // words that are still to be read.
+            const int n = (kBufRounds - k) * kRanfLag;
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                const uint32_t t = (i < n) ? buf[shift + k * kRanfLag + i] : 0u;
+                __syncwarp();
+                if (i < n) buf[new_shift + i] = t;
+                __syncwarp();
             }
         }
         shift = new_shift;
         p0 = new_shift + new_rel;
         __syncwarp();
-        refill(8 - k, lane);
+        refill(kBufRounds - k, lane);
     }
 
     // The 12 raw draws of event slot `lane` of the current warp iteration: three aligned 128-bit

@@ -166,6 +166,30 @@ def test_batches_match_oracle_f64(sims, oracle, valeurs_text, features, kernel):
         assert_acc_close(accs[b], want, REL_F64, what=f"batch {b}")
 
 
+@pytest.mark.parametrize("per_warp", [2, 3, 5, 16])
+def test_stream_continues_across_batches(tp3, oracle, valeurs_text, per_warp, monkeypatch):
+    """A warp that handles several consecutive batches continues the sequential RANF stream instead of
+    jumping again; the per-batch accumulators must not depend on that grouping (bit for bit), and must
+    match the oracle."""
+    nb = 11
+    cfg = tp3.Configuration.parse(valeurs_text)
+    monkeypatch.setenv("TP3_BATCHES_PER_WARP", "1")
+    with tp3.Simulator(cfg) as sim:
+        ref = sim.simulate_batches(3, nb, 7777)
+    monkeypatch.setenv("TP3_BATCHES_PER_WARP", str(per_warp))
+    with tp3.Simulator(cfg) as sim:
+        got = sim.simulate_batches(3, nb, 7777)
+    assert bytes(got) == bytes(ref)
+    run = oracle.run(valeurs_text, "", threads=8, num_events=14 * 10000, want_text=False)
+    scale = (14 * 10000) / 1e7
+    for b in range(nb - 1):
+        want = run.per_batch[3 + b]
+        want.sigma *= scale
+        want.variance *= scale * scale
+        assert got[b].selected_events == want.selected_events
+        assert_acc_close(got[b], want, REL_F64, what=f"batch {3 + b}")
+
+
 @pytest.mark.parametrize("features", ["f32", "standard-random,f32"])
 def test_batches_match_oracle_f32(sims, oracle, valeurs_text, features):
     nb = 12

@@ -408,3 +408,47 @@ def main_run(valeurs_path: str, out_dir: str = "", features="", kernel: int = KE
     if rc != OK:
         raise Tp3Error(rc, buf.value.decode())
     return buf.value.decode(), float(secs.value)
+
+
+# ------------------------------------------------------------------------------ multi-process
+def gather_accumulators(local, world_size: int, rank: int, dist=None, device=None, dst: int = 0):
+    """Per-batch accumulators of every rank, concatenated in rank (= batch) order on `dst`.
+    `local` is this rank's ctypes array of Acc for its contiguous batch range (shard_range).  Works with
+    any torch.distributed backend: byte tensors live on `device` ("cuda" for nccl, "cpu" for gloo).
+    There is no data-path collective in the hot path; this is the one exchange at the end of a run
+    (multi_threading.rs:107-126 gathers the same per-batch results from its worker threads)."""
+    if world_size == 1:
+        return list(local)
+    import torch
+    device = device or "cpu"
+    n_local = len(local)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world_size)]
+    dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=device))
+    counts = [int(c.item()) for c in counts]
+    size = C.sizeof(Acc)
+    width = max(counts) * size  # gather wants equal sizes: pad every rank's bytes to the longest range
+    mine = torch.zeros(width, dtype=torch.uint8)
+    if n_local:
+        mine[: n_local * size] = torch.frombuffer(bytearray(bytes(local)), dtype=torch.uint8)
+    mine = mine.to(device)
+    parts = [torch.empty(width, dtype=torch.uint8, device=device) for _ in counts] if rank == dst else None
+    dist.gather(mine, parts, dst=dst)
+    if rank != dst:
+        return None
+    raw = b"".join(p.cpu().numpy().tobytes()[: c * size] for p, c in zip(parts, counts))
+    return list((Acc * (len(raw) // size)).from_buffer_copy(raw))
+
+
+def run_simulation_distributed(cfg: Configuration, simulate_range, world_size: int, rank: int, dist=None, device=None):
+    """scheduling::run_simulation over `world_size` processes (one GPU each): rank r simulates the
+    contiguous batch range shard_range(r) with `simulate_range(first, n, last_len) -> Acc array`
+    (Simulator.simulate_batches on a GPU), rank 0 folds all batches in batch order and finalizes.
+    The result is bit-identical for every world_size."""
+    nb, last = batch_layout(cfg.num_events)
+    lo, cnt = shard_range(nb, world_size, rank)
+    my_last = last if lo + cnt == nb else EVENT_BATCH_SIZE
+    local = simulate_range(lo, cnt, my_last) if cnt else (Acc * 0)()
+    accs = gather_accumulators(local, world_size, rank, dist, device)
+    if accs is None:
+        return None
+    return finalize(cfg, fold(accs, cfg.flags))

@@ -345,21 +345,52 @@ __global__ void xoshiro_seed_kernel(uint64_t first_batch, uint64_t n_batches, co
     out[4 * i + 0] = g.s0; out[4 * i + 1] = g.s1; out[4 * i + 2] = g.s2; out[4 * i + 3] = g.s3;
 }
 
-// ResultsAccumulator::merge (resacc.rs:133-139) as a left fold in batch order: lane k owns field k.
-template <class F> __global__ void merge_kernel(const tp3_acc* __restrict__ in, uint64_t n, tp3_acc* out) {
-    const int k = threadIdx.x;
-    if (k > 12) return;
-    if (k == 12) {
-        uint64_t t = 0;
-        for (uint64_t b = 0; b < n; ++b) t += in[b].selected_events;
-        out->selected_events = t;
-        return;
+// ResultsAccumulator::merge (resacc.rs:133-139) as a strict left fold in batch order (bit-identical to
+// the host fold). One warp: all lanes stage tiles of 32 accumulators (13 words each) in shared memory
+// with coalesced loads, lane k < 12 then adds field k of the 32 batches sequentially (the additions are
+// the only serial chain, ~8 cycles each), lane 12 sums the event counts.
+template <class F> __global__ void __launch_bounds__(32) merge_kernel(const tp3_acc* __restrict__ in, uint64_t n, tp3_acc* out) {
+    constexpr int kTile = 32, kWords = 13;
+    __shared__ uint64_t tile[2][kTile * kWords];
+    const int lane = threadIdx.x;
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(in);
+    const uint64_t total = n * kWords;
+    auto stage = [&](int buf, uint64_t t) {
+        const uint64_t base = t * kTile * kWords;
+#pragma unroll
+        for (int i = 0; i < kWords; ++i) {
+            const uint64_t idx = base + (uint64_t)i * 32 + lane;
+            tile[buf][i * 32 + lane] = idx < total ? src[idx] : 0ull;
+        }
+    };
+    F acc = 0;
+    uint64_t cnt = 0;
+    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+    stage(0, 0);
+    __syncwarp();
+    for (uint64_t t = 0; t < n_tiles; ++t) {
+        const int cur = (int)(t & 1);
+        if (t + 1 < n_tiles) stage(cur ^ 1, t + 1);
+        const int m = (int)min((uint64_t)kTile, n - t * kTile);
+        if (lane < 12) {
+            const int field = 1 + lane;
+            if (t == 0) {
+                acc = (F)__longlong_as_double((long long)tile[cur][field]);
+                for (int b = 1; b < m; ++b) acc += (F)__longlong_as_double((long long)tile[cur][b * kWords + field]);
+            } else if (m == kTile) {
+#pragma unroll
+                for (int b = 0; b < kTile; ++b) acc += (F)__longlong_as_double((long long)tile[cur][b * kWords + field]);
+            } else {
+                for (int b = 0; b < m; ++b) acc += (F)__longlong_as_double((long long)tile[cur][b * kWords + field]);
+            }
+        } else if (lane == 12) {
+            for (int b = 0; b < m; ++b) cnt += tile[cur][b * kWords];
+        }
+        __syncwarp();
     }
-    const size_t off = 1 + k;  // doubles after the u64
-    const double* base = reinterpret_cast<const double*>(in);
-    F t = (F)base[off];
-    for (uint64_t b = 1; b < n; ++b) t += (F)base[b * 13 + off];
-    reinterpret_cast<double*>(out)[off] = (double)t;
+    uint64_t* dst = reinterpret_cast<uint64_t*>(out);
+    if (lane < 12) dst[1 + lane] = (uint64_t)__double_as_longlong((double)acc);
+    else if (lane == 12) dst[0] = cnt;
 }
 
 // Parity hook for the hand-written FP64 functions (fastmath.cuh): out[i] = f_which(in[i]).

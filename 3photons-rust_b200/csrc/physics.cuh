@@ -104,13 +104,20 @@ __device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMa
         alpha = e_total * (rs * rs);
         beta = rcp_t(m + r[3]);
     }
+    const F am = alpha * m;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const F rq = (q[k][0] * r[0] + q[k][1] * r[1]) + q[k][2] * r[2];
         p[k][3] = alpha * (r[3] * q[k][3] - rq);
-        const F b = beta * rq - q[k][3];
+        if (LITERAL) {
+            const F b = beta * rq - q[k][3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) p[k][c] = alpha * (m * q[k][c] + b * r[c]);
+            for (int c = 0; c < 3; ++c) p[k][c] = alpha * (m * q[k][c] + b * r[c]);
+        } else {
+            const F ab = alpha * (beta * rq - q[k][3]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p[k][c] = am * q[k][c] + ab * r[c];
+        }
     }
     if (SORT) {
 #pragma unroll
@@ -135,7 +142,7 @@ template <class F, bool SORT>
 __device__ __forceinline__ bool keep_event(const F p[3][4], const PhysParams<F>& P) {
     bool ok;
     if (SORT) ok = !(p[2][3] < P.e_min);
-    else ok = !(p[0][3] < P.e_min) && !(p[1][3] < P.e_min) && !(p[2][3] < P.e_min);  // event.rs:96-105
+    else ok = (p[0][3] >= P.e_min) & (p[1][3] >= P.e_min) & (p[2][3] >= P.e_min);  // event.rs:96-105 (min E < e_min rejects)
 #pragma unroll
     for (int k = 0; k < 3; ++k) ok = ok && !(abs_t(p[k][0]) > P.acut * p[k][3]);
 #pragma unroll
@@ -281,8 +288,9 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
         const Cplx<F> cc = cmul(Cplx<F>{cx[i], cy[i]}, Cplx<F>{cx[j], cy[j]});
         s2[k].re = g[i].re * A[j] + g[j].re * A[i] - (cc.re + cc.re);
         s2[k].im = g[i].im * A[j] + g[j].im * A[i] - (cc.im + cc.im);
-        const F dot = (p[i][0] * p[j][0] + p[i][1] * p[j][1]) + p[i][2] * p[j][2];
-        R[k] = (F)2 * (p[i][3] * p[j][3] - dot);
+        // |s_ij|^2 = 2 p_i.p_j = (p_i + p_j)^2 = (p_beams - p_k)^2 = e (e - 2 E_k): momentum conservation,
+        // which RAMBO's conformal transform guarantees to rounding error (evgen.rs:94-106)
+        R[k] = e * (e - (p[k][3] + p[k][3]));
     }
     // T_k = (E+X)(E-X), PQ2_k = (E+X)^2 + (E-X)^2, DPQ_k = (E+X)^2 - (E-X)^2   (units of e^2 pulled out)
     F T[3], S2[3], D2[3];

@@ -214,36 +214,25 @@ def main():
     value = n_events * args.steps / (dev_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ("e2e") -----------------------------
+    # What a caller of the reference's run_simulation gets: the merged accumulator of the whole run,
+    # finalized. Per rank: tp3_simulate_merged = launch + on-device ordered fold + D2H of one 104-byte
+    # accumulator into host memory; the rank partials are gathered (gloo-sized payload, sent over NCCL)
+    # and folded in rank order on rank 0, then finalize() runs on the host.
     acc_bytes = ctypes.sizeof(pkg.Acc)
 
     def e2e_step():
-        ctypes_out = sim.simulate_batches(lo, cnt, my_last)  # launch + D2H of 104 B per batch into host memory
+        mine = sim.simulate_merged(lo, cnt, my_last)
         if world > 1:
-            mine = torch.frombuffer(ctypes_out, dtype=torch.uint8).cuda()
-            sizes = [pkg.shard_range(nb, world, r)[1] * acc_bytes for r in range(world)]
-            parts = [torch.empty(s, dtype=torch.uint8, device="cuda") for s in sizes] if rank == 0 else None
-            dist.gather(mine, parts, dst=0)
+            t = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).cuda()
+            parts = [torch.empty(acc_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+            dist.gather(t, parts, dst=0)
             if rank != 0:
                 return None
-            raw = torch.cat(parts).cpu().numpy().tobytes()
-            accs = (pkg.Acc * nb).from_buffer_copy(raw)
+            accs = [pkg.Acc.from_buffer_copy(p.cpu().numpy().tobytes()) for p in parts]
+            total = pkg.fold(accs, cfg.flags)
         else:
-            accs = ctypes_out
-        total = merge_all(accs)
+            total = mine
         return pkg.finalize(cfg, total)
-
-    def merge_all(accs):
-        # left fold in batch order (sequential.rs:24-36), vectorised per field with the same order
-        import numpy as np
-        arr = np.frombuffer(accs, dtype=np.dtype([("n", "<u8"), ("f", "<f8", (12,))]))
-        total = pkg.Acc()
-        total.selected_events = int(arr["n"].sum())
-        f = np.add.accumulate(arr["f"], axis=0)[-1] if len(arr) else np.zeros(12)  # sequential left fold per field
-        for k in range(5):
-            total.spm2[k] = f[k]
-            total.vars[k] = f[5 + k]
-        total.sigma, total.variance = f[10], f[11]
-        return total
 
     fin = e2e_step()
     barrier()
@@ -276,8 +265,9 @@ def main():
                        "l2": "not applicable: no input tensors; the kernel reads a 281 KB jump table and writes 104 B per batch"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": nb * acc_bytes,
-                    "note": "C-ABI call with host output array; parameters travel as kernel arguments"},
+                    "d2h_bytes_per_step": world * acc_bytes,
+                    "note": "tp3_simulate_merged into a host tp3_acc + finalize(); parameters travel as kernel arguments, "
+                            "so there is no host->device payload"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64" if not f32 else "fp32", "achieved": achieved, "peak": peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,

@@ -1,0 +1,75 @@
+"""The N > 1 path on CPU: a world_size-2 gloo process group runs run_simulation_distributed with
+the ORACLE standing in for the GPU (no GPU here); the sharding, gather and ordered fold are the code
+under test.  The result must be bit-identical to the single-process fold and reproduce the golden
+file for the same event count."""
+import os
+import socket
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_package
+
+N_EVENTS = 45_000  # 5 batches over 2 ranks (2 + 3), the last one short
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _oracle_range_simulator(tp3, valeurs_text, n_events):
+    import ctypes as C
+    import oracle_lib
+
+    def simulate_range(first, n, last_len):
+        run = oracle_lib.run(valeurs_text, "", num_events=n_events, want_text=False)
+        out = (tp3.Acc * n)()
+        for i in range(n):
+            C.memmove(C.byref(out[i]), C.byref(run.per_batch[first + i]), C.sizeof(tp3.Acc))
+        # the range geometry handed to the GPU path must describe exactly these batches
+        nb, last = tp3.batch_layout(n_events)
+        assert last_len == (last if first + n == nb else tp3.EVENT_BATCH_SIZE)
+        return out
+
+    return simulate_range
+
+
+def _worker(rank, world, port, valeurs_text, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    tp3 = load_package()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    cfg = tp3.Configuration.parse(valeurs_text).with_num_events(N_EVENTS)
+    fin = tp3.run_simulation_distributed(cfg, _oracle_range_simulator(tp3, valeurs_text, N_EVENTS), world, rank, dist, "cpu")
+    if rank == 0:
+        q.put((fin.selected_events, fin.sigma, fin.res_data()))
+    else:
+        assert fin is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_run_is_bit_identical_to_single_process(tp3, oracle, valeurs_text, world):
+    cfg = tp3.Configuration.parse(valeurs_text).with_num_events(N_EVENTS)
+    single = tp3.run_simulation_distributed(cfg, _oracle_range_simulator(tp3, valeurs_text, N_EVENTS), 1, 0)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, valeurs_text, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    sel, sigma, res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (sel, sigma, res) == (single.selected_events, single.sigma, single.res_data())
+    # and the fold agrees with the oracle's own whole-run text
+    from numdiff import compare
+    assert compare(res, oracle.run(valeurs_text, "", num_events=N_EVENTS).res_data) == []

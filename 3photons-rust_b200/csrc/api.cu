@@ -500,7 +500,7 @@ int tp3_peak_probe(tp3_ctx* c, int which, double* tflops) {
 }
 
 int tp3_fastmath_probe(tp3_ctx* c, int which, uint32_t n, const double* in, double* out) {
-    if (!c || !in || !out || n == 0 || which < 0 || which > 8) return TP3_E_INVALID;
+    if (!c || !in || !out || n == 0 || which < 0 || which > 10) return TP3_E_INVALID;
     DeviceSlot& s = c->devs[0];
     TP3_CUDA(c, cudaSetDevice(s.dev));
     double *d_in = nullptr, *d_out = nullptr;

@@ -91,9 +91,8 @@ __device__ __forceinline__ double fast_neg_log(double x, const FastMathSmem* sm)
     return fma((double)k, kNegLn2, t.y) - p;
 }
 
-// sin(2 pi u), cos(2 pi u) for u in [0, 1]
-__device__ __forceinline__ void fast_sincos_2pi(double u, double& s, double& c) {
-    const double t = 4.0 * u;
+// sin(2 pi u), cos(2 pi u) given t = 4u in [0, 4] (quarter turns)
+__device__ __forceinline__ void fast_sincos_quarters(double t, double& s, double& c) {
     const double qd = rint(t);
     const int q = __double2int_rn(t);
     const double a = t - qd;  // exact, |a| <= 1/2
@@ -112,6 +111,15 @@ __device__ __forceinline__ void fast_sincos_2pi(double u, double& s, double& c) 
     const int sflip = (int)((unsigned)(q & 2) << 30), cflip = (int)((unsigned)((q + 1) & 2) << 30);
     s = __hiloint2double(__double2hiint(s0) ^ sflip, __double2loint(s0));
     c = __hiloint2double(__double2hiint(c0) ^ cflip, __double2loint(c0));
+}
+__device__ __forceinline__ void fast_sincos_2pi(double u, double& s, double& c) { fast_sincos_quarters(4.0 * u, s, c); }
+
+// (double)n * scale for 0 <= n < 2^32 with ONE FMA and no I2F: the word n dropped into the low half
+// of 2^52 is exactly 2^52 + n, and fma(2^52 + n, scale, -(2^52 * scale)) rounds the exact product
+// n * scale once — bit-identical to the conversion followed by a multiply (2^52 * scale is exact).
+__device__ __forceinline__ double u32_times(uint32_t n, double scale) {
+    const double d = __hiloint2double(0x43300000, (int)n);
+    return fma(d, scale, -4503599627370496.0 * scale);
 }
 
 }  // namespace tp3

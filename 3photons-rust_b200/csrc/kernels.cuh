@@ -106,9 +106,11 @@ template <class F> struct WarpRng<F, RNG_RANF> {
         n = n_next;
         return true;
     }
-    __device__ static F uniform(uint32_t w) {
-        if (sizeof(F) == 8) return (F)((double)(int)w * 1e-9);
-        return (F)((float)(int)w * 1e-9f);
+    // ranf.rs:99: (n as Float) * 1e-9; `quarters` asks for 4u instead (an exact scaling)
+    __device__ static F uniform(uint32_t w, bool quarters) {
+        if (sizeof(F) == 8) return (F)u32_times(w, quarters ? 4e-9 : 1e-9);
+        const float u = (float)(int)w * 1e-9f;
+        return (F)(quarters ? 4.0f * u : u);
     }
 };
 
@@ -133,10 +135,10 @@ template <class F, class Lane> struct XoshiroWarpRng {
     }
 };
 template <> struct WarpRng<double, RNG_XOSHIRO> : XoshiroWarpRng<double, Xoshiro256Lane> {
-    __device__ static double uniform(uint64_t w) { return to_uniform_xo(w); }
+    __device__ static double uniform(uint64_t w, bool quarters) { return (quarters ? 4.0 : 1.0) * to_uniform_xo(w); }
 };
 template <> struct WarpRng<float, RNG_XOSHIRO> : XoshiroWarpRng<float, Xoshiro128Lane> {
-    __device__ static float uniform(uint32_t w) { return to_uniform_xo(w); }
+    __device__ static float uniform(uint32_t w, bool quarters) { return (quarters ? 4.0f : 1.0f) * to_uniform_xo(w); }
 };
 
 template <class F> struct LaneAcc {
@@ -205,9 +207,9 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(con
         if (rng.event_of(it, lane) >= 0) {
             F u[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
+            for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
             gen_event<F, kSort, LITERAL>(u, P.e_total, &sm.fm, p);
-            keep = keep_event<F, kSort>(p, P);
+            keep = keep_event<F, kSort, LITERAL>(p, P);
         }
         if (LITERAL) {
             if (keep) {
@@ -311,10 +313,10 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
             for (int j = 0; j < 12; ++j) d.words[(size_t)e * 12 + j] = (uint64_t)w[j];
         if (!d.momenta) continue;
         F u[12];
-        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j]);
+        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
         F p[3][4];
         gen_event<F, SORT, LITERAL>(u, P.e_total, &sm.fm, p);
-        const bool k = keep_event<F, SORT>(p, P);
+        const bool k = keep_event<F, SORT, LITERAL>(p, P);
         F m[5] = {0, 0, 0, 0, 0};
         if (k) {
             if (LITERAL) me_literal<F>(p, P, m);
@@ -411,6 +413,8 @@ __global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __res
             case 6: fast_sqrt_rsqrt(x, a, b); break;
             case 7: a = mufu_rcp(x); break;
             case 8: a = mufu_rsqrt(x); break;
+            case 9: a = u32_times((uint32_t)x, 1e-9); break;
+            case 10: a = u32_times((uint32_t)x, 4e-9); break;
         }
         out[i] = a;
     }

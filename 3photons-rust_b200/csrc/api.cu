@@ -10,6 +10,7 @@
 
 #include "jump_tables.hpp"
 #include "kernels.cuh"
+#include "faster_evgen.cuh"
 
 using namespace tp3;
 
@@ -30,6 +31,8 @@ struct DeviceSlot {
     tp3_acc* d_out = nullptr;
     size_t out_cap = 0;
     tp3_acc* d_merged = nullptr;
+    uint32_t* d_fe_ranf_states = nullptr;  // faster-evgen: [n][57] batch start states from the host scheduler
+    size_t fe_states_cap = 0;
     // last launch
     uint64_t last_first = 0, last_n = 0;
 };
@@ -48,6 +51,12 @@ struct tp3_ctx {
     std::vector<uint64_t> xo_lane_polys;    // [32][4]
     uint64_t xo_base[4];
     int xo_digits = 0;
+    // faster-evgen, sequential stream: the host scheduler's generator, positioned at the start of batch fe_pos
+    uint64_t fe_pos = 0;
+    uint32_t fe_ranf[56];
+    int fe_ranf_index = 55;
+    uint64_t fe_xo[4];
+    bool fe_ready = false;
 };
 
 namespace {
@@ -145,6 +154,96 @@ void build_xoshiro_tables(tp3_ctx* c) {
     }
 }
 
+
+// ---- faster-evgen: the scheduler's pre-advance of the master generator (evgen.rs:257-267) -------------
+// Host code on purpose: this IS what the reference's scheduler thread does between spawning batch tasks
+// (multi_threading.rs:59-64), and the sequential scheduler gets the same effect by running the batches in
+// order.  The accept / re-roll test must be evaluated exactly as the reference does (no FMA, run's Float).
+template <class F> struct FeHostRanf {
+    uint32_t* n;  // numbers[0..55]
+    int& index;
+    void reset() {
+        for (int i = 1; i < 25; ++i) { int32_t v = (int32_t)n[i] - (int32_t)n[i + 31]; n[i] = (uint32_t)(v < 0 ? v + (int32_t)RANF_MOD : v); }
+        for (int i = 25; i < 56; ++i) { int32_t v = (int32_t)n[i] - (int32_t)n[i - 24]; n[i] = (uint32_t)(v < 0 ? v + (int32_t)RANF_MOD : v); }
+    }
+    template <int N> void take(F* out) {
+        if (index < N) { reset(); index = 55; }
+        index -= N;
+        for (int i = 0; i < N; ++i) out[i] = (F)(int32_t)n[index + 1 + i] * (F)1e-9;
+    }
+};
+template <class F> struct FeHostXo;
+template <> struct FeHostXo<double> {
+    Xoshiro256 g;
+    template <int N> void take(double* out) {
+        for (int i = 0; i < N; ++i) { const uint64_t r = g.s[0] + g.s[3]; g.step(); out[i] = (double)(r >> 11) * (1.0 / 9007199254740992.0); }
+    }
+};
+template <> struct FeHostXo<float> {
+    Xoshiro128 g;
+    template <int N> void take(float* out) {
+        for (int i = 0; i < N; ++i) { const uint32_t r = g.s[0] + g.s[3]; g.step(); out[i] = (float)(r >> 8) * (1.0f / 16777216.0f); }
+    }
+};
+template <class F, class Gen> void fe_skip_events(Gen& gen, uint64_t n_events) {
+    for (uint64_t e = 0; e < n_events; ++e) {
+        F u9[9], v6[6];
+        gen.template take<9>(u9);
+        gen.template take<6>(v6);
+        for (int k = 0; k < 3; ++k) {
+            volatile F x = (F)2 * v6[k] - (F)1, y = (F)2 * v6[3 + k] - (F)1;
+            volatile F xx = x * x, yy = y * y;
+            F r2 = xx + yy;
+            while (r2 > (F)1) {
+                F w[2];
+                gen.template take<2>(w);
+                x = (F)2 * w[0] - (F)1;
+                y = (F)2 * w[1] - (F)1;
+                xx = x * x;
+                yy = y * y;
+                r2 = xx + yy;
+            }
+        }
+    }
+}
+
+// Start states of batches [first, first + n) of the sequential stream -> host arrays.
+void fe_host_states(tp3_ctx* c, uint64_t first, uint64_t n, std::vector<uint32_t>& ranf_out, std::vector<uint64_t>& xo_out) {
+    const bool f32 = c->params.flags & TP3_F32, xo = c->params.flags & TP3_STANDARD_RANDOM;
+    if (!c->fe_ready || c->fe_pos > first) {  // (re)start from the seeded generator
+        if (xo) {
+            for (int i = 0; i < 4; ++i) c->fe_xo[i] = c->xo_base[i];
+        } else {
+            c->fe_ranf[0] = 0;
+            ranf_seed_state(RANF_DEFAULT_SEED, c->fe_ranf + 1);
+            c->fe_ranf_index = 55;
+        }
+        c->fe_pos = 0;
+        c->fe_ready = true;
+    }
+    auto skip = [&](uint64_t events) {
+        if (xo) {
+            if (f32) { FeHostXo<float> g; for (int i = 0; i < 4; ++i) g.g.s[i] = (uint32_t)c->fe_xo[i]; fe_skip_events<float>(g, events); for (int i = 0; i < 4; ++i) c->fe_xo[i] = g.g.s[i]; }
+            else { FeHostXo<double> g; for (int i = 0; i < 4; ++i) g.g.s[i] = c->fe_xo[i]; fe_skip_events<double>(g, events); for (int i = 0; i < 4; ++i) c->fe_xo[i] = g.g.s[i]; }
+        } else {
+            if (f32) { FeHostRanf<float> g{c->fe_ranf, c->fe_ranf_index}; fe_skip_events<float>(g, events); }
+            else { FeHostRanf<double> g{c->fe_ranf, c->fe_ranf_index}; fe_skip_events<double>(g, events); }
+        }
+    };
+    while (c->fe_pos < first) { skip(TP3_EVENT_BATCH_SIZE); ++c->fe_pos; }
+    if (xo) xo_out.resize(n * 4); else ranf_out.resize(n * 57);
+    for (uint64_t b = 0; b < n; ++b) {
+        if (xo) std::memcpy(&xo_out[b * 4], c->fe_xo, 32);
+        else { std::memcpy(&ranf_out[b * 57], c->fe_ranf, 56 * 4); ranf_out[b * 57 + 56] = (uint32_t)c->fe_ranf_index; }
+        skip(TP3_EVENT_BATCH_SIZE);  // every batch but the last of a run is full; a short last batch ends the run
+        ++c->fe_pos;
+    }
+}
+
+template <class F, int RNG> void launch_fe(const FeArgs& a, const tp3_params& p, cudaStream_t st) {
+    faster_evgen_kernel<F, RNG><<<(unsigned)((a.n_batches + kFeThreads - 1) / kFeThreads), kFeThreads, 0, st>>>(a, phys_params<F>(p));
+}
+
 int ensure_out(tp3_ctx* c, DeviceSlot& s, uint64_t n) {
     if (s.out_cap < n) {
         if (s.d_out) TP3_CUDA(c, cudaFree(s.d_out));
@@ -208,8 +307,28 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
             return TP3_E_INVALID;
         }
     }
+    const bool faster = c->params.flags & TP3_FASTER_EVGEN;
+    const bool seq_faster = faster && !(c->params.flags & TP3_FASTER_THREADING);
+    std::vector<uint32_t> fe_ranf;
+    std::vector<uint64_t> fe_xo;
+    if (seq_faster) {
+        fe_host_states(c, first, n, fe_ranf, fe_xo);
+        if (!fe_ranf.empty()) {
+            if (s.fe_states_cap < n) {
+                if (s.d_fe_ranf_states) TP3_CUDA(c, cudaFree(s.d_fe_ranf_states));
+                s.d_fe_ranf_states = nullptr;
+                s.fe_states_cap = 0;
+                TP3_CUDA(c, cudaMalloc(&s.d_fe_ranf_states, n * 57 * sizeof(uint32_t)));
+                s.fe_states_cap = n;
+            }
+            TP3_CUDA(c, cudaMemcpyAsync(s.d_fe_ranf_states, fe_ranf.data(), n * 57 * 4, cudaMemcpyHostToDevice, s.stream));
+        } else {
+            TP3_CUDA(c, cudaMemcpyAsync(s.d_xo_states, fe_xo.data(), n * 32, cudaMemcpyHostToDevice, s.stream));
+        }
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // the host vectors die at the end of this call
+    }
     SimArgs a = make_args(c, s, first, n, last_len);
-    if (c->params.flags & TP3_STANDARD_RANDOM) {
+    if ((c->params.flags & TP3_STANDARD_RANDOM) && !seq_faster) {
         const unsigned blocks = (unsigned)((n + 127) / 128);
         if (c->params.flags & TP3_F32)
             xoshiro_seed_kernel<Xoshiro128Lane><<<blocks, 128, 0, s.stream>>>(first, n, s.d_xo_digit_polys, c->xo_digits,
@@ -221,7 +340,23 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
                                                                               c->xo_base[3], s.d_xo_states);
         ++c->launches;
     }
-    pick_sim(c->params)(a, c->params, s.stream);
+    if (faster) {
+        FeArgs f;
+        std::memset(&f, 0, sizeof f);
+        f.first_batch = first;
+        f.n_batches = n;
+        f.last_batch_len = last_len;
+        f.jump_seeding = a.jump_seeding;
+        f.ranf_states = s.d_fe_ranf_states;
+        f.xo_states = s.d_xo_states;
+        f.out = s.d_out;
+        f.ranf_seed = RANF_DEFAULT_SEED;
+        const bool f32 = c->params.flags & TP3_F32, xo = c->params.flags & TP3_STANDARD_RANDOM;
+        if (f32) { if (xo) launch_fe<float, RNG_XOSHIRO>(f, c->params, s.stream); else launch_fe<float, RNG_RANF>(f, c->params, s.stream); }
+        else { if (xo) launch_fe<double, RNG_XOSHIRO>(f, c->params, s.stream); else launch_fe<double, RNG_RANF>(f, c->params, s.stream); }
+    } else {
+        pick_sim(c->params)(a, c->params, s.stream);
+    }
     ++c->launches;
     TP3_CUDA(c, cudaGetLastError());
     s.last_first = first;
@@ -246,10 +381,6 @@ const char* tp3_last_error(const tp3_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx** out) {
     if (!params || !out || n_dev < 1) {
         g_create_error = "tp3_create: bad arguments";
-        return TP3_E_INVALID;
-    }
-    if (params->flags & TP3_FASTER_EVGEN) {
-        g_create_error = "faster-evgen is not available on the GPU path yet";
         return TP3_E_INVALID;
     }
     int count = 0;
@@ -311,6 +442,7 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_xo_states);
         cudaFree(s.d_out);
         cudaFree(s.d_merged);
+        cudaFree(s.d_fe_ranf_states);
     }
     delete c;
 }
@@ -407,6 +539,10 @@ int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_le
 
 static int run_dump(tp3_ctx* c, uint64_t batch, uint32_t n_events, uint64_t* words, double* momenta, int32_t* kept,
                     double* m2) {
+    if (c->params.flags & TP3_FASTER_EVGEN) {
+        c->err = "per-event dumps are not available under faster-evgen (draw positions are data dependent)";
+        return TP3_E_INVALID;
+    }
     DeviceSlot& s = c->devs[0];
     TP3_CUDA(c, cudaSetDevice(s.dev));
     int rc = ensure_out(c, s, 1);

@@ -69,28 +69,9 @@ template <class F> struct PhysParams {
 // u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187).
 // In the fast variant the phi slot holds 4u (quarter turns; an exact scaling) instead of u.
 // p[k] = (X, Y, Z, E) of photon k, optionally sorted by decreasing E (evgen.rs:109-118).
+// Conformal transform of RAMBO to the total energy + optional sort (evgen.rs:94-118)
 template <class F, bool SORT, bool LITERAL>
-__device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMathSmem* fm, F p[3][4]) {
-    F q[3][4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const F c = (F)2 * u[4 * k] - (F)1;
-        const F e = u[4 * k + 2] * u[4 * k + 3];
-        F sphi, cphi, st, en;
-        if (LITERAL) {
-            sincos_t(Num<F>::TWO_PI * u[4 * k + 1], &sphi, &cphi);
-            st = sqrt_t((F)1 - c * c);
-            en = -log_t(e + Num<F>::MIN_POSITIVE);
-        } else {
-            sincos_quarters_t(u[4 * k + 1], &sphi, &cphi);
-            st = sqrt_pos_t((F)1 - c * c);
-            en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
-        }
-        q[k][0] = en * (st * sphi);
-        q[k][1] = en * (st * cphi);
-        q[k][2] = en * c;
-        q[k][3] = en;
-    }
+__device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, F p[3][4]) {
     F r[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) r[c] = (q[0][c] + q[1][c]) + q[2][c];
@@ -135,6 +116,55 @@ __device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMa
                 }
             }
     }
+}
+
+
+template <class F, bool SORT, bool LITERAL>
+__device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMathSmem* fm, F p[3][4]) {
+    F q[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const F c = (F)2 * u[4 * k] - (F)1;
+        const F e = u[4 * k + 2] * u[4 * k + 3];
+        F sphi, cphi, st, en;
+        if (LITERAL) {
+            sincos_t(Num<F>::TWO_PI * u[4 * k + 1], &sphi, &cphi);
+            st = sqrt_t((F)1 - c * c);
+            en = -log_t(e + Num<F>::MIN_POSITIVE);
+        } else {
+            sincos_quarters_t(u[4 * k + 1], &sphi, &cphi);
+            st = sqrt_pos_t((F)1 - c * c);
+            en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
+        }
+        q[k][0] = en * (st * sphi);
+        q[k][1] = en * (st * cphi);
+        q[k][2] = en * c;
+        q[k][3] = en;
+    }
+    conformal_transform<F, SORT, LITERAL>(q, e_total, p);
+}
+
+// `faster-evgen` raw generation (evgen.rs:143-173): cos_theta and exp(-E) from 9 uniforms, the azimuth
+// from a point (x, y) of the unit disc with squared radius r2 (the rejection loop lives in the caller,
+// because it decides how many random numbers the event consumes).
+template <class F, bool SORT>
+__device__ __forceinline__ void gen_event_faster(const F u9[9], const F xy[3][2], const F r2[3], F e_total,
+                                                 const FastMathSmem* fm, F p[3][4]) {
+    F q[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const F c = (F)2 * u9[k] - (F)1;
+        const F e = u9[3 + k] * u9[6 + k];
+        const F st = sqrt_pos_t((F)1 - c * c);
+        const F en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
+        F s_, n;
+        sqrt_rsqrt_t(r2[k], &s_, &n);  // n = 1 / sqrt(r2)
+        q[k][0] = en * (st * (xy[k][0] * n));
+        q[k][1] = en * (st * (xy[k][1] * n));
+        q[k][2] = en * c;
+        q[k][3] = en;
+    }
+    conformal_transform<F, SORT, false>(q, e_total, p);
 }
 
 // ------------------------------------------------------------------------------ cuts

@@ -287,6 +287,60 @@ def test_default_run_f32(tp3, valeurs_text, features, suffix):
         assert abs(g - w) <= F32_REL_RUN * abs(w) + 1e-4 * abs(w), f"line {ln}: {g} vs {w}"
 
 
+# ------------------------------------------------------------------------------ faster-evgen
+@pytest.mark.parametrize("features", ["faster-evgen", "faster-evgen,no-photon-sorting", "faster-evgen,standard-random",
+                                      "faster-evgen,multi-threading,faster-threading",
+                                      "faster-evgen,standard-random,multi-threading,faster-threading"])
+def test_faster_evgen_batches_match_oracle(sims, oracle, valeurs_text, features):
+    """faster-evgen consumes a data-dependent number of random numbers per event (rejection sampling on the
+    unit disc + RANF's discard-the-rest-of-the-round rule), so this also proves that every accept / re-roll
+    decision and every batch start position equals the reference's: one differing decision shifts the whole
+    stream and nothing downstream would agree to 1e-10."""
+    nb = 40
+    run = oracle.run(valeurs_text, features, threads=8, num_events=nb * 10000, want_text=False)
+    scale = (nb * 10000) / 1e7
+    accs = sims(features).simulate_batches(0, nb)
+    for b in range(nb):
+        want = run.per_batch[b]
+        want.sigma *= scale
+        want.variance *= scale * scale
+        assert accs[b].selected_events == want.selected_events, f"batch {b}"
+        assert_acc_close(accs[b], want, REL_F64, what=f"batch {b}")
+    # the host scheduler's pre-advance continues incrementally and can restart: same bits for a sub-range
+    part = sims(features).simulate_batches(17, 5)
+    assert bytes(part) == bytes((type(part))(*accs[17:22]))
+    again = sims(features).simulate_batches(3, 4)
+    assert bytes(again) == bytes((type(again))(*accs[3:7]))
+
+
+def test_faster_evgen_f32_batches(sims, oracle, valeurs_text):
+    nb = 8
+    features = "faster-evgen,f32"
+    run = oracle.run(valeurs_text, features, threads=8, num_events=nb * 10000, want_text=False)
+    scale = (nb * 10000) / 1e7
+    accs = sims(features).simulate_batches(0, nb)
+    for b in range(nb):
+        want = run.per_batch[b]
+        assert abs(accs[b].selected_events - want.selected_events) <= F32_SELECTED_SLACK_BATCH
+        g, w = acc_fields(accs[b]), acc_fields(want)
+        w[10] *= scale
+        w[11] *= scale * scale
+        for k in (0, 1, 2, 5, 6, 7, 10, 11):
+            assert abs(g[k] - w[k]) <= 8e-4 * abs(w[k]), f"batch {b} field {k}"
+
+
+@pytest.mark.parametrize("features", ["faster-evgen", "faster-evgen,no-photon-sorting"])
+def test_faster_evgen_default_run_matches_golden(tp3, valeurs_text, features):
+    """BASELINE configs[3]: faster-evgen (+ no-photon-sorting, which has no golden of its own and provably
+    prints the same numbers) against reference/res.data-features_faster-evgen: 7 080 375 selected, 1e-10."""
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    fin = tp3.run_simulation(cfg)
+    want = golden("res.data-features_faster-evgen")
+    assert fin.selected_events == 7080375
+    assert compare(fin.res_data(), want, rel=REL_F64) == []
+    assert compare(fin.stdout(), golden("stdout.log-features_faster-evgen"), rel=1e-5) == []
+
+
 def test_whole_program_cli_surface(tp3, valeurs_text, tmp_path):
     """tp3_run = main.rs:75-145: valeurs in, stdout text + res.data / res.times / pil.mc out."""
     (tmp_path / "valeurs").write_text(valeurs_text)

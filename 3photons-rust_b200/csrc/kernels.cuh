@@ -94,10 +94,10 @@ template <class F> struct WarpRng<F, RNG_RANF> {
         const int e = 32 * it + lane;
         return e < n ? e : -1;
     }
-    __device__ void raw(int it, int lane, uint32_t w[12]) {
-        if (it > 0) s.advance(kWarpDraws, lane);
-        s.draws(lane, w);
-    }
+    __device__ __forceinline__ void draws(int, int lane, uint32_t w[12]) { s.draws(lane, w); }
+    // Pipelined refill for the next warp iteration (see RanfWarpStream::begin_next)
+    __device__ __forceinline__ void begin_next(int lane) { s.begin_next(lane); }
+    template <int K> __device__ __forceinline__ void tick(int lane) { s.template tick<K>(lane); }
     // The next batch of the sequential stream starts right after this batch's last draw: step past
     // the (possibly partial) last warp iteration instead of jumping again.
     __device__ bool next_batch(const SimArgs& a, int n_next, int lane) {
@@ -129,10 +129,12 @@ template <class F, class Lane> struct XoshiroWarpRng {
     __device__ int iterations() const { return min(n, kLaneEvents); }
     __device__ int event_of(int it, int) const { return lo + it < hi ? lo + it : -1; }
     __device__ bool next_batch(const SimArgs&, int, int) { return false; }  // re-seeded from the batch state
-    template <class W> __device__ void raw(int, int, W w[12]) {
+    template <class W> __device__ __forceinline__ void draws(int, int, W w[12]) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) w[j] = g.next();
     }
+    __device__ __forceinline__ void begin_next(int) {}
+    template <int K> __device__ __forceinline__ void tick(int) {}
 };
 template <> struct WarpRng<double, RNG_XOSHIRO> : XoshiroWarpRng<double, Xoshiro256Lane> {
     __device__ static double uniform(uint64_t w, bool quarters) { return (quarters ? 4.0 : 1.0) * to_uniform_xo(w); }
@@ -162,6 +164,16 @@ template <class F> struct LaneAcc {
         }
         sigma += w;
         variance += w * w;
+    }
+};
+
+// Tick hook handed to gen_event: step K of the pipelined refill, if there is a next iteration.
+template <class F, int RNG> struct RngTick {
+    WarpRng<F, RNG>& rng;
+    int lane;
+    bool more;
+    template <int K> __device__ __forceinline__ void at() {
+        if (more) rng.template tick<K>(lane);
     }
 };
 
@@ -201,17 +213,23 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(con
     const int n_it = rng.iterations();
     for (int it = 0; it < n_it; ++it) {
         Word w[12];
-        rng.raw(it, lane, w);
-        bool keep = false;
-        F p[3][4];
-        if (rng.event_of(it, lane) >= 0) {
-            F u[12];
+        rng.draws(it, lane, w);
+        // The random numbers of the NEXT iteration are regenerated in seven steps interleaved with this
+        // iteration's physics (each step is a short serial chain; alone it would stall the warp).
+        const bool more = it + 1 < n_it;
+        if (more) rng.begin_next(lane);
+        RngTick<F, RNG> tick{rng, lane, more};
+        F u[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
-            gen_event<F, kSort, LITERAL>(u, P.e_total, &sm.fm, p);
-            keep = keep_event<F, kSort, LITERAL>(p, P);
-        }
+        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
+        F p[3][4];
+        gen_event<F, kSort, LITERAL>(u, P.e_total, &sm.fm, p, tick);  // lanes past the end compute on valid but unused draws
+        tick.template at<4>();
+        const bool keep = rng.event_of(it, lane) >= 0 && keep_event<F, kSort, LITERAL>(p, P);
+        tick.template at<5>();
         if (LITERAL) {
+            tick.template at<6>();
+            tick.template at<7>();
             if (keep) {
                 F m[5];
                 me_literal<F>(p, P, m);
@@ -232,6 +250,8 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(con
         }
         q_count += __popc(mask);
         __syncwarp();
+        tick.template at<6>();
+        tick.template at<7>();
         if (q_count >= 32) {
             const int slot = (q_head + lane) & (kQueue - 1);
             F e[3][4];
@@ -306,7 +326,12 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
     const int n_it = rng.iterations();
     for (int it = 0; it < n_it; ++it) {
         Word w[12];
-        rng.raw(it, lane, w);
+        rng.draws(it, lane, w);
+        if (it + 1 < n_it) {
+            rng.begin_next(lane);
+            rng.template tick<1>(lane); rng.template tick<2>(lane); rng.template tick<3>(lane); rng.template tick<4>(lane);
+            rng.template tick<5>(lane); rng.template tick<6>(lane); rng.template tick<7>(lane);
+        }
         const int e = rng.event_of(it, lane);
         if (e < 0 || e >= (int)d.n_events) continue;
         if (d.words)
@@ -315,7 +340,8 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
         F u[12];
         for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
         F p[3][4];
-        gen_event<F, SORT, LITERAL>(u, P.e_total, &sm.fm, p);
+        NoTick no_tick;
+        gen_event<F, SORT, LITERAL>(u, P.e_total, &sm.fm, p, no_tick);
         const bool k = keep_event<F, SORT, LITERAL>(p, P);
         F m[5] = {0, 0, 0, 0, 0};
         if (k) {

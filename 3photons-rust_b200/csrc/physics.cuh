@@ -119,28 +119,42 @@ __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, 
 }
 
 
-template <class F, bool SORT, bool LITERAL>
-__device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMathSmem* fm, F p[3][4]) {
-    F q[3][4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const F c = (F)2 * u[4 * k] - (F)1;
-        const F e = u[4 * k + 2] * u[4 * k + 3];
-        F sphi, cphi, st, en;
-        if (LITERAL) {
-            sincos_t(Num<F>::TWO_PI * u[4 * k + 1], &sphi, &cphi);
-            st = sqrt_t((F)1 - c * c);
-            en = -log_t(e + Num<F>::MIN_POSITIVE);
-        } else {
-            sincos_quarters_t(u[4 * k + 1], &sphi, &cphi);
-            st = sqrt_pos_t((F)1 - c * c);
-            en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
-        }
-        q[k][0] = en * (st * sphi);
-        q[k][1] = en * (st * cphi);
-        q[k][2] = en * c;
-        q[k][3] = en;
+// Hook called between the stages of an event so that independent work of the same warp (the next
+// iteration's random numbers) can be interleaved with the FP64 chains; NoTick does nothing.
+struct NoTick {
+    template <int K> __device__ __forceinline__ void at() const {}
+};
+
+// One photon of generate_raw (evgen.rs:182-206): u = (cos_theta, phi, r, r') uniforms -> q = (X, Y, Z, E)
+template <class F, bool LITERAL>
+__device__ __forceinline__ void raw_photon(const F* u, const FastMathSmem* fm, F q[4]) {
+    const F c = (F)2 * u[0] - (F)1;
+    const F e = u[2] * u[3];
+    F sphi, cphi, st, en;
+    if (LITERAL) {
+        sincos_t(Num<F>::TWO_PI * u[1], &sphi, &cphi);
+        st = sqrt_t((F)1 - c * c);
+        en = -log_t(e + Num<F>::MIN_POSITIVE);
+    } else {
+        sincos_quarters_t(u[1], &sphi, &cphi);
+        st = sqrt_pos_t((F)1 - c * c);
+        en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
     }
+    q[0] = en * (st * sphi);
+    q[1] = en * (st * cphi);
+    q[2] = en * c;
+    q[3] = en;
+}
+
+template <class F, bool SORT, bool LITERAL, class Tick>
+__device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMathSmem* fm, F p[3][4], Tick& tick) {
+    F q[3][4];
+    raw_photon<F, LITERAL>(u, fm, q[0]);
+    tick.template at<1>();
+    raw_photon<F, LITERAL>(u + 4, fm, q[1]);
+    tick.template at<2>();
+    raw_photon<F, LITERAL>(u + 8, fm, q[2]);
+    tick.template at<3>();
     conformal_transform<F, SORT, LITERAL>(q, e_total, p);
 }
 

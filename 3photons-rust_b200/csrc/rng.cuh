@@ -66,7 +66,10 @@ struct RanfWarpStream {
     uint32_t* buf;
     int shift;     // word offset of round 0 in buf (0..3)
     int p0;        // word offset in buf of the first draw of the current warp iteration; p0 % 4 == 0
-    uint32_t v, w; // this lane's draws r = lane and r = lane + 32 of the newest generated round
+    // This lane's three slots of the newest generated round: slot lane+1 (lanes < 24), slot lane+25
+    // (lanes < 24) and slot lane+49 (lanes < 7). The reference's in-place update (ranf.rs:106-119) then
+    // chains inside the lane: new[i] = old[i] - new[i-24] reads the value this lane has just produced.
+    uint32_t va, vb, vc;
 
     // base_y: round 0 of the generator (55 words, slot order) in shared or global memory;
     // d0: index of this warp's first draw in that generator's stream.
@@ -108,48 +111,89 @@ struct RanfWarpStream {
         // slot order -> consumption order: draw r of the round is slot 55 - r
         shift = (-q0) & 3;
         p0 = shift + q0;
-        v = win[kRanfLag - 1 - lane];
-        w = (lane < kRanfLag - 32) ? win[kRanfLag - 1 - 32 - lane] : 0u;
-        buf[shift + lane] = v;
-        if (lane < kRanfLag - 32) buf[shift + 32 + lane] = w;
+        const int l24 = lane < 24 ? lane : 23;  // lanes >= 24 shadow lane 23: same values, same addresses
+        va = win[l24];
+        vb = win[24 + l24];
+        vc = win[lane < 7 ? 48 + lane : 48];
+        store_round(buf + shift, lane);
         __syncwarp();
         refill(1, lane);
     }
 
-    // Round K of the buffer from round K-1, in consumption order r = 55 - slot:
-    //   r in [31,54]: z'[r] = z[r] - z[r-31]
-    //   r in [ 7,30]: z'[r] = z[r] - z[r+24] + z[r-7]
-    //   r in [ 0, 6]: z'[r] = z[r] - z[r+24] + z[r+48] - z[r+17]
-    // Branch free: every lane loads all four operands from valid addresses and masks the terms its
-    // class does not have (a - 0 and a + 0 pass through ranf_sub / ranf_add unchanged).
-    template <int K> __device__ __forceinline__ void gen_round(const uint32_t* pl, const uint32_t* pa, const uint32_t* pb,
-                                                               uint32_t* po, uint32_t m7, uint32_t m31, bool p23) {
+    // st.shared predicated in one instruction (the compiler turns `if (p) *a = v` into a branch here)
+    __device__ __forceinline__ static void store_if(bool p, uint32_t* addr, uint32_t val) {
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u32 [%0], %1; }" ::"r"((uint32_t)__cvta_generic_to_shared(addr)),
+                     "r"(val), "r"((uint32_t)p)
+                     : "memory");
+    }
+
+    // Write this lane's three slots of a round to its place in consumption order (r = 55 - slot).
+    __device__ __forceinline__ void store_round(uint32_t* round0, int lane) const {
+        uint32_t* pn = round0 - (lane < 24 ? lane : 23);
+        pn[54] = va;                     // slot lane + 1
+        pn[30] = vb;                     // slot lane + 25
+        store_if(lane < 7, pn + 6, vc);  // slot lane + 49
+    }
+
+    // Round K of the buffer from round K-1 (ranf.rs:106-119), three dependent steps inside each lane:
+    //   slots  1..24: new[i] = old[i] - old[i+31]      one shared load (slot lane+32 is draw 23 - lane)
+    //   slots 25..48: new[i] = old[i] - new[i-24]      = vb - (the va just computed)
+    //   slots 49..55: new[i] = old[i] - new[i-24]      = vc - (the vb just computed)
+    template <int K> __device__ __forceinline__ void gen_round(uint32_t* pn, int lane) {
         constexpr int B = (K - 1) * kRanfLag;
-        const uint32_t b = pa[B], c = pb[B], d = pl[B + 17], e = pl[B + 1];
-        const uint32_t t1 = ranf_sub(v, b);
-        const uint32_t t2 = ranf_sub(c, d & m7) & m31;
-        v = ranf_add(t1, t2);
-        w = ranf_sub(w, e);
-        po[B + kRanfLag] = v;
-        if (p23) po[B + kRanfLag + 32] = w;
+        va = ranf_sub(va, pn[B + 23]);
+        vb = ranf_sub(vb, va);
+        vc = ranf_sub(vc, vb);
+        pn[B + kRanfLag + 54] = va;
+        pn[B + kRanfLag + 30] = vb;
+        store_if(lane < 7, pn + B + kRanfLag + 6, vc);
         __syncwarp();
     }
 
+    __device__ __forceinline__ uint32_t* lane_base(int lane) const { return buf + shift - (lane < 24 ? lane : 23); }
+
     // Generate rounds first..7 of the buffer (warp-uniform first >= 1).
     __device__ __forceinline__ void refill(int first, int lane) {
-        uint32_t* po = buf + shift + lane;
-        const uint32_t* pl = po;
-        const uint32_t* pa = pl + (lane == 31 ? -31 : 24);
-        const uint32_t* pb = pl + (lane >= 7 ? -7 : 48);
-        const uint32_t m7 = lane < 7 ? 0xffffffffu : 0u, m31 = lane < 31 ? 0xffffffffu : 0u;
-        const bool p23 = lane < kRanfLag - 32;
-        if (first <= 1) gen_round<1>(pl, pa, pb, po, m7, m31, p23);
-        if (first <= 2) gen_round<2>(pl, pa, pb, po, m7, m31, p23);
-        if (first <= 3) gen_round<3>(pl, pa, pb, po, m7, m31, p23);
-        if (first <= 4) gen_round<4>(pl, pa, pb, po, m7, m31, p23);
-        if (first <= 5) gen_round<5>(pl, pa, pb, po, m7, m31, p23);
-        if (first <= 6) gen_round<6>(pl, pa, pb, po, m7, m31, p23);
-        gen_round<7>(pl, pa, pb, po, m7, m31, p23);
+        uint32_t* pn = lane_base(lane);
+        if (first <= 1) gen_round<1>(pn, lane);
+        if (first <= 2) gen_round<2>(pn, lane);
+        if (first <= 3) gen_round<3>(pn, lane);
+        if (first <= 4) gen_round<4>(pn, lane);
+        if (first <= 5) gen_round<5>(pn, lane);
+        if (first <= 6) gen_round<6>(pn, lane);
+        gen_round<7>(pn, lane);
+    }
+
+    // Pipelined form of advance(384): begin_next() right after the current iteration's draws have been
+    // read, then tick<1..7>() spread over the event physics, so that the serial latency of a round
+    // (load -> 3 x (sub, min) -> store -> warp fence) hides behind independent FP64 work of the same warp.
+    int pend_first;
+    __device__ __forceinline__ void begin_next(int lane) {
+        __syncwarp();
+        const int rel = p0 - shift + kWarpDraws;        // in [384, 438]
+        const int k = rel >= 7 * kRanfLag ? 7 : 6;
+        const int new_rel = rel - k * kRanfLag;
+        const int new_shift = (-new_rel) & 3;
+        if (k == 7) {
+            store_round(buf + new_shift, lane);
+        } else {  // once every 55 iterations two rounds stay: move round 6 through registers
+            const int l24 = lane < 24 ? lane : 23;
+            const uint32_t* src = buf + shift + 6 * kRanfLag - l24;
+            const uint32_t a = src[54], b = src[30], c = src[6];
+            __syncwarp();
+            uint32_t* dst = buf + new_shift - l24;
+            dst[54] = a;
+            dst[30] = b;
+            store_if(lane < 7, dst + 6, c);
+            store_round(buf + new_shift + kRanfLag, lane);
+        }
+        shift = new_shift;
+        p0 = new_shift + new_rel;
+        pend_first = kBufRounds - k;
+        __syncwarp();
+    }
+    template <int K> __device__ __forceinline__ void tick(int lane) {
+        if (K >= pend_first) gen_round<K>(lane_base(lane), lane);
     }
 
     // Step past `consumed` draws (384 after a full warp iteration, 12 * n after a partial one at the
@@ -162,8 +206,7 @@ struct RanfWarpStream {
         const int new_rel = rel - k * kRanfLag;
         const int new_shift = (-new_rel) & 3;
         if (k == 7) {  // the usual case: only the newest round stays, and it is in registers
-            buf[new_shift + lane] = v;
-            if (lane < kRanfLag - 32) buf[new_shift + 32 + lane] = w;
+            store_round(buf + new_shift, lane);
         } else {
             // Batch boundary (consumed = 192 for full batches, so k is 3 or 4): forward copy in chunks of 32.
             // Needs k >= 1: the destination then starts below the source and a chunk never overwrites

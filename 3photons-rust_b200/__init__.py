@@ -23,7 +23,7 @@ from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libtp3.so")
+LIB_PATH = os.environ.get("TP3_LIB") or os.path.join(_HERE, "_build", "libtp3.so")  # TP3_LIB: A/B builds during development
 CLI_PATH = os.path.join(_HERE, "_build", "trois_photons_b200")
 
 EVENT_BATCH_SIZE = 10_000  # scheduling/mod.rs:21

@@ -97,6 +97,14 @@ __device__ __forceinline__ void fast_sincos_quarters(double t, double& s, double
     const int q = __double2int_rn(t);
     const double a = t - qd;  // exact, |a| <= 1/2
     const double y = a * a;
+#ifdef TP3_ESTRIN
+    // Estrin form: two more multiplies, half the dependency depth of Horner
+    const double y2 = y * y, y4 = y2 * y2;
+    double ps = fma(y4, fma(y2, kSinPoly[6], fma(y, kSinPoly[5], kSinPoly[4])),
+                    fma(y2, fma(y, kSinPoly[3], kSinPoly[2]), fma(y, kSinPoly[1], kSinPoly[0])));
+    double pc = fma(y4, fma(y2, kCosPoly[6], fma(y, kCosPoly[5], kCosPoly[4])),
+                    fma(y2, fma(y, kCosPoly[3], kCosPoly[2]), fma(y, kCosPoly[1], kCosPoly[0])));
+#else
     double ps = fma(y, kSinPoly[6], kSinPoly[5]);
     double pc = fma(y, kCosPoly[6], kCosPoly[5]);
 #pragma unroll
@@ -104,6 +112,7 @@ __device__ __forceinline__ void fast_sincos_quarters(double t, double& s, double
         ps = fma(y, ps, kSinPoly[i]);
         pc = fma(y, pc, kCosPoly[i]);
     }
+#endif
     ps *= a;
     // rotate by q quarter turns: (s, c) -> (c, -s) -> (-s, -c) -> (-c, s)
     const bool swap = q & 1;

@@ -17,7 +17,19 @@
 
 namespace tp3 {
 
-constexpr int kWarps = 4;                // batches per CTA
+#ifndef TP3_MIN_CTAS
+#define TP3_MIN_CTAS 4
+#endif
+#ifndef TP3_TICK_SPREAD
+#define TP3_TICK_SPREAD 0   // 1: one round between each physics stage; 0: whole chain at stage TP3_TICK_AT
+#endif
+#ifndef TP3_TICK_AT
+#define TP3_TICK_AT 1
+#endif
+#ifndef TP3_WARPS
+#define TP3_WARPS 4
+#endif
+constexpr int kWarps = TP3_WARPS;        // batches per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kBatch = TP3_EVENT_BATCH_SIZE;
 constexpr int kLaneEvents = (kBatch + 31) / 32;  // xoshiro: contiguous events per lane (313)
@@ -173,7 +185,14 @@ template <class F, int RNG> struct RngTick {
     int lane;
     bool more;
     template <int K> __device__ __forceinline__ void at() {
+#if TP3_TICK_SPREAD
         if (more) rng.template tick<K>(lane);
+#else
+        if (more && K == TP3_TICK_AT) {  // whole chain in one place: no fences inside, the compiler interleaves it
+            rng.template tick<1>(lane); rng.template tick<2>(lane); rng.template tick<3>(lane); rng.template tick<4>(lane);
+            rng.template tick<5>(lane); rng.template tick<6>(lane); rng.template tick<7>(lane);
+        }
+#endif
     }
 };
 
@@ -185,7 +204,7 @@ __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
 }
 
 template <class F, int RNG, bool SORT, bool LITERAL>
-__global__ void __launch_bounds__(kThreads, LITERAL ? 2 : 4) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
+__global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
     __shared__ BlockSmem<F> sm;
     using Word = typename RawWord<F, RNG>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -136,23 +136,29 @@ struct RanfWarpStream {
     }
 
     // Round K of the buffer from round K-1 (ranf.rs:106-119), three dependent steps inside each lane:
-    //   slots  1..24: new[i] = old[i] - old[i+31]      one shared load (slot lane+32 is draw 23 - lane)
+    //   slots  1..24: new[i] = old[i] - old[i+31]      old[slot lane+32] lives in another lane's register
     //   slots 25..48: new[i] = old[i] - new[i-24]      = vb - (the va just computed)
     //   slots 49..55: new[i] = old[i] - new[i-24]      = vc - (the vb just computed)
+    // Slot lane+32 is slot 25+L of lane L = lane+7 (L in 7..23) or slot 49+L of lane L = lane-17 (L in 0..6):
+    // every lane publishes h = (L < 7 ? vc : vb) and reads it from lane (lane+7) mod 24 with ONE shuffle.
+    // The recurrence therefore never reads shared memory: the stores below only feed the consumers, and no
+    // warp fence is needed between rounds, so the compiler can interleave the chain with FP64 work.
     template <int K> __device__ __forceinline__ void gen_round(uint32_t* pn, int lane) {
-        constexpr int B = (K - 1) * kRanfLag;
-        va = ranf_sub(va, pn[B + 23]);
+        constexpr int B = K * kRanfLag;
+        const int l24 = lane < 24 ? lane : 23;
+        const uint32_t h = lane < 7 ? vc : vb;
+        const uint32_t o = __shfl_sync(0xffffffffu, h, l24 < 17 ? l24 + 7 : l24 - 17);
+        va = ranf_sub(va, o);
         vb = ranf_sub(vb, va);
         vc = ranf_sub(vc, vb);
-        pn[B + kRanfLag + 54] = va;
-        pn[B + kRanfLag + 30] = vb;
-        store_if(lane < 7, pn + B + kRanfLag + 6, vc);
-        __syncwarp();
+        pn[B + 54] = va;
+        pn[B + 30] = vb;
+        store_if(lane < 7, pn + B + 6, vc);
     }
 
     __device__ __forceinline__ uint32_t* lane_base(int lane) const { return buf + shift - (lane < 24 ? lane : 23); }
 
-    // Generate rounds first..7 of the buffer (warp-uniform first >= 1).
+    // Generate rounds first..7 of the buffer (warp-uniform first >= 1) from the registers va, vb, vc.
     __device__ __forceinline__ void refill(int first, int lane) {
         uint32_t* pn = lane_base(lane);
         if (first <= 1) gen_round<1>(pn, lane);
@@ -162,11 +168,13 @@ struct RanfWarpStream {
         if (first <= 5) gen_round<5>(pn, lane);
         if (first <= 6) gen_round<6>(pn, lane);
         gen_round<7>(pn, lane);
+        __syncwarp();
     }
 
     // Pipelined form of advance(384): begin_next() right after the current iteration's draws have been
     // read, then tick<1..7>() spread over the event physics, so that the serial latency of a round
-    // (load -> 3 x (sub, min) -> store -> warp fence) hides behind independent FP64 work of the same warp.
+    // (shuffle -> 3 x (sub, min) -> stores) hides behind independent FP64 work of the same warp. The
+    // consumer's __syncwarp() (draws()) publishes the stores.
     int pend_first;
     __device__ __forceinline__ void begin_next(int lane) {
         __syncwarp();
@@ -229,6 +237,7 @@ struct RanfWarpStream {
     // The 12 raw draws of event slot `lane` of the current warp iteration: three aligned 128-bit
     // loads, bank-conflict free across the warp (lane stride 48 bytes).
     __device__ __forceinline__ void draws(int lane, uint32_t out[kDrawsPerEvent]) const {
+        __syncwarp();  // the rounds stored by other lanes since the last fence become visible
         const uint4* p = reinterpret_cast<const uint4*>(buf + p0 + lane * kDrawsPerEvent);
 #pragma unroll
         for (int g = 0; g < 3; ++g) {

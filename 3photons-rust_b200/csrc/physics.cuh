@@ -42,16 +42,27 @@ __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(
 __device__ __forceinline__ double abs_t(double x) { return fabs(x); }
 __device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
 
-// Fast-path math: hand-written FP64 (fastmath.cuh); f32 keeps libdevice (MUFU based, already lean).
+// Fast-path math: hand-written FP64 (fastmath.cuh). The f32 fast path goes straight to the SFU
+// approximations (MUFU.LG2 / SIN / COS / RCP / RSQ, 2-3 ulp): the stated f32 bounds are three
+// orders of magnitude looser than that, and the f32 literal kernel keeps the IEEE libdevice functions.
 __device__ __forceinline__ double rcp_t(double x) { return fast_rcp(x); }
-__device__ __forceinline__ float rcp_t(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float rcp_t(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double neg_log_t(double x, const FastMathSmem* sm) { return fast_neg_log(x, sm); }
-__device__ __forceinline__ float neg_log_t(float x, const FastMathSmem*) { return -logf(x); }
+__device__ __forceinline__ float neg_log_t(float x, const FastMathSmem*) { return -__logf(x); }
 // argument in quarter turns: t = 4u (exact scaling of the reference's uniform)
 __device__ __forceinline__ void sincos_quarters_t(double t, double* s, double* c) { fast_sincos_quarters(t, *s, *c); }
-__device__ __forceinline__ void sincos_quarters_t(float t, float* s, float* c) { sincospif(0.5f * t, s, c); }
+__device__ __forceinline__ void sincos_quarters_t(float t, float* s, float* c) {
+    const float qf = rintf(t);
+    const int q = __float2int_rn(t);
+    const float x = (t - qf) * 1.57079632679489661923f;  // |x| <= pi/4: the SFU's most accurate range
+    const float ps = __sinf(x), pc = __cosf(x);
+    const bool swap = q & 1;
+    const float s0 = swap ? pc : ps, c0 = swap ? ps : pc;
+    *s = __int_as_float(__float_as_int(s0) ^ (int)((unsigned)(q & 2) << 30));
+    *c = __int_as_float(__float_as_int(c0) ^ (int)((unsigned)((q + 1) & 2) << 30));
+}
 __device__ __forceinline__ double sqrt_pos_t(double x) { return fast_sqrt(x); }
-__device__ __forceinline__ float sqrt_pos_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ float sqrt_pos_t(float x) { return x * rsqrtf(x + 1e-30f); }
 __device__ __forceinline__ void sqrt_rsqrt_t(double x, double* s, double* rs) { fast_sqrt_rsqrt(x, *s, *rs); }
 __device__ __forceinline__ void sqrt_rsqrt_t(float x, float* s, float* rs) {
     *rs = rsqrtf(x);

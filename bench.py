@@ -7,10 +7,11 @@
     python bench.py --impl reference ...      # the reference's CPU path (oracle restatement)
 
 Workload (BASELINE.json configs[4], the configuration the metric is quoted on): the default
-`valeurs` with num_events = 10^10, i.e. 10^6 batches of 10 000 events (scheduling/mod.rs:21),
-default features (f64, RANF, sorted photons).  The batch range is sharded contiguously over the
-ranks (strong scaling: total work fixed), no data-path collective; per-batch accumulators are
-gathered and left-folded in batch order on rank 0 for the end-to-end number.
+`valeurs` with num_events = 10^10 per GPU, i.e. 10^6 batches of 10 000 events (scheduling/mod.rs:21),
+default features (f64, RANF, sorted photons).  The run's batch range is sharded contiguously over the
+ranks with no data-path collective (weak scaling by default: N GPUs simulate N x 10^10 events;
+--scaling strong splits 10^10 events over the ranks); the rank results are gathered and folded on
+rank 0 for the end-to-end number.
 
 A "step" is one pass of the fused kernel over this rank's batch range.
   value : whole-job events/s, device time (CUDA events on the launching stream, max over ranks),
@@ -45,7 +46,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--events", type=float, default=1e10, help="total events per step (all GPUs)")
+    ap.add_argument("--events", type=float, default=1e10, help="events per step PER GPU (weak) or in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--features", default="", help="cargo-style feature list, e.g. f32,standard-random")
     ap.add_argument("--kernel", default="fast", choices=["fast", "literal"])
     ap.add_argument("--cpu-sample-events", type=float, default=5e7)
@@ -86,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -132,7 +134,7 @@ def run_reference(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": "events/sec", "value": rate, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "default valeurs shape, 1e10 events (configs[4]); CPU arm times a bounded sample",
                    "features": REFERENCE_FEATURES},
         "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "sample": desc},
@@ -161,7 +163,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n_events = int(args.events)
+    # weak scaling (default): every GPU gets the 1e10-event workload, i.e. the run has N x 1e10 events and
+    # is sharded by contiguous batch ranges; strong: the 1e10 events are split over the N GPUs.
+    n_events = int(args.events) * (world if args.scaling == "weak" else 1)
     cfg = pkg.Configuration.parse(valeurs_text(), args.features).with_num_events(n_events)
     kernel = pkg.KERNEL_FAST if args.kernel == "fast" else pkg.KERNEL_LITERAL
     nb, last = pkg.batch_layout(n_events)
@@ -258,9 +262,9 @@ def main():
         line = {
             "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if f32 else "f64", "data": "synthetic",
-            "config": {"workload": f"default valeurs, num_events={n_events:.3g} ({nb} batches of 10000; BASELINE configs[4], "
-                                   "the shape of configs[1]); contiguous batch ranges per GPU",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if f32 else "f64", "data": "synthetic",
+            "config": {"workload": f"default valeurs, num_events={n_events:.3g} ({nb} batches of 10000; BASELINE configs[4] = 1e10 events "
+                                   f"{'per GPU' if args.scaling == 'weak' else 'in total'}, the shape of configs[1]); contiguous batch ranges per GPU",
                        "features": args.features or "default (f64, RANF, photon sorting)", "kernel": args.kernel,
                        "l2": "not applicable: no input tensors; the kernel reads a 281 KB jump table and writes 104 B per batch"},
             "clocks": clocks,

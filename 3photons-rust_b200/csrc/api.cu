@@ -31,6 +31,8 @@ struct DeviceSlot {
     tp3_acc* d_out = nullptr;
     size_t out_cap = 0;
     tp3_acc* d_merged = nullptr;
+    cudaStream_t merge_stream = nullptr;   // folds chunk i while chunk i+1 is simulated
+    cudaEvent_t chunk_done = nullptr, merge_done = nullptr;
     uint32_t* d_fe_ranf_states = nullptr;  // faster-evgen: [n][57] batch start states from the host scheduler
     size_t fe_states_cap = 0;
     // last launch
@@ -291,9 +293,10 @@ SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
 }
 
 // Enqueue seeding (xoshiro) + the fused kernel for [first, first+n) on one device slot.
-int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len) {
+int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len, uint64_t slot_off = 0,
+                  uint64_t cap = 0) {
     TP3_CUDA(c, cudaSetDevice(s.dev));
-    int rc = ensure_out(c, s, n);
+    int rc = ensure_out(c, s, cap ? cap : n);
     if (rc) return rc;
     if (n > 0x7fffffffull) {
         c->err = "too many batches in one launch";
@@ -328,16 +331,19 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // the host vectors die at the end of this call
     }
     SimArgs a = make_args(c, s, first, n, last_len);
+    a.out = s.d_out + slot_off;
+    if (a.xo_batch_states) a.xo_batch_states += 4 * slot_off;
+    uint64_t* xo_states = s.d_xo_states ? s.d_xo_states + 4 * slot_off : nullptr;
     if ((c->params.flags & TP3_STANDARD_RANDOM) && !seq_faster) {
         const unsigned blocks = (unsigned)((n + 127) / 128);
         if (c->params.flags & TP3_F32)
             xoshiro_seed_kernel<Xoshiro128Lane><<<blocks, 128, 0, s.stream>>>(first, n, s.d_xo_digit_polys, c->xo_digits,
                                                                               c->xo_base[0], c->xo_base[1], c->xo_base[2],
-                                                                              c->xo_base[3], s.d_xo_states);
+                                                                              c->xo_base[3], xo_states);
         else
             xoshiro_seed_kernel<Xoshiro256Lane><<<blocks, 128, 0, s.stream>>>(first, n, s.d_xo_digit_polys, c->xo_digits,
                                                                               c->xo_base[0], c->xo_base[1], c->xo_base[2],
-                                                                              c->xo_base[3], s.d_xo_states);
+                                                                              c->xo_base[3], xo_states);
         ++c->launches;
     }
     if (faster) {
@@ -443,6 +449,9 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_out);
         cudaFree(s.d_merged);
         cudaFree(s.d_fe_ranf_states);
+        if (s.merge_stream) cudaStreamDestroy(s.merge_stream);
+        if (s.chunk_done) cudaEventDestroy(s.chunk_done);
+        if (s.merge_done) cudaEventDestroy(s.merge_done);
     }
     delete c;
 }
@@ -512,18 +521,50 @@ int tp3_simulate_batches(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_l
 }
 
 int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
-    if (!out) return TP3_E_INVALID;
-    int rc = tp3_simulate_batches_device(c, first, n, last_len);
-    if (rc) return rc;
-    std::vector<tp3_acc> parts;
-    for (auto& s : c->devs) {
-        if (!s.last_n) continue;
-        TP3_CUDA(c, cudaSetDevice(s.dev));
-        if (c->params.flags & TP3_F32) merge_kernel<float><<<1, 32, 0, s.stream>>>(s.d_out, s.last_n, s.d_merged);
-        else merge_kernel<double><<<1, 32, 0, s.stream>>>(s.d_out, s.last_n, s.d_merged);
-        ++c->launches;
-        TP3_CUDA(c, cudaGetLastError());
+    if (!c || !out || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE) {
+        if (c) c->err = "tp3_simulate_merged: bad range";
+        return TP3_E_INVALID;
     }
+    // The ordered fold is one serial chain of additions, so it is overlapped with the simulation: every device
+    // range is cut into chunks; while chunk i+1 is being simulated on the main stream, a second stream folds
+    // chunk i into the running accumulator (strict batch order is kept: the folds are serialised on that stream).
+    const bool chunked = !(c->params.flags & TP3_FASTER_EVGEN);
+    const size_t G = c->devs.size();
+    const bool f32 = c->params.flags & TP3_F32;
+    for (size_t g = 0; g < G; ++g) {
+        DeviceSlot& s = c->devs[g];
+        uint64_t off, cnt;
+        split(n, G, g, off, cnt);
+        s.last_n = 0;
+        if (!cnt) continue;
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        if (!s.merge_stream) {
+            int prio_lo = 0, prio_hi = 0;  // the single fold CTA should get the first SM slot that frees up
+            TP3_CUDA(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            TP3_CUDA(c, cudaStreamCreateWithPriority(&s.merge_stream, cudaStreamNonBlocking, prio_hi));
+            TP3_CUDA(c, cudaEventCreateWithFlags(&s.chunk_done, cudaEventDisableTiming));
+            TP3_CUDA(c, cudaEventCreateWithFlags(&s.merge_done, cudaEventDisableTiming));
+        }
+        const uint32_t range_last = (off + cnt == n) ? last_len : TP3_EVENT_BATCH_SIZE;
+        const uint64_t n_chunks = (chunked && cnt >= 65536) ? 8 : 1;
+        TP3_CUDA(c, cudaStreamWaitEvent(s.merge_stream, s.merge_done, 0));  // previous call's fold (if any) is over
+        for (uint64_t k = 0; k < n_chunks; ++k) {
+            const uint64_t lo = cnt * k / n_chunks, hi = cnt * (k + 1) / n_chunks;
+            int rc = enqueue_range(c, s, first + off + lo, hi - lo, hi == cnt ? range_last : TP3_EVENT_BATCH_SIZE, lo, cnt);
+            if (rc) return rc;
+            TP3_CUDA(c, cudaEventRecord(s.chunk_done, s.stream));
+            TP3_CUDA(c, cudaStreamWaitEvent(s.merge_stream, s.chunk_done, 0));
+            if (f32) merge_kernel<float><<<1, kMergeThreads, 0, s.merge_stream>>>(s.d_out + lo, hi - lo, s.d_merged, k == 0);
+            else merge_kernel<double><<<1, kMergeThreads, 0, s.merge_stream>>>(s.d_out + lo, hi - lo, s.d_merged, k == 0);
+            ++c->launches;
+            TP3_CUDA(c, cudaGetLastError());
+        }
+        TP3_CUDA(c, cudaEventRecord(s.merge_done, s.merge_stream));
+        TP3_CUDA(c, cudaStreamWaitEvent(s.stream, s.merge_done, 0));  // the main stream owns the result
+        s.last_first = first + off;
+        s.last_n = cnt;
+    }
+    std::vector<tp3_acc> parts;
     for (auto& s : c->devs) {
         if (!s.last_n) continue;
         tp3_acc h;

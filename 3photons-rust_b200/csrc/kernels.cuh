@@ -393,51 +393,63 @@ __global__ void xoshiro_seed_kernel(uint64_t first_batch, uint64_t n_batches, co
 }
 
 // ResultsAccumulator::merge (resacc.rs:133-139) as a strict left fold in batch order (bit-identical to
-// the host fold). One warp: all lanes stage tiles of 32 accumulators (13 words each) in shared memory
-// with coalesced loads, lane k < 12 then adds field k of the 32 batches sequentially (the additions are
-// the only serial chain, ~8 cycles each), lane 12 sums the event counts.
-template <class F> __global__ void __launch_bounds__(32) merge_kernel(const tp3_acc* __restrict__ in, uint64_t n, tp3_acc* out) {
-    constexpr int kTile = 32, kWords = 13;
-    __shared__ uint64_t tile[2][kTile * kWords];
-    const int lane = threadIdx.x;
+// the host fold). The only serial part is the chain of additions (one per batch and field); everything
+// else is arranged around it: warps 1..7 stage tiles of 256 accumulators in shared memory (coalesced,
+// double buffered) while lane k < 12 of warp 0 adds field k of the current tile sequentially and lane 12
+// sums the event counts.
+constexpr int kMergeThreads = 256, kMergeTile = 224;  // 2 x 224 x 104 B = 46.6 KB of static shared memory
+template <class F> __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const tp3_acc* __restrict__ in, uint64_t n, tp3_acc* out,
+                                                                                 bool first_chunk) {
+    constexpr int kWords = 13;
+    __shared__ uint64_t tile[2][kMergeTile * kWords];
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t* src = reinterpret_cast<const uint64_t*>(in);
     const uint64_t total = n * kWords;
-    auto stage = [&](int buf, uint64_t t) {
-        const uint64_t base = t * kTile * kWords;
-#pragma unroll
-        for (int i = 0; i < kWords; ++i) {
-            const uint64_t idx = base + (uint64_t)i * 32 + lane;
-            tile[buf][i * 32 + lane] = idx < total ? src[idx] : 0ull;
+    auto stage = [&](int buf, uint64_t t, int first, int step) {
+        const uint64_t base = t * kMergeTile * kWords;
+        for (int i = first; i < kMergeTile * kWords; i += step) {
+            const uint64_t idx = base + i;
+            tile[buf][i] = idx < total ? src[idx] : 0ull;
         }
     };
+    // a later chunk continues the fold from the running accumulator left in `out` by the previous chunk
+    uint64_t* dst = reinterpret_cast<uint64_t*>(out);
     F acc = 0;
     uint64_t cnt = 0;
-    const uint64_t n_tiles = (n + kTile - 1) / kTile;
-    stage(0, 0);
-    __syncwarp();
+    if (!first_chunk) {
+        if (tid < 12) acc = (F)__longlong_as_double((long long)dst[1 + tid]);
+        else if (tid == 12) cnt = dst[0];
+    }
+    const uint64_t n_tiles = (n + kMergeTile - 1) / kMergeTile;
+    stage(0, 0, tid, kMergeThreads);
+    __syncthreads();
     for (uint64_t t = 0; t < n_tiles; ++t) {
         const int cur = (int)(t & 1);
-        if (t + 1 < n_tiles) stage(cur ^ 1, t + 1);
-        const int m = (int)min((uint64_t)kTile, n - t * kTile);
-        if (lane < 12) {
-            const int field = 1 + lane;
-            if (t == 0) {
-                acc = (F)__longlong_as_double((long long)tile[cur][field]);
-                for (int b = 1; b < m; ++b) acc += (F)__longlong_as_double((long long)tile[cur][b * kWords + field]);
-            } else if (m == kTile) {
-#pragma unroll
-                for (int b = 0; b < kTile; ++b) acc += (F)__longlong_as_double((long long)tile[cur][b * kWords + field]);
-            } else {
-                for (int b = 0; b < m; ++b) acc += (F)__longlong_as_double((long long)tile[cur][b * kWords + field]);
+        if (tid >= 32) {
+            if (t + 1 < n_tiles) stage(cur ^ 1, t + 1, tid - 32, kMergeThreads - 32);
+        } else {
+            const int m = (int)min((uint64_t)kMergeTile, n - t * kMergeTile);
+            if (lane < 12) {
+                const uint64_t* col = &tile[cur][1 + lane];
+                int b = 0;
+                if (t == 0 && first_chunk) {  // the fold starts FROM the first accumulator (sequential.rs:24-26)
+                    acc = (F)__longlong_as_double((long long)col[0]);
+                    b = 1;
+                }
+                if (b == 0 && m == kMergeTile) {
+#pragma unroll 32
+                    for (int i = 0; i < kMergeTile; ++i) acc += (F)__longlong_as_double((long long)col[i * kWords]);
+                } else {
+                    for (; b < m; ++b) acc += (F)__longlong_as_double((long long)col[b * kWords]);
+                }
+            } else if (lane == 12) {
+                for (int b = 0; b < m; ++b) cnt += tile[cur][b * kWords];
             }
-        } else if (lane == 12) {
-            for (int b = 0; b < m; ++b) cnt += tile[cur][b * kWords];
         }
-        __syncwarp();
+        __syncthreads();
     }
-    uint64_t* dst = reinterpret_cast<uint64_t*>(out);
-    if (lane < 12) dst[1 + lane] = (uint64_t)__double_as_longlong((double)acc);
-    else if (lane == 12) dst[0] = cnt;
+    if (tid < 12) dst[1 + tid] = (uint64_t)__double_as_longlong((double)acc);
+    else if (tid == 12) dst[0] = cnt;
 }
 
 // Parity hook for the hand-written FP64 functions (fastmath.cuh): out[i] = f_which(in[i]).

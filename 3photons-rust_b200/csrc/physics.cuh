@@ -239,6 +239,10 @@ template <class F> __device__ __forceinline__ Cplx<F> cmul(Cplx<F> a, Cplx<F> b)
     return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
 }
 template <class F> __device__ __forceinline__ Cplx<F> csqr(Cplx<F> a) { return cmul(a, a); }
+// acc + a b with four FMAs (a separate multiply and add would be six instructions)
+template <class F> __device__ __forceinline__ Cplx<F> cmac(Cplx<F> acc, Cplx<F> a, Cplx<F> b) {
+    return {fma_t(a.re, b.re, fma_t(-a.im, b.im, acc.re)), fma_t(a.re, b.im, fma_t(a.im, b.re, acc.im))};
+}
 template <class F> __device__ __forceinline__ Cplx<F> cadd(Cplx<F> a, Cplx<F> b) { return {a.re + b.re, a.im + b.im}; }
 template <class F> __device__ __forceinline__ Cplx<F> csub(Cplx<F> a, Cplx<F> b) { return {a.re - b.re, a.im - b.im}; }
 template <class F> __device__ __forceinline__ Cplx<F> cscale(Cplx<F> a, F s) { return {a.re * s, a.im * s}; }
@@ -380,8 +384,8 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
     Cplx<F> Sa = cmul(tk[0], s2[0]), Sb = cmul(Cplx<F>{cx[0], cy[0]}, s2[0]);
 #pragma unroll
     for (int k = 1; k < 3; ++k) {
-        Sa = cadd(Sa, cmul(tk[k], s2[k]));
-        Sb = cadd(Sb, cmul(Cplx<F>{cx[k], cy[k]}, s2[k]));
+        Sa = cmac(Sa, tk[k], s2[k]);
+        Sb = cmac(Sb, Cplx<F>{cx[k], cy[k]}, s2[k]);
     }
     m[2] = (P.g_beta_m * P.g_beta_m) * ((F)4 * e2 * e2) * (cnorm(Sa) + (F)4 * cnorm(Sb));
     // mixed: u_k = -(e/2) ub_k, U = -(e/2)^3 Ub, W_k = s2_k u_k conj(U) / D = s2_k ub_k conj(Ub) (e/2)^4 / (e^6 Dn)

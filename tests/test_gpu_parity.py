@@ -352,6 +352,21 @@ def test_whole_program_cli_surface(tp3, valeurs_text, tmp_path):
     assert secs > 0
 
 
+def test_cli_binary(tp3, valeurs_text, tmp_path):
+    """The command-line twin of the reference binary: run in a directory holding `valeurs`."""
+    import subprocess
+    (tmp_path / "valeurs").write_text(valeurs_text)
+    r = subprocess.run([tp3.CLI_PATH, "--features", "standard-random"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert compare(r.stdout, golden("stdout.log-features_standard-random"), rel=1e-5) == []
+    assert compare((tmp_path / "res.data").read_text(), golden("res.data-features_standard-random"), rel=REL_F64) == []
+    bad = subprocess.run([tp3.CLI_PATH, "--features", "nonsense"], cwd=tmp_path, capture_output=True, text=True)
+    assert bad.returncode == 2
+    (tmp_path / "valeurs").write_text(valeurs_text.replace("10000000", "0", 1))
+    err = subprocess.run([tp3.CLI_PATH], cwd=tmp_path, capture_output=True, text=True)
+    assert err.returncode == 1 and "Please simulate at least one event" in err.stderr
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_properties(tp3, valeurs_text):
     """At 10^9 events (10^5 batches, no oracle possible in seconds): (i) range additivity — two

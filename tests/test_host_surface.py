@@ -142,3 +142,50 @@ def test_host_xoshiro_jump_matches_oracle_stream(tp3, oracle, f32, features):
         assert (st[0] + st[3]) & mask == oracle.rng_words(features, batch, 1)[0]
         assert tp3.lib().tp3_host_xoshiro_state(f32, 0, batch, st) == 0
         assert (st[0] + st[3]) & mask == oracle.rng_words(features + ",multi-threading,faster-threading", batch, 1)[0]
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """The product never falls back to anything: without the built CUDA library the package refuses to work."""
+    import subprocess
+    import sys
+    code = ("import importlib.util, sys; spec = importlib.util.spec_from_file_location('tp3x', r'%s'); "
+            "m = importlib.util.module_from_spec(spec); sys.modules['tp3x'] = m; spec.loader.exec_module(m); m.lib()"
+            % os.path.join(ROOT, "3photons-rust_b200", "__init__.py"))
+    env = dict(os.environ, TP3_LIB=str(tmp_path / "does_not_exist.so"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_merge_is_done_in_the_runs_float(tp3):
+    """ResultsAccumulator::merge adds in Float (resacc.rs:133-139): under f32 the sums round to f32."""
+    import numpy as np
+    a, b = tp3.Acc(), tp3.Acc()
+    a.selected_events, b.selected_events = 3, 4
+    a.sigma, b.sigma = float(np.float32(1.0)), float(np.float32(1e-8))
+    a.spm2[0], b.spm2[0] = 0.1, 0.2
+    m64 = tp3.merge(tp3.Acc.from_buffer_copy(a), b, 0)
+    assert m64.selected_events == 7 and m64.sigma == 1.0 + float(np.float32(1e-8)) and m64.spm2[0] == 0.1 + 0.2
+    m32 = tp3.merge(tp3.Acc.from_buffer_copy(a), b, tp3.F32)
+    assert m32.sigma == 1.0  # 1e-8 is below half an ulp of 1.0f
+    assert m32.spm2[0] == float(np.float32(0.1) + np.float32(0.2))
+
+
+@pytest.mark.parametrize("value,f64_text,f32_text", [
+    (11.303932414679, "11.303932414679", "11.304"),
+    (0.0028014060468836, "0.0028014060468836", "0.0028014"),
+    (2.4782579584832e-4, "2.4782579584832e-4", "2.4783e-4"),
+    (389379660.0, "389379660", "3.8938e8"),
+    (0.0, "0", "0"),
+    (128.0, "128", "128"),
+    (-4.559, "-4.559", "-4.559"),
+])
+def test_engineering_format_matches_reference_goldens(tp3, valeurs_text, value, f64_text, f32_text):
+    """output.rs:230-269 (`%g`-like writer) through the res.data text: put the value in the sigma slot."""
+    for features, want in (("", f64_text), ("f32", f32_text)):
+        cfg = tp3.Configuration.parse(valeurs_text, features)
+        fin = tp3.Final()
+        fin.sigma = value
+        fin.prec = 1.0
+        text = tp3.FinalResults(fin, cfg).res_data()
+        line = [l for l in text.splitlines() if l.startswith(" Section Efficace")][0]
+        assert line.split(":")[1].strip() == want

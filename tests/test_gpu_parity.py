@@ -352,6 +352,25 @@ def test_whole_program_cli_surface(tp3, valeurs_text, tmp_path):
     assert secs > 0
 
 
+@pytest.mark.parametrize("features", ["", "standard-random", "faster-evgen"])
+def test_single_process_multi_device(tp3, valeurs_text, features):
+    """tp3_create with several devices: contiguous sub-ranges per device, same bits as one device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    with tp3.Simulator(cfg, devices=[0]) as one:
+        want = one.simulate_batches(5, 37, 1234)
+        want_merged = one.simulate_merged(5, 37, 1234)
+    with tp3.Simulator(cfg, devices=[0, 1]) as two:
+        got = two.simulate_batches(5, 37, 1234)
+        got_merged = two.simulate_merged(5, 37, 1234)
+    assert bytes(got) == bytes(want)
+    # two device partials folded on the host: same sums up to the association of one addition
+    assert got_merged.selected_events == want_merged.selected_events
+    assert_acc_close(got_merged, want_merged, 1e-14)
+
+
 def test_cli_binary(tp3, valeurs_text, tmp_path):
     """The command-line twin of the reference binary: run in a directory holding `valeurs`."""
     import subprocess

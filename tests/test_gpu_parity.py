@@ -210,6 +210,47 @@ def test_batches_match_oracle_f32(sims, oracle, valeurs_text, features):
             assert abs(g[k] - w[k]) <= F32_REL_BATCH * abs(w[k]) + 3e-4 * abs(w[k]) * F32_SELECTED_SLACK_BATCH, f"batch {b} field {k}"
 
 
+# ----------------------------------------------------------------- other configurations
+def _edit_valeurs(text, **items):
+    """Replace the first token of the given (0-based) item lines of a `valeurs` text."""
+    lines = text.splitlines()
+    for idx, val in items.items():
+        i = int(idx[1:])
+        rest = lines[i].split(None, 1)
+        lines[i] = f"{val}\t\t{rest[1] if len(rest) > 1 else ''}"
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["fast", "literal"])
+@pytest.mark.parametrize("name,edits", [
+    ("plane-cut", dict(i5="0.218e0")),                                    # sin(normal, beam) cut active (valeurs:24)
+    ("no-cuts", dict(i2="1.e0", i3="1.e0", i4="0.e0", i5="0.e0")),       # valeurs:26-29: everything is kept
+    ("tight", dict(i2="0.5e0", i3="0.3e0", i4="20.e0", i5="0.4e0")),      # most events rejected
+    ("off-peak", dict(i1="100.e0", i13="0.7e0", i14="1.3e0")),            # delta != 0: R_MX contributes, beta+ != beta-
+])
+def test_other_configurations_match_oracle(tp3, oracle, valeurs_text, name, edits, kernel):
+    """Cut thresholds, energies and couplings other than the default file: per-batch parity with the oracle."""
+    nb = 6
+    text = _edit_valeurs(valeurs_text, i0=str(nb * 10000), **edits)
+    run = oracle.run(text, "", want_text=False)
+    cfg = tp3.Configuration.parse(text)
+    with tp3.Simulator(cfg, kernel) as sim:
+        accs = sim.simulate_batches(0, nb)
+    for b in range(nb):
+        want = run.per_batch[b]
+        assert accs[b].selected_events == want.selected_events, f"{name} batch {b}"
+        # Without cuts the matrix elements are singular for photons collinear with the beam and a handful of
+        # such events dominate the sums; their value depends on the last bits of the generated momenta (CUDA vs
+        # glibc sin/cos/log), so only ~1e-8 can be promised there. Every regularised configuration holds 1e-10.
+        rel = 1e-7 if name == "no-cuts" else REL_F64
+        if want.selected_events:
+            assert_acc_close(accs[b], want, rel, what=f"{name} batch {b}")
+    if name == "no-cuts":
+        assert all(a.selected_events == 10000 for a in accs)
+    fin, ofin = tp3.finalize(cfg, tp3.fold(accs)), oracle.run(text, "")
+    assert compare(fin.res_data(), ofin.res_data, rel=1e-6 if name == "no-cuts" else REL_F64) == []
+
+
 # ------------------------------------------------------------- ragged / edge-case geometry
 @pytest.mark.parametrize("n_events", [1, 31, 32, 33, 1279, 1280, 1281, 9999, 10001, 25000])
 def test_ragged_event_counts(tp3, oracle, valeurs_text, n_events):

@@ -22,13 +22,17 @@ __constant__ double kLog1p[5] = {TP3_LOG1P_COEFFS};
 __constant__ double kSinPoly[7] = {TP3_SIN_COEFFS};
 __constant__ double kCosPoly[7] = {TP3_COS_COEFFS};
 __constant__ double kNegLn2 = TP3_NEG_LN2;
+__constant__ double kRotSin[3] = {TP3_ROT_SIN_COEFFS};
+__constant__ double kRotCos[3] = {TP3_ROT_COS_COEFFS};
 
 struct FastMathSmem {
     double2 log_tab[128];
+    double2 sincos_tab[256];  // {sin, cos}(2 pi k / 256)
 };
 
 __device__ __forceinline__ void fastmath_load(FastMathSmem* sm) {
     for (int i = threadIdx.x; i < 128; i += blockDim.x) sm->log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sm->sincos_tab[i] = make_double2(kSinCosTable[i][0], kSinCosTable[i][1]);
 }
 
 __device__ __forceinline__ double mufu_rcp(double x) {
@@ -122,6 +126,21 @@ __device__ __forceinline__ void fast_sincos_quarters(double t, double& s, double
     c = __hiloint2double(__double2hiint(c0) ^ cflip, __double2loint(c0));
 }
 __device__ __forceinline__ void fast_sincos_2pi(double u, double& s, double& c) { fast_sincos_quarters(4.0 * u, s, c); }
+
+// sin(2 pi u), cos(2 pi u) given t = 256 u in [0, 256]: table of 256 directions + rotation by the remainder.
+// 2 pi u = 2 pi (k + d) / 256 with k = rint(t), |d| <= 1/2 (exact), so the rotation angle is at most pi/256 and
+// degree-5 / degree-6 Taylor polynomials are exact to 1e-17; no quadrant logic, 12 FP64 instructions.
+__device__ __forceinline__ void fast_sincos_256(double t, const FastMathSmem* sm, double& s, double& c) {
+    const double kf = rint(t);
+    const int k = __double2int_rn(t) & 255;
+    const double2 sc = sm->sincos_tab[k];
+    const double d = t - kf;
+    const double d2 = d * d;
+    const double sb = d * fma(d2, fma(d2, kRotSin[2], kRotSin[1]), kRotSin[0]);
+    const double cb = fma(d2, fma(d2, fma(d2, kRotCos[2], kRotCos[1]), kRotCos[0]), 1.0);
+    s = fma(sc.x, cb, sc.y * sb);
+    c = fma(sc.y, cb, -(sc.x * sb));
+}
 
 // (double)n * scale for 0 <= n < 2^32 with ONE FMA and no I2F: the word n dropped into the low half
 // of 2^52 is exactly 2^52 + n, and fma(2^52 + n, scale, -(2^52 * scale)) rounds the exact product

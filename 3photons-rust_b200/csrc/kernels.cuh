@@ -118,11 +118,11 @@ template <class F> struct WarpRng<F, RNG_RANF> {
         n = n_next;
         return true;
     }
-    // ranf.rs:99: (n as Float) * 1e-9; `quarters` asks for 4u instead (an exact scaling)
-    __device__ static F uniform(uint32_t w, bool quarters) {
-        if (sizeof(F) == 8) return (F)u32_times(w, quarters ? 4e-9 : 1e-9);
+    // ranf.rs:99: (n as Float) * 1e-9; `phi` asks for PhiScale<F>::value * u instead (an exact scaling)
+    __device__ static F uniform(uint32_t w, bool phi) {
+        if (sizeof(F) == 8) return (F)u32_times(w, phi ? 256e-9 : 1e-9);
         const float u = (float)(int)w * 1e-9f;
-        return (F)(quarters ? 4.0f * u : u);
+        return (F)(phi ? 4.0f * u : u);
     }
 };
 
@@ -149,10 +149,10 @@ template <class F, class Lane> struct XoshiroWarpRng {
     template <int K> __device__ __forceinline__ void tick(int) {}
 };
 template <> struct WarpRng<double, RNG_XOSHIRO> : XoshiroWarpRng<double, Xoshiro256Lane> {
-    __device__ static double uniform(uint64_t w, bool quarters) { return (quarters ? 4.0 : 1.0) * to_uniform_xo(w); }
+    __device__ static double uniform(uint64_t w, bool phi) { return (phi ? 256.0 : 1.0) * to_uniform_xo(w); }
 };
 template <> struct WarpRng<float, RNG_XOSHIRO> : XoshiroWarpRng<float, Xoshiro128Lane> {
-    __device__ static float uniform(uint32_t w, bool quarters) { return (quarters ? 4.0f : 1.0f) * to_uniform_xo(w); }
+    __device__ static float uniform(uint32_t w, bool phi) { return (phi ? 4.0f : 1.0f) * to_uniform_xo(w); }
 };
 
 template <class F> struct LaneAcc {
@@ -235,7 +235,11 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
         rng.draws(it, lane, w);
         // The random numbers of the NEXT iteration are regenerated in seven steps interleaved with this
         // iteration's physics (each step is a short serial chain; alone it would stall the warp).
+#ifdef TP3_EXPERIMENT_FAKE_RNG   /* timing experiment only: reuse the same draws, results are wrong */
+        const bool more = false;
+#else
         const bool more = it + 1 < n_it;
+#endif
         if (more) rng.begin_next(lane);
         RngTick<F, RNG> tick{rng, lane, more};
         F u[12];
@@ -282,9 +286,13 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
             __syncwarp();
             q_head = (q_head + 32) & (kQueue - 1);
             q_count -= 32;
+#ifndef TP3_EXPERIMENT_NO_ME
             F m[5];
             me_fast<F>(e, P, m);
             acc.integrate(m, P.sigma_contribs);
+#else
+            acc.spm2[0] += e[0][0] + e[1][1] + e[2][2];
+#endif
         }
     }
     if (!LITERAL && lane < q_count) {  // drain
@@ -462,8 +470,8 @@ __global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __res
         double a = 0, b = 0;
         switch (which) {
             case 0: a = fast_neg_log(x, &fm); break;
-            case 1: fast_sincos_2pi(x, a, b); break;
-            case 2: fast_sincos_2pi(x, b, a); break;
+            case 1: fast_sincos_256(256.0 * x, &fm, a, b); break;
+            case 2: fast_sincos_256(256.0 * x, &fm, b, a); break;
             case 3: a = fast_sqrt(x); break;
             case 4: a = fast_rcp(x); break;
             case 5: fast_sqrt_rsqrt(x, b, a); break;
@@ -471,7 +479,7 @@ __global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __res
             case 7: a = mufu_rcp(x); break;
             case 8: a = mufu_rsqrt(x); break;
             case 9: a = u32_times((uint32_t)x, 1e-9); break;
-            case 10: a = u32_times((uint32_t)x, 4e-9); break;
+            case 10: a = u32_times((uint32_t)x, 256e-9); break;
         }
         out[i] = a;
     }

@@ -49,9 +49,13 @@ __device__ __forceinline__ double rcp_t(double x) { return fast_rcp(x); }
 __device__ __forceinline__ float rcp_t(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double neg_log_t(double x, const FastMathSmem* sm) { return fast_neg_log(x, sm); }
 __device__ __forceinline__ float neg_log_t(float x, const FastMathSmem*) { return -__logf(x); }
-// argument in quarter turns: t = 4u (exact scaling of the reference's uniform)
-__device__ __forceinline__ void sincos_quarters_t(double t, double* s, double* c) { fast_sincos_quarters(t, *s, *c); }
-__device__ __forceinline__ void sincos_quarters_t(float t, float* s, float* c) {
+// The azimuth uniform arrives pre-scaled by an exact power of two: 256 u in f64 (table + rotation), 4 u in f32
+// (quarter turns for the SFU path).
+template <class F> struct PhiScale;
+template <> struct PhiScale<double> { static constexpr double value = 256.0; };
+template <> struct PhiScale<float> { static constexpr float value = 4.0f; };
+__device__ __forceinline__ void sincos_scaled_t(double t, const FastMathSmem* fm, double* s, double* c) { fast_sincos_256(t, fm, *s, *c); }
+__device__ __forceinline__ void sincos_scaled_t(float t, const FastMathSmem*, float* s, float* c) {
     const float qf = rintf(t);
     const int q = __float2int_rn(t);
     const float x = (t - qf) * 1.57079632679489661923f;  // |x| <= pi/4: the SFU's most accurate range
@@ -78,7 +82,7 @@ template <class F> struct PhysParams {
 
 // ------------------------------------------------------------------ event generation
 // u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187).
-// In the fast variant the phi slot holds 4u (quarter turns; an exact scaling) instead of u.
+// In the fast variant the phi slot holds PhiScale<F>::value * u (an exact power-of-two scaling) instead of u.
 // p[k] = (X, Y, Z, E) of photon k, optionally sorted by decreasing E (evgen.rs:109-118).
 // Conformal transform of RAMBO to the total energy + optional sort (evgen.rs:94-118)
 template <class F, bool SORT, bool LITERAL>
@@ -147,7 +151,7 @@ __device__ __forceinline__ void raw_photon(const F* u, const FastMathSmem* fm, F
         st = sqrt_t((F)1 - c * c);
         en = -log_t(e + Num<F>::MIN_POSITIVE);
     } else {
-        sincos_quarters_t(u[1], &sphi, &cphi);
+        sincos_scaled_t(u[1], fm, &sphi, &cphi);
         st = sqrt_pos_t((F)1 - c * c);
         en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
     }

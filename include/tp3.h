@@ -118,7 +118,7 @@ int  tp3_events_dump(tp3_ctx* ctx, uint64_t batch, uint32_t n, double* momenta, 
 
 /* The hand-written FP64 functions of the fast kernel, evaluated on the device: out[i] = f(in[i]).
  * which: 0 -log x, 1 sin(2 pi x), 2 cos(2 pi x), 3 sqrt x, 4 1/x, 5 1/sqrt x, 6 sqrt x (paired form),
- *        7 raw MUFU.RCP64H seed, 8 raw MUFU.RSQ64H seed, 9 / 10 (u32)x * 1e-9 / 4e-9 by the single-FMA route. */
+ *        7 raw MUFU.RCP64H seed, 8 raw MUFU.RSQ64H seed, 9 / 10 (u32)x * 1e-9 / 256e-9 by the single-FMA route. */
 int  tp3_fastmath_probe(tp3_ctx* ctx, int which, uint32_t n, const double* in, double* out);
 
 /* ---- measurement ------------------------------------------------------------------- */

@@ -201,18 +201,19 @@ __device__ __forceinline__ void gen_event_faster(const F u9[9], const F xy[3][2]
 // the common factor E/2 drops out of evcut.rs:52-62 and :80-92.
 template <class F, bool SORT, bool LITERAL>
 __device__ __forceinline__ bool keep_event(const F p[3][4], const PhysParams<F>& P) {
+    // All comparisons are evaluated (no short circuit: they are independent, a chain of && would serialise them)
     bool ok;
     if (SORT) ok = !(p[2][3] < P.e_min);
     else ok = (p[0][3] >= P.e_min) & (p[1][3] >= P.e_min) & (p[2][3] >= P.e_min);  // event.rs:96-105 (min E < e_min rejects)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) ok = ok && !(abs_t(p[k][0]) > P.acut * p[k][3]);
+    for (int k = 0; k < 3; ++k) ok = ok & !(abs_t(p[k][0]) > P.acut * p[k][3]);
     if (LITERAL) {
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int b = a + 1; b < 3; ++b) {
                 const F num = (p[a][0] * p[b][0] + p[a][1] * p[b][1]) + p[a][2] * p[b][2];
-                ok = ok && !(num > P.bcut * (p[a][3] * p[b][3]));
+                ok = ok & !(num > P.bcut * (p[a][3] * p[b][3]));
             }
     } else {
         // p_i.p_j (3-vectors) = E_i E_j - (p_i + p_j)^2 / 2 = E_i E_j - e (e - 2 E_k) / 2 by momentum conservation
@@ -222,7 +223,7 @@ __device__ __forceinline__ bool keep_event(const F p[3][4], const PhysParams<F>&
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int i = (k == 0) ? 1 : 0, j = (k == 2) ? 1 : 2;
-            ok = ok && !(omb * (p[i][3] * p[j][3]) > P.e_total * (he - p[k][3]));
+            ok = ok & !(omb * (p[i][3] * p[j][3]) > P.e_total * (he - p[k][3]));
         }
     }
     if (P.sincut > (F)0) {  // |n_x| < sincut |n|  (uniform branch; the default sincut is 0)

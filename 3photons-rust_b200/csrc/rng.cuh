@@ -148,19 +148,9 @@ struct RanfWarpStream {
         const int l24 = lane < 24 ? lane : 23;
         const uint32_t h = lane < 7 ? vc : vb;
         const uint32_t o = __shfl_sync(0xffffffffu, h, l24 < 17 ? l24 + 7 : l24 - 17);
-#ifdef TP3_RNG_SHORTCHAIN
-        // same values, dependency depth 1 after the shuffle: vb' = vb - va + o and vc' = (vc - vb + va) - o,
-        // with the o-independent parts reduced to [0, 1e9) while the shuffle is in flight
-        const uint32_t t = ranf_sub(vb, va);                  // vb - va
-        const uint32_t u = ranf_add(ranf_sub(vc, vb), va);    // vc - vb + va
-        va = ranf_sub(va, o);
-        vb = ranf_add(t, o);
-        vc = ranf_sub(u, o);
-#else
         va = ranf_sub(va, o);
         vb = ranf_sub(vb, va);
         vc = ranf_sub(vc, vb);
-#endif
         pn[B + 54] = va;
         pn[B + 30] = vb;
         store_if(lane < 7, pn + B + 6, vc);
@@ -212,6 +202,7 @@ struct RanfWarpStream {
     }
     template <int K> __device__ __forceinline__ void tick(int lane) {
         if (K >= pend_first) gen_round<K>(lane_base(lane), lane);
+    }
     }
 
     // Step past `consumed` draws (384 after a full warp iteration, 12 * n after a partial one at the

@@ -203,7 +203,6 @@ struct RanfWarpStream {
     template <int K> __device__ __forceinline__ void tick(int lane) {
         if (K >= pend_first) gen_round<K>(lane_base(lane), lane);
     }
-    }
 
     // Step past `consumed` draws (384 after a full warp iteration, 12 * n after a partial one at the
     // end of a batch): the rounds that still hold unconsumed draws move to the front (re-aligned to

@@ -1,0 +1,70 @@
+//! Raw bindings to `include/tp3.h` (ABI version 1). UNCOMPILED in this repository: no Rust toolchain.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const TP3_EVENT_BATCH_SIZE: u32 = 10_000; // scheduling/mod.rs:21
+
+pub const TP3_F32: u32 = 1 << 0;
+pub const TP3_FASTER_EVGEN: u32 = 1 << 1;
+pub const TP3_FASTER_THREADING: u32 = 1 << 2;
+pub const TP3_MULTI_THREADING: u32 = 1 << 3;
+pub const TP3_NO_PHOTON_SORTING: u32 = 1 << 4;
+pub const TP3_STANDARD_RANDOM: u32 = 1 << 5;
+
+pub const TP3_KERNEL_FAST: u32 = 0;
+pub const TP3_KERNEL_LITERAL: u32 = 1;
+
+pub const TP3_OK: c_int = 0;
+
+/// `tp3_params`: everything the per-event kernel reads (the closure's captured state, main.rs:103-115).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct tp3_params {
+    pub num_events_total: u64,
+    pub e_total: f64,
+    pub acut: f64,
+    pub bcut: f64,
+    pub e_min: f64,
+    pub sincut: f64,
+    pub g_a: f64,
+    pub g_beta_p: f64,
+    pub g_beta_m: f64,
+    pub sigma_contribs: [f64; 5],
+    pub flags: u32,
+    pub kernel: u32,
+}
+
+/// `tp3_acc`: the 13 sums of one `ResultsAccumulator` (resacc.rs:19-34).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct tp3_acc {
+    pub selected_events: u64,
+    pub spm2: [f64; 5],
+    pub vars: [f64; 5],
+    pub sigma: f64,
+    pub variance: f64,
+}
+
+#[repr(C)]
+pub struct tp3_ctx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn tp3_abi_version() -> c_int;
+    pub fn tp3_create(params: *const tp3_params, n_dev: c_int, dev_ids: *const c_int, out: *mut *mut tp3_ctx) -> c_int;
+    pub fn tp3_destroy(ctx: *mut tp3_ctx);
+    pub fn tp3_last_error(ctx: *const tp3_ctx) -> *const c_char;
+    pub fn tp3_set_stream(ctx: *mut tp3_ctx, dev_slot: c_int, cuda_stream: *mut c_void) -> c_int;
+    pub fn tp3_simulate_batches(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
+                                out_per_batch: *mut tp3_acc) -> c_int;
+    pub fn tp3_simulate_batches_device(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32) -> c_int;
+    pub fn tp3_fetch(ctx: *mut tp3_ctx, out_per_batch: *mut tp3_acc, n_batches: u64) -> c_int;
+    pub fn tp3_simulate_merged(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
+                               out_merged: *mut tp3_acc) -> c_int;
+    pub fn tp3_synchronize(ctx: *mut tp3_ctx) -> c_int;
+    pub fn tp3_launch_count(ctx: *const tp3_ctx) -> u64;
+    pub fn tp3_rng_dump(ctx: *mut tp3_ctx, batch: u64, n_words: u32, out_words: *mut u64) -> c_int;
+    pub fn tp3_events_dump(ctx: *mut tp3_ctx, batch: u64, n: u32, momenta: *mut f64, kept: *mut i32, m2_sums: *mut f64) -> c_int;
+    pub fn tp3_peak_probe(ctx: *mut tp3_ctx, which: c_int, tflops: *mut f64) -> c_int;
+}

@@ -11,6 +11,7 @@
 #include "jump_tables.hpp"
 #include "kernels.cuh"
 #include "faster_evgen.cuh"
+#include "fe_scan.cuh"
 
 using namespace tp3;
 
@@ -59,6 +60,9 @@ struct tp3_ctx {
     int fe_ranf_index = 55;
     uint64_t fe_xo[4];
     bool fe_ready = false;
+    // faster-evgen, RANF, sequential stream: where the device scan stands (always at a round start)
+    uint64_t scan_round = 0, scan_events = 0;
+    int scan_state = 0;
 };
 
 namespace {
@@ -242,6 +246,99 @@ void fe_host_states(tp3_ctx* c, uint64_t first, uint64_t n, std::vector<uint32_t
     }
 }
 
+
+// ---- faster-evgen + RANF: batch start states by a scan over per-round transition maps (fe_scan.cuh) ----------
+// Fills s.d_fe_ranf_states[0..n) for batches [first, first + n) of the sequential stream, entirely on the device
+// (the host only chains ~1 segment map per 1024 rounds).
+int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
+    const bool f32 = c->params.flags & TP3_F32;
+    if (first * (uint64_t)TP3_EVENT_BATCH_SIZE < c->scan_events || c->scan_round == 0) {
+        c->scan_round = 0;
+        c->scan_events = 0;
+        c->scan_state = 0;
+    }
+    if (s.fe_states_cap < n) {
+        if (s.d_fe_ranf_states) TP3_CUDA(c, cudaFree(s.d_fe_ranf_states));
+        s.d_fe_ranf_states = nullptr;
+        s.fe_states_cap = 0;
+        TP3_CUDA(c, cudaMalloc(&s.d_fe_ranf_states, n * 57 * sizeof(uint32_t)));
+        s.fe_states_cap = n;
+    }
+    FeBoundary* d_bnd = nullptr;
+    TP3_CUDA(c, cudaMalloc(&d_bnd, n * sizeof(FeBoundary)));
+    const uint64_t last_target = (first + n - 1) * (uint64_t)TP3_EVENT_BATCH_SIZE;  // event index of the last boundary wanted
+    uint64_t* d_maps = nullptr;
+    uint8_t *d_seg_exit = nullptr, *d_seg_state = nullptr;
+    uint32_t* d_seg_count = nullptr;
+    uint64_t* d_seg_events = nullptr;
+    size_t maps_cap = 0;
+    int rc = TP3_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_bnd); cudaFree(d_maps); cudaFree(d_seg_exit); cudaFree(d_seg_state); cudaFree(d_seg_count); cudaFree(d_seg_events);
+    };
+    auto check = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == TP3_OK) {
+            c->err = std::string(what) + ": " + cudaGetErrorString(e);
+            rc = TP3_E_CUDA;
+        }
+        return e == cudaSuccess;
+    };
+    // a boundary is found when the running event count passes it: scan until the count exceeds last_target
+    while (rc == TP3_OK && c->scan_events <= last_target) {
+        const uint64_t remaining = last_target + 1 - c->scan_events;
+        uint64_t n_rounds = (uint64_t)((double)remaining * 0.36) + 4 * kFeSegRounds;  // ~0.32 rounds per event
+        if (n_rounds > (1ull << 24)) n_rounds = 1ull << 24;                            // 128 MB of maps per pass
+        const uint64_t n_seg = (n_rounds + kFeSegRounds - 1) / kFeSegRounds;
+        if (maps_cap < n_rounds) {
+            cudaFree(d_maps); cudaFree(d_seg_exit); cudaFree(d_seg_state); cudaFree(d_seg_count); cudaFree(d_seg_events);
+            d_maps = nullptr; d_seg_exit = d_seg_state = nullptr; d_seg_count = nullptr; d_seg_events = nullptr;
+            if (!check(cudaMalloc(&d_maps, n_rounds * 8), "cudaMalloc maps")) break;
+            if (!check(cudaMalloc(&d_seg_exit, n_seg * 9), "cudaMalloc")) break;
+            if (!check(cudaMalloc(&d_seg_state, n_seg), "cudaMalloc")) break;
+            if (!check(cudaMalloc(&d_seg_count, n_seg * 9 * 4), "cudaMalloc")) break;
+            if (!check(cudaMalloc(&d_seg_events, n_seg * 8), "cudaMalloc")) break;
+            maps_cap = n_rounds;
+        }
+        const unsigned map_blocks = (unsigned)((n_seg + 3) / 4), seg_blocks = (unsigned)((n_seg + 127) / 128);
+        if (f32) fe_round_maps_kernel<float><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, d_maps);
+        else fe_round_maps_kernel<double><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, d_maps);
+        fe_segment_kernel<<<seg_blocks, 128, 0, s.stream>>>(d_maps, n_rounds, d_seg_exit, d_seg_count);
+        c->launches += 2;
+        std::vector<uint8_t> seg_exit(n_seg * 9), seg_state(n_seg);
+        std::vector<uint32_t> seg_count(n_seg * 9);
+        std::vector<uint64_t> seg_events(n_seg);
+        if (!check(cudaMemcpyAsync(seg_exit.data(), d_seg_exit, n_seg * 9, cudaMemcpyDeviceToHost, s.stream), "D2H")) break;
+        if (!check(cudaMemcpyAsync(seg_count.data(), d_seg_count, n_seg * 9 * 4, cudaMemcpyDeviceToHost, s.stream), "D2H")) break;
+        if (!check(cudaStreamSynchronize(s.stream), "fe scan maps")) break;
+        int state = c->scan_state;
+        uint64_t events = c->scan_events;
+        for (uint64_t g = 0; g < n_seg; ++g) {  // chain the segment maps (multi_threading.rs:59-64 does this event by event)
+            seg_state[g] = (uint8_t)state;
+            seg_events[g] = events;
+            events += seg_count[g * 9 + state];
+            state = seg_exit[g * 9 + state];
+        }
+        if (!check(cudaMemcpyAsync(d_seg_state, seg_state.data(), n_seg, cudaMemcpyHostToDevice, s.stream), "H2D")) break;
+        if (!check(cudaMemcpyAsync(d_seg_events, seg_events.data(), n_seg * 8, cudaMemcpyHostToDevice, s.stream), "H2D")) break;
+        fe_boundaries_kernel<<<seg_blocks, 128, 0, s.stream>>>(d_maps, c->scan_round, n_rounds, d_seg_state, d_seg_events, first, n, d_bnd);
+        ++c->launches;
+        if (!check(cudaStreamSynchronize(s.stream), "fe boundaries")) break;  // the host vectors die with this iteration
+        c->scan_round += n_rounds;
+        c->scan_events = events;
+        c->scan_state = state;
+    }
+    if (rc == TP3_OK) {
+        const unsigned blocks = (unsigned)((n + 3) / 4);
+        if (f32) fe_batch_states_kernel<float><<<blocks, 128, 0, s.stream>>>(s.d_ranf_table, d_bnd, n, s.d_fe_ranf_states);
+        else fe_batch_states_kernel<double><<<blocks, 128, 0, s.stream>>>(s.d_ranf_table, d_bnd, n, s.d_fe_ranf_states);
+        ++c->launches;
+        check(cudaGetLastError(), "fe batch states");
+        check(cudaStreamSynchronize(s.stream), "fe batch states");
+    }
+    cleanup();
+    return rc;
+}
+
 template <class F, int RNG> void launch_fe(const FeArgs& a, const tp3_params& p, cudaStream_t st) {
     faster_evgen_kernel<F, RNG><<<(unsigned)((a.n_batches + kFeThreads - 1) / kFeThreads), kFeThreads, 0, st>>>(a, phys_params<F>(p));
 }
@@ -314,7 +411,11 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     const bool seq_faster = faster && !(c->params.flags & TP3_FASTER_THREADING);
     std::vector<uint32_t> fe_ranf;
     std::vector<uint64_t> fe_xo;
-    if (seq_faster) {
+    const bool device_scan = seq_faster && !(c->params.flags & TP3_STANDARD_RANDOM) && !std::getenv("TP3_FE_HOST_SCAN");
+    if (device_scan) {
+        rc = fe_device_states_ranf(c, s, first, n);
+        if (rc) return rc;
+    } else if (seq_faster) {
         fe_host_states(c, first, n, fe_ranf, fe_xo);
         if (!fe_ranf.empty()) {
             if (s.fe_states_cap < n) {
@@ -427,7 +528,9 @@ int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx*
             e = up(c->xo_digit_polys.data(), c->xo_digit_polys.size() * 8, (void**)&s.d_xo_digit_polys);
             if (e == cudaSuccess) e = up(c->xo_lane_polys.data(), c->xo_lane_polys.size() * 8, (void**)&s.d_xo_lane_polys);
         } else {
-            e = up(c->ranf_table.data(), c->ranf_table.size() * 4, (void**)&s.d_ranf_table);
+            std::vector<uint32_t> t(c->ranf_table);  // the seeded round 0 rides behind the table (fe_scan.cuh)
+            t.insert(t.end(), c->ranf_base, c->ranf_base + kRanfLag);
+            e = up(t.data(), t.size() * 4, (void**)&s.d_ranf_table);
         }
         if (e == cudaSuccess) e = cudaMalloc(&s.d_merged, sizeof(tp3_acc));
         c->devs.push_back(s);

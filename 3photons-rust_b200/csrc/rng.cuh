@@ -58,6 +58,42 @@ __device__ __forceinline__ uint32_t ranf_next_slot(const uint32_t* y, int i /*1.
     return ranf_add(ranf_sub(y[i - 1], y[i - 24 - 1]), ranf_sub(y[i - 48 - 1], y[i - 17 - 1]));
 }
 
+// Warp-cooperative jump-ahead: win[0..54] <- round `rho0` of the generator whose round 0 is base_y (slot order),
+// with <= kRanfDigits applications of the tabulated polynomials x^(55 d 256^k) mod P (jump_tables.hpp).
+// win must hold 2 * 55 words.
+__device__ inline void ranf_jump_to_round(uint32_t* win, const uint32_t* base_y, uint64_t rho0,
+                                          const uint32_t* __restrict__ jump_table, int lane) {
+    for (int i = lane; i < kRanfLag; i += 32) win[i] = base_y[i];
+    __syncwarp();
+    for (int k = 0; k < kRanfDigits; ++k) {
+        const unsigned d = (unsigned)((rho0 >> (8 * k)) & 0xffu);
+        if (d == 0) continue;  // warp-uniform
+        // extend the window to y[0..109]
+        for (int i = lane + 1; i <= kRanfLag; i += 32) win[kRanfLag + i - 1] = ranf_next_slot(win, i);
+        __syncwarp();
+        const uint32_t* __restrict__ c = jump_table + ((size_t)k * 256 + d) * kRanfLag;
+        uint32_t o[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            uint64_t acc = 0;
+            if (i < kRanfLag) {
+#pragma unroll 5
+                for (int j = 0; j < kRanfLag; ++j) {
+                    acc += (uint64_t)__ldg(c + j) * win[i + j];
+                    if ((j % 16) == 15) acc %= kRanfMod;  // 16 products < 1.6e19 < 2^64
+                }
+                acc %= kRanfMod;
+            }
+            o[h] = (uint32_t)acc;
+        }
+        __syncwarp();
+        win[lane] = o[0];
+        if (lane + 32 < kRanfLag) win[lane + 32] = o[1];
+        __syncwarp();
+    }
+}
+
 // One warp regenerates the reference's stream for a contiguous range of events.
 // The buffer is linear (no ring arithmetic): all shared-memory offsets inside a refill are
 // compile-time immediates relative to per-lane pointers, and every lane keeps its own two values
@@ -79,35 +115,7 @@ struct RanfWarpStream {
         uint32_t* win = sm->win;
         const uint64_t rho0 = d0 / kRanfLag;
         const int q0 = (int)(d0 - rho0 * kRanfLag);
-        for (int i = lane; i < kRanfLag; i += 32) win[i] = base_y[i];
-        __syncwarp();
-        for (int k = 0; k < kRanfDigits; ++k) {
-            const unsigned d = (unsigned)((rho0 >> (8 * k)) & 0xffu);
-            if (d == 0) continue;  // warp-uniform
-            // extend the window to y[0..109]
-            for (int i = lane + 1; i <= kRanfLag; i += 32) win[kRanfLag + i - 1] = ranf_next_slot(win, i);
-            __syncwarp();
-            const uint32_t* __restrict__ c = jump_table + ((size_t)k * 256 + d) * kRanfLag;
-            uint32_t o[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-                uint64_t acc = 0;
-                if (i < kRanfLag) {
-#pragma unroll 5
-                    for (int j = 0; j < kRanfLag; ++j) {
-                        acc += (uint64_t)__ldg(c + j) * win[i + j];
-                        if ((j % 16) == 15) acc %= kRanfMod;  // 16 products < 1.6e19 < 2^64
-                    }
-                    acc %= kRanfMod;
-                }
-                o[h] = (uint32_t)acc;
-            }
-            __syncwarp();
-            win[lane] = o[0];
-            if (lane + 32 < kRanfLag) win[lane + 32] = o[1];
-            __syncwarp();
-        }
+        ranf_jump_to_round(win, base_y, rho0, jump_table, lane);
         // slot order -> consumption order: draw r of the round is slot 55 - r
         shift = (-q0) & 3;
         p0 = shift + q0;

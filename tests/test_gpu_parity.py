@@ -354,6 +354,23 @@ def test_faster_evgen_batches_match_oracle(sims, oracle, valeurs_text, features)
     assert bytes(again) == bytes((type(again))(*accs[3:7]))
 
 
+@pytest.mark.parametrize("features,first,nb", [("faster-evgen", 0, 300), ("faster-evgen", 4990, 260), ("faster-evgen,f32", 7, 64)])
+def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, monkeypatch):
+    """The batch start states of the sequential RANF stream come from a scan over per-round transition maps on the
+    GPU (fe_scan.cuh); the reference's own method — walking the stream event by event on the scheduler thread,
+    evgen.rs:257-267 — is kept on the host behind TP3_FE_HOST_SCAN for this cross-check: identical bits.
+    (4990 + 260 batches = 5.25e7 events cross the 2^24-round pass boundary of the scan.)"""
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    with tp3.Simulator(cfg) as sim:
+        dev = sim.simulate_batches(first, nb)
+        dev_again = sim.simulate_batches(first + 5, 20)  # continues / restarts the cached scan
+    monkeypatch.setenv("TP3_FE_HOST_SCAN", "1")
+    with tp3.Simulator(cfg) as sim:
+        host = sim.simulate_batches(first, nb)
+    assert bytes(dev) == bytes(host)
+    assert bytes(dev_again) == bytes((type(dev_again))(*host[5:25]))
+
+
 def test_faster_evgen_f32_batches(sims, oracle, valeurs_text):
     nb = 8
     features = "faster-evgen,f32"

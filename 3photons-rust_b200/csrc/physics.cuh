@@ -151,9 +151,22 @@ __device__ __forceinline__ void raw_photon(const F* u, const FastMathSmem* fm, F
         st = sqrt_t((F)1 - c * c);
         en = -log_t(e + Num<F>::MIN_POSITIVE);
     } else {
+#ifdef TP3_EXPERIMENT_KO_SINCOS   /* timing experiments only (wrong results): knock one function out */
+        sphi = u[1];
+        cphi = (F)1 - u[1];
+#else
         sincos_scaled_t(u[1], fm, &sphi, &cphi);
+#endif
+#ifdef TP3_EXPERIMENT_KO_SQRT
+        st = (F)1 - c * c;
+#else
         st = sqrt_pos_t((F)1 - c * c);
+#endif
+#ifdef TP3_EXPERIMENT_KO_LOG
+        en = e + (F)1;
+#else
         en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
+#endif
     }
     q[0] = en * (st * sphi);
     q[1] = en * (st * cphi);

@@ -78,13 +78,43 @@ __device__ __forceinline__ int fe_walk_round(const uint32_t* slots, int stride, 
     return s;
 }
 
+// The disc tests of a round, evaluated once: bit j of A = outside(slots[j], slots[j+1]) (a re-roll served at index j),
+// bit j of B = outside(slots[j], slots[j+3]) (point p of a 6-number request served at index j - p).
+template <class F> __device__ __forceinline__ void fe_round_masks(const uint32_t* slots, uint64_t& A, uint64_t& B) {
+    A = 0;
+    B = 0;
+#pragma unroll 6
+    for (int j = 0; j < kRanfLag - 1; ++j) A |= (uint64_t)fe_outside<F>(slots[j], slots[j + 1]) << j;
+#pragma unroll 4
+    for (int j = 0; j < kRanfLag - 3; ++j) B |= (uint64_t)fe_outside<F>(slots[j], slots[j + 3]) << j;
+}
+
+// fe_walk_round on the precomputed masks: integer only, the same instruction stream for every entry state
+__device__ __forceinline__ int fe_walk_masks(uint64_t A, uint64_t B, int s, int& count) {
+    // next state after the 6-number request, indexed by (n0 | n1 << 1 | n2 << 2); after an accepted re-roll, indexed by s
+    constexpr uint32_t kAfterSix = 0x0u | (2u << 4) | (6u << 8) | (4u << 12) | (8u << 16) | (3u << 20) | (7u << 24) | (5u << 28);
+    constexpr uint64_t kAfterRoll = (0ull << 8) | (8ull << 12) | (6ull << 16) | (7ull << 20) | (0ull << 24) | (8ull << 28) | (0ull << 32);
+    int idx = 55;
+    count = 0;
+    for (;;) {
+        const int need = s == 0 ? 9 : s == 1 ? 6 : 2;
+        if (idx < need) break;
+        idx -= need;
+        const int after_six = (int)((kAfterSix >> (4 * (int)((B >> idx) & 7u))) & 15u);
+        const int after_roll = ((A >> idx) & 1u) ? s : (int)((kAfterRoll >> (4 * s)) & 15u);
+        count += s == 0;
+        s = s == 0 ? 1 : s == 1 ? after_six : after_roll;
+    }
+    return s;
+}
+
 // map word of a round: bits [4s, 4s+4) = exit state for entry state s, bits [36 + 3s, 36 + 3s + 3) = events started
 __device__ __forceinline__ int fe_map_exit(uint64_t m, int s) { return (int)((m >> (4 * s)) & 15u); }
 __device__ __forceinline__ int fe_map_count(uint64_t m, int s) { return (int)((m >> (36 + 3 * s)) & 7u); }
 
 struct FeScanSmem {
     uint32_t win[2 * kRanfLag + 2];
-    uint32_t tile[kFeTile][kRanfLag + 1];  // 32 consecutive rounds, slot order; row stride 56 words
+    uint32_t tile[kFeTile][kRanfLag + 2];  // 32 consecutive rounds, slot order; odd row stride (57): lane = row reads are conflict free
 };
 
 // 1. per-round maps for rounds [first_round, first_round + n_rounds); one warp per segment of kFeSegRounds rounds
@@ -109,11 +139,12 @@ __global__ void __launch_bounds__(128) fe_round_maps_kernel(const uint32_t* __re
             __syncwarp();
         }
         if (t0 + lane < n_seg) {
-            uint64_t m = 0;
+            uint64_t A, B, m = 0;
+            fe_round_masks<F>(w.tile[lane], A, B);
 #pragma unroll 1
             for (int s = 0; s < 9; ++s) {
                 int cnt;
-                const int e = fe_walk_round<F>(w.tile[lane], 1, s, cnt, -1, nullptr);
+                const int e = fe_walk_masks(A, B, s, cnt);
                 m |= (uint64_t)e << (4 * s);
                 m |= (uint64_t)cnt << (36 + 3 * s);
             }

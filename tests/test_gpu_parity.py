@@ -446,18 +446,21 @@ def test_cli_binary(tp3, valeurs_text, tmp_path):
 
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_properties(tp3, valeurs_text):
-    """At 10^9 events (10^5 batches, no oracle possible in seconds): (i) range additivity — two
-    half-range launches equal one whole-range launch bit for bit, (ii) acceptance and sigma agree
-    with the 10^7-event golden within Monte-Carlo error, (iii) no NaN anywhere."""
-    n = 10**9
+    """At BASELINE's full size, 10^10 events = 10^6 batches (no oracle possible in seconds): (i) range additivity —
+    two half-range launches folded on the host equal one whole-range launch folded on the device, bit for bit,
+    (ii) acceptance and sigma agree with the 10^7-event golden within Monte-Carlo error, (iii) no NaN anywhere."""
+    n = 10**10
     cfg = tp3.Configuration.parse(valeurs_text).with_num_events(n)
     nb, last = tp3.batch_layout(n)
     with tp3.Simulator(cfg) as sim:
         whole = sim.simulate_merged(0, nb, last)
         a = sim.simulate_batches(0, nb // 2)
         b = sim.simulate_batches(nb // 2, nb - nb // 2, last)
-    total = tp3.fold(list(a) + list(b))
-    assert bytes(total) == bytes(whole)
+    import numpy as np
+    arr = np.concatenate([np.frombuffer(x, dtype=np.dtype([("n", "<u8"), ("f", "<f8", (12,))])) for x in (a, b)])
+    folded = np.add.accumulate(arr["f"], axis=0)[-1]  # sequential left fold per field, like ResultsAccumulator::merge
+    assert int(arr["n"].sum()) == whole.selected_events
+    assert folded.tolist() == list(whole.spm2) + list(whole.vars) + [whole.sigma, whole.variance]
     fin = tp3.finalize(cfg, whole)
     assert abs(fin.selected_events / n - 0.7082165) < 5 * math.sqrt(0.7082 * 0.2918 / n) + 5 * math.sqrt(0.7082 * 0.2918 / 1e7)
     assert abs(fin.sigma - 11.303932414679) < 5 * 0.0028014060468836

@@ -7,10 +7,11 @@
 // are no special-case branches (the operands of this kernel are known to be finite and normal), and
 // the argument reductions use what we know about the inputs:
 //   neg_log      x in (0, 2): 128-entry table of (1/c, -log c) in shared memory + degree-6 log1p
-//   sincos_2pi   u in [0, 1): exact quadrant reduction of t = 4u, degree-6 polynomials in a^2
+//   sincos_256   u in [0, 1): 2 pi u = 2 pi (k + d) / 256, table of 256 directions in shared memory + rotation by
+//                the exact remainder d (|d| <= 1/2) with degree-5 / degree-6 polynomials; no quadrant logic
 //   sqrt / rsqrt / rcp        MUFU seed (RSQ64H / RCP64H) + Newton steps in FMA form
-// Accuracy (tests/test_gpu_parity.py::test_fastmath_accuracy, measured on B200): <= 2 ulp each,
-// i.e. ~1e-16 relative, four orders of magnitude inside the 1e-13 per-event budget that keeps every
+// Accuracy (tests/test_gpu_parity.py::test_fastmath_accuracy, measured on B200): <= 2 ulp for sqrt / rcp / rsqrt,
+// <= 3e-16 (log) and <= 2.5e-16 (sin, cos) absolute, i.e. ~1e-16 relative, four orders of magnitude inside the 1e-13 per-event budget that keeps every
 // accumulated quantity within 1e-10 of the reference.
 #pragma once
 
@@ -19,8 +20,6 @@ namespace tp3 {
 #include "fastmath_tables.inc"
 
 __constant__ double kLog1p[5] = {TP3_LOG1P_COEFFS};
-__constant__ double kSinPoly[7] = {TP3_SIN_COEFFS};
-__constant__ double kCosPoly[7] = {TP3_COS_COEFFS};
 __constant__ double kNegLn2 = TP3_NEG_LN2;
 __constant__ double kRotSin[3] = {TP3_ROT_SIN_COEFFS};
 __constant__ double kRotCos[3] = {TP3_ROT_COS_COEFFS};
@@ -94,38 +93,6 @@ __device__ __forceinline__ double fast_neg_log(double x, const FastMathSmem* sm)
     p = fma(r * r, p, r);  // log1p(r)
     return fma((double)k, kNegLn2, t.y) - p;
 }
-
-// sin(2 pi u), cos(2 pi u) given t = 4u in [0, 4] (quarter turns)
-__device__ __forceinline__ void fast_sincos_quarters(double t, double& s, double& c) {
-    const double qd = rint(t);
-    const int q = __double2int_rn(t);
-    const double a = t - qd;  // exact, |a| <= 1/2
-    const double y = a * a;
-#ifdef TP3_ESTRIN
-    // Estrin form: two more multiplies, half the dependency depth of Horner
-    const double y2 = y * y, y4 = y2 * y2;
-    double ps = fma(y4, fma(y2, kSinPoly[6], fma(y, kSinPoly[5], kSinPoly[4])),
-                    fma(y2, fma(y, kSinPoly[3], kSinPoly[2]), fma(y, kSinPoly[1], kSinPoly[0])));
-    double pc = fma(y4, fma(y2, kCosPoly[6], fma(y, kCosPoly[5], kCosPoly[4])),
-                    fma(y2, fma(y, kCosPoly[3], kCosPoly[2]), fma(y, kCosPoly[1], kCosPoly[0])));
-#else
-    double ps = fma(y, kSinPoly[6], kSinPoly[5]);
-    double pc = fma(y, kCosPoly[6], kCosPoly[5]);
-#pragma unroll
-    for (int i = 4; i >= 0; --i) {
-        ps = fma(y, ps, kSinPoly[i]);
-        pc = fma(y, pc, kCosPoly[i]);
-    }
-#endif
-    ps *= a;
-    // rotate by q quarter turns: (s, c) -> (c, -s) -> (-s, -c) -> (-c, s)
-    const bool swap = q & 1;
-    const double s0 = swap ? pc : ps, c0 = swap ? ps : pc;
-    const int sflip = (int)((unsigned)(q & 2) << 30), cflip = (int)((unsigned)((q + 1) & 2) << 30);
-    s = __hiloint2double(__double2hiint(s0) ^ sflip, __double2loint(s0));
-    c = __hiloint2double(__double2hiint(c0) ^ cflip, __double2loint(c0));
-}
-__device__ __forceinline__ void fast_sincos_2pi(double u, double& s, double& c) { fast_sincos_quarters(4.0 * u, s, c); }
 
 // sin(2 pi u), cos(2 pi u) given t = 256 u in [0, 256]: table of 256 directions + rotation by the remainder.
 // 2 pi u = 2 pi (k + d) / 256 with k = rint(t), |d| <= 1/2 (exact), so the rotation angle is at most pi/256 and

@@ -27,16 +27,12 @@ template <> struct Num<float> {
     static constexpr float RAC8 = 2.0f * 1.41421356237309504880f;
 };
 
-__device__ __forceinline__ void sincospi_t(double x, double* s, double* c) { sincospi(x, s, c); }
-__device__ __forceinline__ void sincospi_t(float x, float* s, float* c) { sincospif(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
 __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __forceinline__ double log_t(double x) { return log(x); }
 __device__ __forceinline__ float log_t(float x) { return logf(x); }
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
-__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
-__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double abs_t(double x) { return fabs(x); }
@@ -81,10 +77,8 @@ template <class F> struct PhysParams {
 };
 
 // ------------------------------------------------------------------ event generation
-// u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187).
-// In the fast variant the phi slot holds PhiScale<F>::value * u (an exact power-of-two scaling) instead of u.
-// p[k] = (X, Y, Z, E) of photon k, optionally sorted by decreasing E (evgen.rs:109-118).
-// Conformal transform of RAMBO to the total energy + optional sort (evgen.rs:94-118)
+// Conformal transform of RAMBO to the total energy + optional sort (evgen.rs:94-118):
+// q[k] = raw (X, Y, Z, E) of photon k  ->  p[k] = (X, Y, Z, E), optionally sorted by decreasing E.
 template <class F, bool SORT, bool LITERAL>
 __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, F p[3][4]) {
     F r[4];
@@ -174,6 +168,8 @@ __device__ __forceinline__ void raw_photon(const F* u, const FastMathSmem* fm, F
     q[3] = en;
 }
 
+// u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187). In the fast
+// variant the phi slot holds PhiScale<F>::value * u (an exact power-of-two scaling) instead of u.
 template <class F, bool SORT, bool LITERAL, class Tick>
 __device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMathSmem* fm, F p[3][4], Tick& tick) {
     F q[3][4];

@@ -501,7 +501,10 @@ int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx*
     ranf_seed_state(RANF_DEFAULT_SEED, c->ranf_base);
     const bool xo = params->flags & TP3_STANDARD_RANDOM;
     if (xo) build_xoshiro_tables(c);
-    else c->ranf_table = ranf_round_jump_table();
+    else {
+        static const std::vector<uint32_t> table = ranf_round_jump_table();  // 1280 polynomial products: built once per process
+        c->ranf_table = table;
+    }
     auto fail = [&](int code, const std::string& msg) {
         g_create_error = msg;
         tp3_destroy(c);

@@ -690,6 +690,10 @@ static int run_dump(tp3_ctx* c, uint64_t batch, uint32_t n_events, uint64_t* wor
         c->err = "per-event dumps are not available under faster-evgen (draw positions are data dependent)";
         return TP3_E_INVALID;
     }
+    if (!(c->params.flags & TP3_STANDARD_RANDOM) && (c->params.flags & TP3_FASTER_THREADING) && batch >= 6200) {
+        c->err = "RANF jump() seeding is only defined for the first 6200 batches (seed < 1e9)";
+        return TP3_E_INVALID;
+    }
     DeviceSlot& s = c->devs[0];
     TP3_CUDA(c, cudaSetDevice(s.dev));
     int rc = ensure_out(c, s, 1);

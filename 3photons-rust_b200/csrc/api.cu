@@ -2,6 +2,7 @@
 // No CPU fallback lives here: without a usable device every compute entry point fails.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -250,28 +251,40 @@ void fe_host_states(tp3_ctx* c, uint64_t first, uint64_t n, std::vector<uint32_t
 // ---- faster-evgen + RANF: batch start states by a scan over per-round transition maps (fe_scan.cuh) ----------
 // Fills s.d_fe_ranf_states[0..n) for batches [first, first + n) of the sequential stream, entirely on the device
 // (the host only chains ~1 segment map per 1024 rounds).
-int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
+// `split` boundaries per batch (1, or 32 with part_len 313): n * split generator states in batch-major order.
+int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t split) {
     const bool f32 = c->params.flags & TP3_F32;
+    const uint32_t part_len = split == 1 ? (uint32_t)TP3_EVENT_BATCH_SIZE : (uint32_t)kLaneEvents;
+    const uint64_t n_bnd = n * split;
+    const bool timing = std::getenv("TP3_FE_TIMING") != nullptr;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    double t_maps = 0, t_chain = 0, t_bnd = 0, t_states = 0;
+    int passes = 0;
     if (first * (uint64_t)TP3_EVENT_BATCH_SIZE < c->scan_events || c->scan_round == 0) {
         c->scan_round = 0;
         c->scan_events = 0;
         c->scan_state = 0;
     }
-    if (s.fe_states_cap < n) {
+    if (s.fe_states_cap < n_bnd) {
         if (s.d_fe_ranf_states) TP3_CUDA(c, cudaFree(s.d_fe_ranf_states));
         s.d_fe_ranf_states = nullptr;
         s.fe_states_cap = 0;
-        TP3_CUDA(c, cudaMalloc(&s.d_fe_ranf_states, n * 57 * sizeof(uint32_t)));
-        s.fe_states_cap = n;
+        TP3_CUDA(c, cudaMalloc(&s.d_fe_ranf_states, n_bnd * 57 * sizeof(uint32_t)));
+        s.fe_states_cap = n_bnd;
     }
     FeBoundary* d_bnd = nullptr;
-    TP3_CUDA(c, cudaMalloc(&d_bnd, n * sizeof(FeBoundary)));
-    const uint64_t last_target = (first + n - 1) * (uint64_t)TP3_EVENT_BATCH_SIZE;  // event index of the last boundary wanted
+    TP3_CUDA(c, cudaMalloc(&d_bnd, n_bnd * sizeof(FeBoundary)));
+    // event index of the last boundary wanted, and of the first one a following call for the next batches would want
+    const uint64_t last_target = (first + n - 1) * (uint64_t)TP3_EVENT_BATCH_SIZE + (uint64_t)(split - 1) * part_len;
+    const uint64_t next_first = (first + n) * (uint64_t)TP3_EVENT_BATCH_SIZE;
     uint64_t* d_maps = nullptr;
     uint8_t *d_seg_exit = nullptr, *d_seg_state = nullptr;
     uint32_t* d_seg_count = nullptr;
     uint64_t* d_seg_events = nullptr;
-    size_t maps_cap = 0;
+    size_t maps_cap = 0, seg_cap = 0;
     int rc = TP3_OK;
     auto cleanup = [&]() {
         cudaFree(d_bnd); cudaFree(d_maps); cudaFree(d_seg_exit); cudaFree(d_seg_state); cudaFree(d_seg_count); cudaFree(d_seg_events);
@@ -284,32 +297,40 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n)
         return e == cudaSuccess;
     };
     // a boundary is found when the running event count passes it: scan until the count exceeds last_target
-    while (rc == TP3_OK && c->scan_events <= last_target) {
+    while (rc == TP3_OK) {
         const uint64_t remaining = last_target + 1 - c->scan_events;
-        uint64_t n_rounds = (uint64_t)((double)remaining * 0.36) + 4 * kFeSegRounds;  // ~0.32 rounds per event
-        if (n_rounds > (1ull << 24)) n_rounds = 1ull << 24;                            // 128 MB of maps per pass
-        const uint64_t n_seg = (n_rounds + kFeSegRounds - 1) / kFeSegRounds;
-        if (maps_cap < n_rounds) {
+        uint64_t n_rounds = (uint64_t)((double)remaining * 0.325) + 8192;  // 0.3206 rounds per event (16.64 numbers + 3.1 discarded per round)
+        if (n_rounds > (1ull << 27)) n_rounds = 1ull << 27;                 // 1 GB of maps per pass
+        // one lane per segment: enough segments to fill the device (~8 warps per scheduler), as long as possible otherwise
+        uint32_t seg_rounds = 64;
+        while (seg_rounds < (uint32_t)kFeMaxSegRounds && n_rounds / (2 * seg_rounds) >= (uint64_t)s.sm_count * 4 * 8 * 32) seg_rounds *= 2;
+        const uint64_t n_seg = (n_rounds + seg_rounds - 1) / seg_rounds;
+        if (maps_cap < n_rounds || seg_cap < n_seg) {
             cudaFree(d_maps); cudaFree(d_seg_exit); cudaFree(d_seg_state); cudaFree(d_seg_count); cudaFree(d_seg_events);
             d_maps = nullptr; d_seg_exit = d_seg_state = nullptr; d_seg_count = nullptr; d_seg_events = nullptr;
+            maps_cap = seg_cap = 0;
             if (!check(cudaMalloc(&d_maps, n_rounds * 8), "cudaMalloc maps")) break;
             if (!check(cudaMalloc(&d_seg_exit, n_seg * 9), "cudaMalloc")) break;
             if (!check(cudaMalloc(&d_seg_state, n_seg), "cudaMalloc")) break;
             if (!check(cudaMalloc(&d_seg_count, n_seg * 9 * 4), "cudaMalloc")) break;
             if (!check(cudaMalloc(&d_seg_events, n_seg * 8), "cudaMalloc")) break;
             maps_cap = n_rounds;
+            seg_cap = n_seg;
         }
-        const unsigned map_blocks = (unsigned)((n_seg + 3) / 4), seg_blocks = (unsigned)((n_seg + 127) / 128);
-        if (f32) fe_round_maps_kernel<float><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, d_maps);
-        else fe_round_maps_kernel<double><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, d_maps);
-        fe_segment_kernel<<<seg_blocks, 128, 0, s.stream>>>(d_maps, n_rounds, d_seg_exit, d_seg_count);
+        const unsigned map_blocks = (unsigned)((n_seg + 127) / 128), seg_blocks = (unsigned)((n_seg + 127) / 128);
+        if (f32) fe_round_maps_kernel<float><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, seg_rounds, d_maps);
+        else fe_round_maps_kernel<double><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, seg_rounds, d_maps);
+        fe_segment_kernel<<<seg_blocks, 128, 0, s.stream>>>(d_maps, n_rounds, seg_rounds, d_seg_exit, d_seg_count);
         c->launches += 2;
+        ++passes;
+        auto t0 = now();
         std::vector<uint8_t> seg_exit(n_seg * 9), seg_state(n_seg);
         std::vector<uint32_t> seg_count(n_seg * 9);
         std::vector<uint64_t> seg_events(n_seg);
         if (!check(cudaMemcpyAsync(seg_exit.data(), d_seg_exit, n_seg * 9, cudaMemcpyDeviceToHost, s.stream), "D2H")) break;
         if (!check(cudaMemcpyAsync(seg_count.data(), d_seg_count, n_seg * 9 * 4, cudaMemcpyDeviceToHost, s.stream), "D2H")) break;
         if (!check(cudaStreamSynchronize(s.stream), "fe scan maps")) break;
+        auto t1 = now();
         int state = c->scan_state;
         uint64_t events = c->scan_events;
         for (uint64_t g = 0; g < n_seg; ++g) {  // chain the segment maps (multi_threading.rs:59-64 does this event by event)
@@ -320,27 +341,48 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n)
         }
         if (!check(cudaMemcpyAsync(d_seg_state, seg_state.data(), n_seg, cudaMemcpyHostToDevice, s.stream), "H2D")) break;
         if (!check(cudaMemcpyAsync(d_seg_events, seg_events.data(), n_seg * 8, cudaMemcpyHostToDevice, s.stream), "H2D")) break;
-        fe_boundaries_kernel<<<seg_blocks, 128, 0, s.stream>>>(d_maps, c->scan_round, n_rounds, d_seg_state, d_seg_events, first, n, d_bnd);
+        auto t2 = now();
+        fe_boundaries_kernel<<<seg_blocks, 128, 0, s.stream>>>(d_maps, c->scan_round, n_rounds, seg_rounds, d_seg_state, d_seg_events, split,
+                                                               part_len, first * split, n_bnd, d_bnd);
         ++c->launches;
         if (!check(cudaStreamSynchronize(s.stream), "fe boundaries")) break;  // the host vectors die with this iteration
+        t_maps += ms(t0, t1);
+        t_chain += ms(t1, t2);
+        t_bnd += ms(t2, now());
+        if (events > last_target) {
+            // Done. Leave the scan at the last segment start that a call for the following batches can resume from.
+            uint64_t g = n_seg - 1;
+            while (g > 0 && seg_events[g] > next_first) --g;
+            c->scan_round += g * seg_rounds;
+            c->scan_events = seg_events[g];
+            c->scan_state = seg_state[g];
+            break;
+        }
         c->scan_round += n_rounds;
         c->scan_events = events;
         c->scan_state = state;
     }
     if (rc == TP3_OK) {
-        const unsigned blocks = (unsigned)((n + 3) / 4);
-        if (f32) fe_batch_states_kernel<float><<<blocks, 128, 0, s.stream>>>(s.d_ranf_table, d_bnd, n, s.d_fe_ranf_states);
-        else fe_batch_states_kernel<double><<<blocks, 128, 0, s.stream>>>(s.d_ranf_table, d_bnd, n, s.d_fe_ranf_states);
+        auto t0 = now();
+        const uint32_t chain = split == 1 ? 4 : split;
+        const unsigned blocks = (unsigned)(((n_bnd + chain - 1) / chain + 3) / 4);
+        if (f32) fe_batch_states_kernel<float><<<blocks, 128, 0, s.stream>>>(s.d_ranf_table, d_bnd, n_bnd, chain, s.d_fe_ranf_states);
+        else fe_batch_states_kernel<double><<<blocks, 128, 0, s.stream>>>(s.d_ranf_table, d_bnd, n_bnd, chain, s.d_fe_ranf_states);
         ++c->launches;
         check(cudaGetLastError(), "fe batch states");
         check(cudaStreamSynchronize(s.stream), "fe batch states");
+        t_states = ms(t0, now());
     }
+    if (timing)
+        std::fprintf(stderr, "[tp3 fe scan] batches %llu split %u passes %d: maps+segments %.2f ms, host chain %.2f ms, boundaries %.2f ms, states %.2f ms\n",
+                     (unsigned long long)n, split, passes, t_maps, t_chain, t_bnd, t_states);
     cleanup();
     return rc;
 }
 
 template <class F, int RNG> void launch_fe(const FeArgs& a, const tp3_params& p, cudaStream_t st) {
-    faster_evgen_kernel<F, RNG><<<(unsigned)((a.n_batches + kFeThreads - 1) / kFeThreads), kFeThreads, 0, st>>>(a, phys_params<F>(p));
+    const uint64_t units = a.n_batches * a.split;
+    faster_evgen_kernel<F, RNG><<<(unsigned)((units + kFeThreads - 1) / kFeThreads), kFeThreads, 0, st>>>(a, phys_params<F>(p));
 }
 
 int ensure_out(tp3_ctx* c, DeviceSlot& s, uint64_t n) {
@@ -412,8 +454,14 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     std::vector<uint32_t> fe_ranf;
     std::vector<uint64_t> fe_xo;
     const bool device_scan = seq_faster && !(c->params.flags & TP3_STANDARD_RANDOM) && !std::getenv("TP3_FE_HOST_SCAN");
+    uint32_t fe_split = 1;
     if (device_scan) {
-        rc = fe_device_states_ranf(c, s, first, n);
+        // One lane per 313 events: fills the device for any run size and keeps a warp's lanes on one batch (measured
+        // faster than one thread per batch at every size).  Costs 7.3 KB of start states per batch, so very long
+        // ranges fall back to one thread per batch.
+        fe_split = n <= (1ull << 20) ? 32 : 1;
+        if (const char* e = std::getenv("TP3_FE_SPLIT")) fe_split = std::atoi(e) == 32 ? 32 : 1;  // test hook
+        rc = fe_device_states_ranf(c, s, first, n, fe_split);
         if (rc) return rc;
     } else if (seq_faster) {
         fe_host_states(c, first, n, fe_ranf, fe_xo);
@@ -454,6 +502,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         f.n_batches = n;
         f.last_batch_len = last_len;
         f.jump_seeding = a.jump_seeding;
+        f.split = fe_split;
         f.ranf_states = s.d_fe_ranf_states;
         f.xo_states = s.d_xo_states;
         f.out = s.d_out;

@@ -7,8 +7,9 @@
 // the batch, which is exactly why the reference's reproducible multi-threaded mode re-runs the
 // rejection loop on its scheduler thread (evgen.rs:257-267, "Bottleneck!" in VALIDATION.md:46-48).
 //
-// To reproduce the reference's integers exactly, the stream of one batch is walked sequentially:
-// ONE THREAD = ONE BATCH (32 consecutive batches per warp), private generator state per thread
+// To reproduce the reference's integers exactly, the stream is walked sequentially from known start states:
+// ONE THREAD = ONE BATCH (32 consecutive batches per warp) or, when the scan also supplies the states at the 32
+// lane boundaries inside every batch (fe_scan.cuh), ONE THREAD = 313 EVENTS; private generator state per thread
 // (RANF: 56 words in shared memory, column layout, so a warp's accesses are conflict free; xoshiro:
 // registers).  Batch start states come from the scheduler: the host pre-advances its generator batch by
 // batch exactly like the reference's scheduler thread does, or, under faster-threading, every batch is
@@ -28,7 +29,8 @@ struct FeArgs {
     uint64_t n_batches;
     uint32_t last_batch_len;
     uint32_t jump_seeding;
-    const uint32_t* ranf_states;   // [n_batches][57]: numbers[0..55] + index (sequential mode)
+    uint32_t split;                // 1: one thread per batch; 32: one warp per batch, lane l owns events [313 l, 313 (l + 1))
+    const uint32_t* ranf_states;   // [n_batches * split][57]: numbers[0..55] + index (sequential mode)
     const uint64_t* xo_states;     // [n_batches][4]
     tp3_acc* out;
     int32_t ranf_seed;
@@ -93,7 +95,8 @@ template <> struct XoThread<float> {
 };
 
 template <class F, class Gen>
-__device__ __forceinline__ void fe_simulate(Gen& gen, int n_ev, const PhysParams<F>& P, const FastMathSmem* fm, tp3_acc* out) {
+__device__ __forceinline__ void fe_simulate(Gen& gen, int n_ev, const PhysParams<F>& P, const FastMathSmem* fm, bool warp_reduce,
+                                            tp3_acc* out) {
     LaneAcc<F> acc;
     acc.clear();
     for (int ev = 0; ev < n_ev; ++ev) {
@@ -125,6 +128,20 @@ __device__ __forceinline__ void fe_simulate(Gen& gen, int n_ev, const PhysParams
             acc.integrate(m, P.sigma_contribs);
         }
     }
+    if (warp_reduce) {  // warp-uniform: the 32 lanes hold the parts of one batch (same tree as simulate_kernel)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                acc.spm2[k] += shfl_xor_t(acc.spm2[k], off);
+                acc.vars[k] += shfl_xor_t(acc.vars[k], off);
+            }
+            acc.sigma += shfl_xor_t(acc.sigma, off);
+            acc.variance += shfl_xor_t(acc.variance, off);
+            acc.selected += __shfl_xor_sync(0xffffffffu, acc.selected, off);
+        }
+        if (threadIdx.x & 31) return;
+    }
     out->selected_events = acc.selected;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -141,9 +158,13 @@ __global__ void __launch_bounds__(kFeThreads) faster_evgen_kernel(const FeArgs a
     __shared__ uint32_t ranf_state[RNG == RNG_RANF ? 56 * kFeThreads : 1];
     fastmath_load(&fm);
     __syncthreads();
-    const uint64_t slot = (uint64_t)blockIdx.x * kFeThreads + threadIdx.x;
-    if (slot >= a.n_batches) return;
-    const int n_ev = (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
+    const uint64_t unit = (uint64_t)blockIdx.x * kFeThreads + threadIdx.x;
+    const bool split = a.split == 32;
+    const uint64_t slot = split ? unit >> 5 : unit;
+    if (slot >= a.n_batches) return;  // whole warps when split
+    const int n_batch = (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
+    const int part = split ? (int)(unit & 31) : 0;
+    const int n_ev = split ? max(0, min(n_batch - part * kLaneEvents, kLaneEvents)) : n_batch;
     const uint64_t batch = a.first_batch + slot;
     if (RNG == RNG_RANF) {
         RanfThread<F> gen;
@@ -151,11 +172,11 @@ __global__ void __launch_bounds__(kFeThreads) faster_evgen_kernel(const FeArgs a
         if (a.jump_seeding) {
             gen.seed((int32_t)((uint32_t)a.ranf_seed + 123456u * (uint32_t)batch));
         } else {
-            const uint32_t* s = a.ranf_states + slot * 57;
+            const uint32_t* s = a.ranf_states + unit * 57;
             for (int i = 0; i < 56; ++i) gen.n(i) = s[i];
             gen.index = (int)s[56];
         }
-        fe_simulate<F, RanfThread<F>>(gen, n_ev, P, &fm, a.out + slot);
+        fe_simulate<F, RanfThread<F>>(gen, n_ev, P, &fm, split, a.out + slot);
     } else {
         XoThread<F> gen;
         const uint64_t* s = a.xo_states + 4 * slot;
@@ -163,7 +184,7 @@ __global__ void __launch_bounds__(kFeThreads) faster_evgen_kernel(const FeArgs a
         gen.g.s1 = (decltype(gen.g.s0))s[1];
         gen.g.s2 = (decltype(gen.g.s0))s[2];
         gen.g.s3 = (decltype(gen.g.s0))s[3];
-        fe_simulate<F, XoThread<F>>(gen, n_ev, P, &fm, a.out + slot);
+        fe_simulate<F, XoThread<F>>(gen, n_ev, P, &fm, split, a.out + slot);
     }
 }
 

@@ -10,13 +10,14 @@
 //     6 + f2       re-rolling point 1
 //     8            re-rolling point 2
 // and what happens inside the round depends only on that state and on the round's 55 numbers.  Hence
-//   1. fe_round_maps_kernel   for every round and every entry state: exit state + number of events started
-//                             (one lane per round, so the 32 lanes of a warp run the same code on different data);
-//   2. fe_segment_kernel      composes the maps of 1024 consecutive rounds (one thread per segment);
+//   1. fe_round_maps_kernel   for every round and every entry state that can occur: exit state + number of events
+//                             started (one lane per segment of consecutive rounds, private generator per lane);
+//   2. fe_segment_kernel      composes the maps of the rounds of a segment (one thread per segment);
 //   3. (host)                 chains the segment maps: entry state and event count at every segment start;
 //   4. fe_boundaries_kernel   re-walks the per-round maps of a segment with its true entry state and records
-//                             for every batch boundary (event index 10000 b) the round, entry state and rank of
-//                             that event start inside the round;
+//                             for every boundary (event index 10000 b, or 10000 b + 313 l when the batch kernel
+//                             runs one lane per 313 events) the round, entry state and rank of that event start
+//                             inside the round;
 //   5. fe_batch_states_kernel regenerates that round by jump-ahead, walks to the boundary and writes the
 //                             generator state (numbers[0..55], index) the batch kernel starts from.
 // The accept / re-roll test is evaluated exactly as the reference does (run's Float, no FMA contraction).
@@ -26,8 +27,8 @@
 
 namespace tp3 {
 
-constexpr int kFeSegRounds = 1024;  // rounds per segment
-constexpr int kFeTile = 32;         // rounds walked in parallel by one warp
+constexpr int kFeMaxSegRounds = 1024;  // rounds per segment (the host picks a power of two up to this)
+constexpr int kFeTile = 32;             // segments walked in parallel by one warp
 
 template <class F> __device__ __forceinline__ bool fe_outside(uint32_t a, uint32_t b) {
     const F ua = sizeof(F) == 8 ? (F)((double)(int)a * 1e-9) : (F)((float)(int)a * 1e-9f);
@@ -112,64 +113,116 @@ __device__ __forceinline__ int fe_walk_masks(uint64_t A, uint64_t B, int s, int&
 __device__ __forceinline__ int fe_map_exit(uint64_t m, int s) { return (int)((m >> (4 * s)) & 15u); }
 __device__ __forceinline__ int fe_map_count(uint64_t m, int s) { return (int)((m >> (36 + 3 * s)) & 7u); }
 
+// One round for one lane: (GEN) advance the lane's private generator by one round in place (ranf.rs:106-119 on
+// row[k] = numbers[k + 1]) and evaluate the disc tests of the new round, every number converted once.
+template <class F> __device__ __forceinline__ F fe_disc_term(uint32_t w) {
+    const F u = sizeof(F) == 8 ? (F)u32_times(w, 1e-9) : (F)((float)(int)w * 1e-9f);
+    const F x = (F)2 * u - (F)1;
+    return mul_rn(x, x);
+}
+template <class F, bool GEN> __device__ __forceinline__ void fe_round_fused(uint32_t* row, uint64_t& A, uint64_t& B) {
+    uint32_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
+    uint32_t nw[kRanfLag];
+    F q[kRanfLag];
+#pragma unroll
+    for (int k = 0; k < kRanfLag; ++k) {
+        uint32_t v = row[k];
+        if (GEN) {
+            v = ranf_sub(v, k < 24 ? row[k + 31] : nw[k - 24]);
+            row[k] = v;
+        }
+        nw[k] = v;
+        q[k] = fe_disc_term<F>(v);
+        if (k >= 1 && add_rn(q[k - 1], q[k]) > (F)1) {
+            if (k - 1 < 32) a_lo |= 1u << ((k - 1) & 31);
+            else a_hi |= 1u << ((k - 1) & 31);
+        }
+        if (k >= 3 && add_rn(q[k - 3], q[k]) > (F)1) {
+            if (k - 3 < 32) b_lo |= 1u << ((k - 3) & 31);
+            else b_hi |= 1u << ((k - 3) & 31);
+        }
+    }
+    A = ((uint64_t)a_hi << 32) | a_lo;
+    B = ((uint64_t)b_hi << 32) | b_lo;
+}
+
 struct FeScanSmem {
     uint32_t win[2 * kRanfLag + 2];
-    uint32_t tile[kFeTile][kRanfLag + 2];  // 32 consecutive rounds, slot order; odd row stride (57): lane = row reads are conflict free
+    uint32_t tile[kFeTile][kRanfLag + 2];  // one private generator per lane; odd row stride (57): lane = row accesses are conflict free
 };
 
-// 1. per-round maps for rounds [first_round, first_round + n_rounds); one warp per segment of kFeSegRounds rounds
+constexpr uint64_t kFeNine4 = 0x111111111ull;  // replicates a 4-bit field nine times
+constexpr uint64_t kFeNine3 = 0111111111ull;   // (octal) replicates a 3-bit field nine times
+
+// 1. per-round maps for rounds [first_round, first_round + n_rounds), cut into segments of seg_rounds rounds.
+// ONE LANE = ONE SEGMENT, walked round after round with a private generator (started by jump-ahead), so that the
+// walk only follows the states that are still possible: all nine entry states of the segment at its first round,
+// the image of those nine afterwards.  The images collapse to a single state within a few rounds (requests that do
+// not fit leave every walk at a round start); from then on a round costs one walk and its map word carries that one
+// (exit, count) pair in all nine fields.  Entries of states that no walk from the segment start can be in are 0;
+// nothing downstream ever reads them.
 template <class F>
 __global__ void __launch_bounds__(128) fe_round_maps_kernel(const uint32_t* __restrict__ jump_table, uint64_t first_round,
-                                                          uint64_t n_rounds, uint64_t* __restrict__ maps) {
+                                                          uint64_t n_rounds, uint32_t seg_rounds, uint64_t* __restrict__ maps) {
     __shared__ FeScanSmem sm[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FeScanSmem& w = sm[warp];
-    const uint64_t seg = (uint64_t)blockIdx.x * 4 + warp;
-    const uint64_t r0 = seg * kFeSegRounds;
-    if (r0 >= n_rounds) return;
-    const int n_seg = (int)min((uint64_t)kFeSegRounds, n_rounds - r0);
+    const uint64_t seg0 = ((uint64_t)blockIdx.x * 4 + warp) * kFeTile;
+    if (seg0 * seg_rounds >= n_rounds) return;
     // the seeded round 0 travels at the end of the jump table allocation (see api.cu)
-    ranf_jump_to_round(w.win, jump_table + (size_t)kRanfDigits * 256 * kRanfLag, first_round + r0, jump_table, lane);
-    for (int i = lane; i < kRanfLag; i += 32) w.tile[0][i] = w.win[i];
-    __syncwarp();
-    for (int t0 = 0; t0 < n_seg; t0 += kFeTile) {
-        // rows 1..31 from row 0 (row 0 of the next tile from row 31 at the end)
-        for (int r = 1; r < kFeTile; ++r) {
-            for (int i = lane + 1; i <= kRanfLag; i += 32) w.tile[r][i - 1] = ranf_next_slot(w.tile[r - 1], i);
-            __syncwarp();
-        }
-        if (t0 + lane < n_seg) {
-            uint64_t A, B, m = 0;
-            fe_round_masks<F>(w.tile[lane], A, B);
-#pragma unroll 1
-            for (int s = 0; s < 9; ++s) {
+    const uint32_t* base = jump_table + (size_t)kRanfDigits * 256 * kRanfLag;
+    for (int k = 0; k < kFeTile; ++k) {
+        const uint64_t r = (seg0 + k) * seg_rounds;
+        if (r >= n_rounds) break;  // warp-uniform
+        ranf_jump_to_round(w.win, base, first_round + r, jump_table, lane);
+        for (int i = lane; i < kRanfLag; i += 32) w.tile[k][i] = w.win[i];
+        __syncwarp();
+    }
+    const uint64_t r0 = (seg0 + lane) * seg_rounds;
+    const int n_mine = r0 < n_rounds ? (int)min((uint64_t)seg_rounds, n_rounds - r0) : 0;
+    const int n_max = __shfl_sync(0xffffffffu, n_mine, 0);  // lane 0 owns the earliest segment, hence the longest
+    uint32_t* row = w.tile[lane];
+    uint64_t cur = 0x876543210ull;  // where each of the nine segment-entry states is now
+    bool single = false;
+    for (int t = 0; t < n_max; ++t) {
+        if (t >= n_mine) continue;
+        uint64_t A, B, m;
+        if (t == 0) fe_round_fused<F, false>(row, A, B);
+        else fe_round_fused<F, true>(row, A, B);
+        if (single) {
+            int cnt;
+            const int e = fe_walk_masks(A, B, (int)(cur & 15u), cnt);
+            m = (uint64_t)e * kFeNine4 | ((uint64_t)cnt * kFeNine3) << 36;
+            cur = (uint64_t)e;
+        } else {
+            uint32_t img = 0;
+#pragma unroll
+            for (int s = 0; s < 9; ++s) img |= 1u << ((cur >> (4 * s)) & 15u);
+            m = 0;
+            while (img) {
+                const int s = __ffs(img) - 1;
+                img &= img - 1;
                 int cnt;
                 const int e = fe_walk_masks(A, B, s, cnt);
-                m |= (uint64_t)e << (4 * s);
-                m |= (uint64_t)cnt << (36 + 3 * s);
+                m |= (uint64_t)e << (4 * s) | (uint64_t)cnt << (36 + 3 * s);
             }
-            maps[r0 + t0 + lane] = m;
+            uint64_t nxt = 0;
+#pragma unroll
+            for (int s = 0; s < 9; ++s) nxt |= (uint64_t)fe_map_exit(m, (int)((cur >> (4 * s)) & 15u)) << (4 * s);
+            cur = nxt;
+            single = cur == (cur & 15u) * kFeNine4;
         }
-        __syncwarp();
-        if (t0 + kFeTile < n_seg) {
-            uint32_t a = 0, b = 0;
-            if (lane + 1 <= kRanfLag) a = ranf_next_slot(w.tile[kFeTile - 1], lane + 1);
-            if (lane + 33 <= kRanfLag) b = ranf_next_slot(w.tile[kFeTile - 1], lane + 33);
-            __syncwarp();
-            w.tile[0][lane] = a;
-            if (lane + 32 < kRanfLag) w.tile[0][lane + 32] = b;
-            __syncwarp();
-        }
+        maps[r0 + t] = m;
     }
 }
 
 // 2. composed map of every segment: for each entry state, the exit state and the number of events started
-__global__ void fe_segment_kernel(const uint64_t* __restrict__ maps, uint64_t n_rounds, uint8_t* __restrict__ seg_exit,
-                                  uint32_t* __restrict__ seg_count) {
+__global__ void fe_segment_kernel(const uint64_t* __restrict__ maps, uint64_t n_rounds, uint32_t seg_rounds,
+                                  uint8_t* __restrict__ seg_exit, uint32_t* __restrict__ seg_count) {
     const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t r0 = seg * kFeSegRounds;
+    const uint64_t r0 = seg * seg_rounds;
     if (r0 >= n_rounds) return;
-    const uint64_t r1 = min(n_rounds, r0 + kFeSegRounds);
+    const uint64_t r1 = min(n_rounds, r0 + seg_rounds);
     int cur[9];
     uint32_t cnt[9];
     for (int s = 0; s < 9; ++s) {
@@ -196,54 +249,71 @@ struct FeBoundary {
     uint32_t rank;    // the boundary is the rank-th event start of the round (0-based)
 };
 
-// 4. batch boundaries inside every segment. seg_state / seg_events: entry state and global event index at the segment start.
-__global__ void fe_boundaries_kernel(const uint64_t* __restrict__ maps, uint64_t first_round, uint64_t n_rounds,
+// 4. boundaries inside every segment. seg_state / seg_events: entry state and global event index at the segment start.
+// Boundary j (global) is the event 10000 (j / split) + part_len (j % split): every batch start (split = 1), or every
+// lane start inside every batch (split = 32, part_len = 313).  Boundaries are further apart than the events one round
+// can start, so a round holds at most one.
+__device__ __forceinline__ uint64_t fe_boundary_event(uint64_t j, uint32_t split, uint32_t part_len) {
+    return (j / split) * (uint64_t)kBatch + (j % split) * (uint64_t)part_len;
+}
+__global__ void fe_boundaries_kernel(const uint64_t* __restrict__ maps, uint64_t first_round, uint64_t n_rounds, uint32_t seg_rounds,
                                      const uint8_t* __restrict__ seg_state, const uint64_t* __restrict__ seg_events,
-                                     uint64_t first_batch, uint64_t n_batches, FeBoundary* __restrict__ out) {
+                                     uint32_t split, uint32_t part_len, uint64_t first_boundary, uint64_t n_boundaries,
+                                     FeBoundary* __restrict__ out) {
     const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t r0 = seg * kFeSegRounds;
+    const uint64_t r0 = seg * seg_rounds;
     if (r0 >= n_rounds) return;
-    const uint64_t r1 = min(n_rounds, r0 + kFeSegRounds);
+    const uint64_t r1 = min(n_rounds, r0 + seg_rounds);
     int cur = seg_state[seg];
     uint64_t ev = seg_events[seg];
     // next boundary at or after ev
-    uint64_t b = (ev + kBatch - 1) / kBatch;
+    const uint64_t rem = ev % kBatch;
+    uint64_t j = (ev / kBatch) * split + min((uint64_t)split, (rem + part_len - 1) / part_len);
+    uint64_t target = fe_boundary_event(j, split, part_len);
     for (uint64_t r = r0; r < r1; ++r) {
         const uint64_t m = maps[r];
         const int c = fe_map_count(m, cur);
-        const uint64_t target = b * kBatch;
         if (target < ev + c) {  // (target >= ev by construction)
-            if (b >= first_batch && b < first_batch + n_batches) {
+            if (j >= first_boundary && j < first_boundary + n_boundaries) {
                 FeBoundary o;
                 o.round = first_round + r;
                 o.state = (uint32_t)cur;
                 o.rank = (uint32_t)(target - ev);
-                out[b - first_batch] = o;
+                out[j - first_boundary] = o;
             }
-            ++b;
+            ++j;
+            target = fe_boundary_event(j, split, part_len);
         }
         ev += c;
         cur = fe_map_exit(m, cur);
     }
 }
 
-// 5. generator state at every batch boundary: numbers[0..55] + index, the layout faster_evgen_kernel reads
+// 5. generator state at every boundary: numbers[0..55] + index, the layout faster_evgen_kernel reads.  One warp per
+// run of `chain` consecutive boundaries: a full jump-ahead to the first one, short relative jumps to the others.
 template <class F>
 __global__ void __launch_bounds__(128) fe_batch_states_kernel(const uint32_t* __restrict__ jump_table, const FeBoundary* __restrict__ bnd,
-                                                            uint64_t n_batches, uint32_t* __restrict__ states) {
+                                                            uint64_t n_boundaries, uint32_t chain, uint32_t* __restrict__ states) {
     __shared__ uint32_t win[4][2 * kRanfLag + 2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t i = (uint64_t)blockIdx.x * 4 + warp;
-    if (i >= n_batches) return;
-    const FeBoundary b = bnd[i];
-    ranf_jump_to_round(win[warp], jump_table + (size_t)kRanfDigits * 256 * kRanfLag, b.round, jump_table, lane);
-    uint32_t* o = states + i * 57;
-    for (int k = lane; k < kRanfLag; k += 32) o[1 + k] = win[warp][k];
-    if (lane == 0) {
-        int cnt, idx = 55;
-        fe_walk_round<F>(win[warp], 1, (int)b.state, cnt, (int)b.rank, &idx);
-        o[0] = 0;
-        o[56] = (uint32_t)idx;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * 4 + warp) * chain;
+    if (i0 >= n_boundaries) return;
+    const uint64_t i1 = min(n_boundaries, i0 + chain);
+    uint64_t at = 0;
+    for (uint64_t i = i0; i < i1; ++i) {
+        const FeBoundary b = bnd[i];
+        if (i == i0) ranf_jump_to_round(win[warp], jump_table + (size_t)kRanfDigits * 256 * kRanfLag, b.round, jump_table, lane);
+        else ranf_jump_to_round(win[warp], win[warp], b.round - at, jump_table, lane);  // boundaries are in stream order
+        at = b.round;
+        uint32_t* o = states + i * 57;
+        for (int k = lane; k < kRanfLag; k += 32) o[1 + k] = win[warp][k];
+        if (lane == 0) {
+            int cnt, idx = 55;
+            fe_walk_round<F>(win[warp], 1, (int)b.state, cnt, (int)b.rank, &idx);
+            o[0] = 0;
+            o[56] = (uint32_t)idx;
+        }
+        __syncwarp();
     }
 }
 

@@ -1,0 +1,22 @@
+"""faster-evgen timing probe (development aid): events/s of the exact sequential-stream path at several sizes,
+one thread per batch (split 1) vs one lane per 313 events (split 32); TP3_FE_TIMING=1 prints the scan phases."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+pkg = g.package()
+text = open(os.path.join(g.ROOT, "tests", "golden", "valeurs")).read()
+sizes = [int(x) for x in sys.argv[1:]] or [1000, 20000, 200000]
+for features in ["faster-evgen,no-photon-sorting", "faster-evgen,f32"]:
+    cfg = pkg.Configuration.parse(text, features)
+    with pkg.Simulator(cfg, 0) as sim:
+        sim.simulate_merged(0, 100)
+        for n_batches in sizes:
+            for split in ("1", "32"):
+                os.environ["TP3_FE_SPLIT"] = split
+                best = 1e9
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    acc = sim.simulate_merged(0, n_batches)
+                    best = min(best, time.perf_counter() - t0)
+                ev = n_batches * 10000
+                print(f"features={features!r:34} batches={n_batches:8d} split={split:>2} {ev/best:.4g} events/s ({best*1e3:.1f} ms) selected={acc.selected_events}", flush=True)

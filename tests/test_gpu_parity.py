@@ -354,21 +354,33 @@ def test_faster_evgen_batches_match_oracle(sims, oracle, valeurs_text, features)
     assert bytes(again) == bytes((type(again))(*accs[3:7]))
 
 
+@pytest.mark.parametrize("split", [1, 32])
 @pytest.mark.parametrize("features,first,nb", [("faster-evgen", 0, 300), ("faster-evgen", 4990, 260), ("faster-evgen,f32", 7, 64)])
-def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, monkeypatch):
-    """The batch start states of the sequential RANF stream come from a scan over per-round transition maps on the
-    GPU (fe_scan.cuh); the reference's own method — walking the stream event by event on the scheduler thread,
-    evgen.rs:257-267 — is kept on the host behind TP3_FE_HOST_SCAN for this cross-check: identical bits.
-    (4990 + 260 batches = 5.25e7 events cross the 2^24-round pass boundary of the scan.)"""
+def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, split, monkeypatch):
+    """The start states of the sequential RANF stream come from a scan over per-round transition maps on the GPU
+    (fe_scan.cuh); the reference's own method — walking the stream event by event on the scheduler thread,
+    evgen.rs:257-267 — is kept on the host behind TP3_FE_HOST_SCAN for this cross-check.
+    split = 1: one thread per batch from the scanned batch starts: identical bits.
+    split = 32: the scan also locates the 32 lane starts inside every batch and a warp shares the batch: identical
+    event selection (one differing draw position would change it), sums equal up to the order of the additions.
+    The last batch is ragged (1234 events: most lanes of its warp have nothing to do)."""
     cfg = tp3.Configuration.parse(valeurs_text, features)
+    monkeypatch.setenv("TP3_FE_SPLIT", str(split))
     with tp3.Simulator(cfg) as sim:
-        dev = sim.simulate_batches(first, nb)
+        dev = sim.simulate_batches(first, nb, 1234)
         dev_again = sim.simulate_batches(first + 5, 20)  # continues / restarts the cached scan
     monkeypatch.setenv("TP3_FE_HOST_SCAN", "1")
     with tp3.Simulator(cfg) as sim:
-        host = sim.simulate_batches(first, nb)
-    assert bytes(dev) == bytes(host)
-    assert bytes(dev_again) == bytes((type(dev_again))(*host[5:25]))
+        host = sim.simulate_batches(first, nb, 1234)
+        host_again = sim.simulate_batches(first + 5, 20)
+    if split == 1:
+        assert bytes(dev) == bytes(host)
+        assert bytes(dev_again) == bytes(host_again)
+        return
+    rel = 1e-12 if "f32" not in features else 5e-5
+    for got, want in list(zip(dev, host)) + list(zip(dev_again, host_again)):
+        assert got.selected_events == want.selected_events
+        assert_acc_close(got, want, rel, what="split 32 vs host walk")
 
 
 def test_faster_evgen_f32_batches(sims, oracle, valeurs_text):

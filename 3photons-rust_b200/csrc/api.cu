@@ -300,7 +300,7 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n,
     while (rc == TP3_OK) {
         const uint64_t remaining = last_target + 1 - c->scan_events;
         uint64_t n_rounds = (uint64_t)((double)remaining * 0.325) + 8192;  // 0.3206 rounds per event (16.64 numbers + 3.1 discarded per round)
-        if (n_rounds > (1ull << 27)) n_rounds = 1ull << 27;                 // 1 GB of maps per pass
+        if (n_rounds > (1ull << 28)) n_rounds = 1ull << 28;                 // 2 GB of maps per pass
         // one lane per segment: enough segments to fill the device (~8 warps per scheduler), as long as possible otherwise
         uint32_t seg_rounds = 64;
         while (seg_rounds < (uint32_t)kFeMaxSegRounds && n_rounds / (2 * seg_rounds) >= (uint64_t)s.sm_count * 4 * 8 * 32) seg_rounds *= 2;

@@ -27,7 +27,7 @@
 
 namespace tp3 {
 
-constexpr int kFeMaxSegRounds = 1024;  // rounds per segment (the host picks a power of two up to this)
+constexpr int kFeMaxSegRounds = 2048;  // rounds per segment (the host picks a power of two up to this)
 constexpr int kFeTile = 32;             // segments walked in parallel by one warp
 
 template <class F> __device__ __forceinline__ bool fe_outside(uint32_t a, uint32_t b) {
@@ -90,21 +90,27 @@ template <class F> __device__ __forceinline__ void fe_round_masks(const uint32_t
     for (int j = 0; j < kRanfLag - 3; ++j) B |= (uint64_t)fe_outside<F>(slots[j], slots[j + 3]) << j;
 }
 
-// fe_walk_round on the precomputed masks: integer only, the same instruction stream for every entry state
-__device__ __forceinline__ int fe_walk_masks(uint64_t A, uint64_t B, int s, int& count) {
+// fe_walk_round on the precomputed masks, driven by a 72-entry table in shared memory:
+// entry [8 s + bits] = next state | (numbers the next state asks for) << 4, where bits = the three disc tests of a
+// 6-number request (s = 1) or, in bit 0, the disc test of a re-roll (s >= 2).
+__device__ __forceinline__ int fe_need(int s) { return s == 0 ? 9 : s == 1 ? 6 : 2; }
+__device__ inline uint8_t fe_walk_entry(int s, int bits) {
     // next state after the 6-number request, indexed by (n0 | n1 << 1 | n2 << 2); after an accepted re-roll, indexed by s
     constexpr uint32_t kAfterSix = 0x0u | (2u << 4) | (6u << 8) | (4u << 12) | (8u << 16) | (3u << 20) | (7u << 24) | (5u << 28);
     constexpr uint64_t kAfterRoll = (0ull << 8) | (8ull << 12) | (6ull << 16) | (7ull << 20) | (0ull << 24) | (8ull << 28) | (0ull << 32);
-    int idx = 55;
+    const int n = s == 0 ? 1 : s == 1 ? (int)((kAfterSix >> (4 * bits)) & 15u) : (bits & 1) ? s : (int)((kAfterRoll >> (4 * s)) & 15u);
+    return (uint8_t)(n | fe_need(n) << 4);
+}
+__device__ __forceinline__ int fe_walk_masks(uint64_t A, uint64_t B, int s, int& count, const uint8_t* __restrict__ tab) {
+    int idx = 55, need = fe_need(s);
     count = 0;
-    for (;;) {
-        const int need = s == 0 ? 9 : s == 1 ? 6 : 2;
-        if (idx < need) break;
+    while (idx >= need) {
         idx -= need;
-        const int after_six = (int)((kAfterSix >> (4 * (int)((B >> idx) & 7u))) & 15u);
-        const int after_roll = ((A >> idx) & 1u) ? s : (int)((kAfterRoll >> (4 * s)) & 15u);
-        count += s == 0;
-        s = s == 0 ? 1 : s == 1 ? after_six : after_roll;
+        count += need >> 3;  // a 9-number request starts an event
+        const uint64_t X = need == 6 ? B : A;
+        const uint32_t e = tab[8 * s + ((uint32_t)(X >> idx) & 7u)];
+        s = (int)(e & 15u);
+        need = (int)(e >> 4);
     }
     return s;
 }
@@ -165,7 +171,10 @@ template <class F>
 __global__ void __launch_bounds__(128) fe_round_maps_kernel(const uint32_t* __restrict__ jump_table, uint64_t first_round,
                                                           uint64_t n_rounds, uint32_t seg_rounds, uint64_t* __restrict__ maps) {
     __shared__ FeScanSmem sm[4];
+    __shared__ uint8_t walk_tab[72];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 72) walk_tab[threadIdx.x] = fe_walk_entry(threadIdx.x >> 3, threadIdx.x & 7);
+    __syncthreads();
     FeScanSmem& w = sm[warp];
     const uint64_t seg0 = ((uint64_t)blockIdx.x * 4 + warp) * kFeTile;
     if (seg0 * seg_rounds >= n_rounds) return;
@@ -174,7 +183,8 @@ __global__ void __launch_bounds__(128) fe_round_maps_kernel(const uint32_t* __re
     for (int k = 0; k < kFeTile; ++k) {
         const uint64_t r = (seg0 + k) * seg_rounds;
         if (r >= n_rounds) break;  // warp-uniform
-        ranf_jump_to_round(w.win, base, first_round + r, jump_table, lane);
+        if (k == 0) ranf_jump_to_round(w.win, base, first_round + r, jump_table, lane);
+        else ranf_jump_to_round(w.win, w.win, seg_rounds, jump_table, lane);  // the next segment starts seg_rounds later
         for (int i = lane; i < kRanfLag; i += 32) w.tile[k][i] = w.win[i];
         __syncwarp();
     }
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(128) fe_round_maps_kernel(const uint32_t* __re
         else fe_round_fused<F, true>(row, A, B);
         if (single) {
             int cnt;
-            const int e = fe_walk_masks(A, B, (int)(cur & 15u), cnt);
+            const int e = fe_walk_masks(A, B, (int)(cur & 15u), cnt, walk_tab);
             m = (uint64_t)e * kFeNine4 | ((uint64_t)cnt * kFeNine3) << 36;
             cur = (uint64_t)e;
         } else {
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(128) fe_round_maps_kernel(const uint32_t* __re
                 const int s = __ffs(img) - 1;
                 img &= img - 1;
                 int cnt;
-                const int e = fe_walk_masks(A, B, s, cnt);
+                const int e = fe_walk_masks(A, B, s, cnt, walk_tab);
                 m |= (uint64_t)e << (4 * s) | (uint64_t)cnt << (36 + 3 * s);
             }
             uint64_t nxt = 0;

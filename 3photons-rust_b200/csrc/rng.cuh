@@ -50,6 +50,14 @@ __device__ __forceinline__ uint32_t ranf_add(uint32_t a, uint32_t b) {
     return min(v, v - kRanfMod);
 }
 
+// a mod 1e9 for any 64-bit a (nvcc does not strength-reduce 64-bit division by a constant): the quotient estimate
+// floor(a * floor(2^64 / 1e9) / 2^64) is the true quotient or one less, so the remainder estimate is < 2e9.
+__device__ __forceinline__ uint32_t ranf_mod64(uint64_t a) {
+    const uint64_t q = __umul64hi(a, 18446744073ull);
+    const uint32_t r = (uint32_t)(a - q * kRanfMod);
+    return min(r, r - kRanfMod);
+}
+
 // Next round in slot order: y[0..54] = numbers[1..55] (ranf.rs:106-119 with the in-place updates
 // substituted: every new slot is a +- combination of at most four OLD slots)
 __device__ __forceinline__ uint32_t ranf_next_slot(const uint32_t* y, int i /*1..55*/) {
@@ -81,9 +89,9 @@ __device__ inline void ranf_jump_to_round(uint32_t* win, const uint32_t* base_y,
 #pragma unroll 5
                 for (int j = 0; j < kRanfLag; ++j) {
                     acc += (uint64_t)__ldg(c + j) * win[i + j];
-                    if ((j % 16) == 15) acc %= kRanfMod;  // 16 products < 1.6e19 < 2^64
+                    if ((j % 16) == 15) acc = ranf_mod64(acc);  // 16 products < 1.6e19 < 2^64
                 }
-                acc %= kRanfMod;
+                acc = ranf_mod64(acc);
             }
             o[h] = (uint32_t)acc;
         }

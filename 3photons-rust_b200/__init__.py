@@ -168,6 +168,9 @@ def lib() -> C.CDLL:
         "tp3_simulate_merged": (C.c_int, [vp, u64, u64, u32, P(Acc)]),
         "tp3_synchronize": (C.c_int, [vp]),
         "tp3_launch_count": (u64, [vp]),
+        "tp3_histograms_enable": (C.c_int, [vp, u32]),
+        "tp3_histograms_reset": (C.c_int, [vp]),
+        "tp3_histograms_fetch": (C.c_int, [vp, P(u64), P(C.c_double)]),
         "tp3_rng_dump": (C.c_int, [vp, u64, u32, P(u64)]),
         "tp3_events_dump": (C.c_int, [vp, u64, u32, P(dbl), P(i32), P(dbl)]),
         "tp3_peak_probe": (C.c_int, [vp, C.c_int, P(dbl)]),
@@ -195,7 +198,7 @@ ABI_SYMBOLS = [
     "tp3_simulate_batches_device", "tp3_fetch", "tp3_simulate_merged", "tp3_synchronize", "tp3_launch_count",
     "tp3_rng_dump", "tp3_events_dump", "tp3_peak_probe", "tp3_fastmath_probe", "tp3_config_parse", "tp3_params_from_config", "tp3_merge",
     "tp3_finalize", "tp3_format_res_data", "tp3_format_stdout", "tp3_run", "tp3_host_ranf_round",
-    "tp3_host_xoshiro_state",
+    "tp3_host_xoshiro_state", "tp3_histograms_enable", "tp3_histograms_reset", "tp3_histograms_fetch",
 ]
 
 
@@ -366,6 +369,25 @@ class Simulator:
     def launch_count(self) -> int:
         return int(lib().tp3_launch_count(self._h))
 
+    # per-event observables: the hook the reference leaves empty (main.rs:117-122,133; include/tp3.h)
+    def histograms_enable(self, num_bins: int):
+        """Fill `num_bins`-bin histograms of x_k = 2 E_k / e_total and cos(theta_k) (k = 0, 1, 2) in every
+        following simulate call; 0 switches them off."""
+        self._check(lib().tp3_histograms_enable(self._h, num_bins))
+        self._hist_bins = num_bins
+
+    def histograms_reset(self):
+        self._check(lib().tp3_histograms_reset(self._h))
+
+    def histograms_fetch(self) -> "Histograms":
+        n = HIST_OBSERVABLES * getattr(self, "_hist_bins", 0)
+        counts = (C.c_uint64 * max(n, 1))()
+        weights = (C.c_double * max(n, 1))()
+        self._check(lib().tp3_histograms_fetch(self._h, counts, weights))
+        nb = self._hist_bins
+        return Histograms(nb, [list(counts[o * nb:(o + 1) * nb]) for o in range(HIST_OBSERVABLES)],
+                          [list(weights[o * nb:(o + 1) * nb]) for o in range(HIST_OBSERVABLES)])
+
     def rng_dump(self, batch: int, n_words: int) -> List[int]:
         out = (C.c_uint64 * n_words)()
         self._check(lib().tp3_rng_dump(self._h, batch, n_words, out))
@@ -389,6 +411,31 @@ class Simulator:
         t = C.c_double()
         self._check(lib().tp3_peak_probe(self._h, which, C.byref(t)))
         return float(t.value)
+
+
+HIST_OBSERVABLES = 6
+HIST_NAMES = ("x_1", "x_2", "x_3", "cos_theta_1", "cos_theta_2", "cos_theta_3")
+HIST_RANGES = ((0.0, 1.0),) * 3 + ((-1.0, 1.0),) * 3
+
+
+class Histograms:
+    """Per-event observables of the selected events: counts[o][b] events and weights[o][b] = sum of the event
+    weights m . sigma_contribs (pb) in bin b of observable o (HIST_NAMES, uniform bins over HIST_RANGES).
+    Additive over batches, devices and ranks (`+`)."""
+
+    def __init__(self, num_bins: int, counts, weights):
+        self.num_bins, self.counts, self.weights = num_bins, counts, weights
+
+    def __add__(self, other: "Histograms") -> "Histograms":
+        assert self.num_bins == other.num_bins
+        return Histograms(self.num_bins, [[a + b for a, b in zip(x, y)] for x, y in zip(self.counts, other.counts)],
+                          [[a + b for a, b in zip(x, y)] for x, y in zip(self.weights, other.weights)])
+
+    def differential(self, o: int) -> List[float]:
+        """d sigma / d observable per bin (what main.rs:133 calls normalising the histograms): weight / bin width."""
+        lo, hi = HIST_RANGES[o]
+        width = (hi - lo) / self.num_bins
+        return [w / width for w in self.weights[o]]
 
 
 def run_simulation(cfg: Configuration, kernel: int = KERNEL_FAST, devices: Optional[Sequence[int]] = None) -> FinalResults:
@@ -437,6 +484,22 @@ def gather_accumulators(local, world_size: int, rank: int, dist=None, device=Non
         return None
     raw = b"".join(p.cpu().numpy().tobytes()[: c * size] for p, c in zip(parts, counts))
     return list((Acc * (len(raw) // size)).from_buffer_copy(raw))
+
+
+def reduce_histograms(local: "Histograms", world_size: int, rank: int, dist=None, device=None, dst: int = 0):
+    """Sum of every rank's per-event observable histograms on `dst` (None elsewhere): histograms are additive, so
+    this is one small reduce at the end of a run, like the accumulator gather."""
+    if world_size == 1:
+        return local
+    import torch
+    device = device or "cpu"
+    c = torch.tensor(local.counts, dtype=torch.int64, device=device)
+    w = torch.tensor(local.weights, dtype=torch.float64, device=device)
+    dist.reduce(c, dst)
+    dist.reduce(w, dst)
+    if rank != dst:
+        return None
+    return Histograms(local.num_bins, c.cpu().tolist(), w.cpu().tolist())
 
 
 def run_simulation_distributed(cfg: Configuration, simulate_range, world_size: int, rank: int, dist=None, device=None):

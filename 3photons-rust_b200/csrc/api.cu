@@ -2,6 +2,7 @@
 // No CPU fallback lives here: without a usable device every compute entry point fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +36,8 @@ struct DeviceSlot {
     tp3_acc* d_merged = nullptr;
     cudaStream_t merge_stream = nullptr;   // folds chunk i while chunk i+1 is simulated
     cudaEvent_t chunk_done = nullptr, merge_done = nullptr;
+    unsigned long long* d_hist_counts = nullptr;  // per-event observables: [TP3_HIST_OBSERVABLES][hist_bins]
+    double* d_hist_weights = nullptr;
     uint32_t* d_fe_ranf_states = nullptr;  // faster-evgen: [n][57] batch start states from the host scheduler
     size_t fe_states_cap = 0;
     // last launch
@@ -48,6 +51,7 @@ struct tp3_ctx {
     std::vector<DeviceSlot> devs;
     std::string err;
     uint64_t launches = 0;
+    uint32_t hist_bins = 0;  // per-event observables on (tp3_histograms_enable)
     // host copies of the seeding data
     uint32_t ranf_base[kRanfLag];
     std::vector<uint32_t> ranf_table;
@@ -96,6 +100,15 @@ void launch_sim(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
     const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
     simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, 0, st>>>(a, phys_params<F>(p));
 }
+// Fast kernel with the per-event observable epilogue: CTA histograms in dynamic shared memory (12 bytes per bin).
+template <class F, int RNG, bool SORT>
+void launch_sim_hist(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
+    const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
+    const size_t dyn = (size_t)TP3_HIST_OBSERVABLES * a.hist_bins * (sizeof(double) + sizeof(uint32_t));
+    auto kernel = simulate_kernel<F, RNG, SORT, false, true>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  // an error shows up at the launch
+    kernel<<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, dyn, st>>>(a, phys_params<F>(p));
+}
 template <class F, int RNG, bool SORT, bool LITERAL>
 void launch_dump(const SimArgs& a, const tp3_params& p, const DumpArgs& d, cudaStream_t st) {
     dump_kernel<F, RNG, SORT, LITERAL><<<1, kThreads, 0, st>>>(a, phys_params<F>(p), d);
@@ -112,9 +125,14 @@ template <class F, int RNG> DumpFn pick_dump2(bool sort, bool literal) {
     if (sort) return literal ? launch_dump<F, RNG, true, true> : launch_dump<F, RNG, true, false>;
     return literal ? launch_dump<F, RNG, false, true> : launch_dump<F, RNG, false, false>;
 }
-SimFn pick_sim(const tp3_params& p) {
+template <class F, int RNG> SimFn pick_sim_hist2(bool sort) { return sort ? launch_sim_hist<F, RNG, true> : launch_sim_hist<F, RNG, false>; }
+SimFn pick_sim(const tp3_params& p, bool hist = false) {
     const bool f32 = p.flags & TP3_F32, xo = p.flags & TP3_STANDARD_RANDOM;
     const bool sort = !(p.flags & TP3_NO_PHOTON_SORTING), lit = p.kernel == TP3_KERNEL_LITERAL;
+    if (hist) {
+        if (f32) return xo ? pick_sim_hist2<float, RNG_XOSHIRO>(sort) : pick_sim_hist2<float, RNG_RANF>(sort);
+        return xo ? pick_sim_hist2<double, RNG_XOSHIRO>(sort) : pick_sim_hist2<double, RNG_RANF>(sort);
+    }
     if (f32) return xo ? pick_sim2<float, RNG_XOSHIRO>(sort, lit) : pick_sim2<float, RNG_RANF>(sort, lit);
     return xo ? pick_sim2<double, RNG_XOSHIRO>(sort, lit) : pick_sim2<double, RNG_RANF>(sort, lit);
 }
@@ -511,7 +529,10 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         if (f32) { if (xo) launch_fe<float, RNG_XOSHIRO>(f, c->params, s.stream); else launch_fe<float, RNG_RANF>(f, c->params, s.stream); }
         else { if (xo) launch_fe<double, RNG_XOSHIRO>(f, c->params, s.stream); else launch_fe<double, RNG_RANF>(f, c->params, s.stream); }
     } else {
-        pick_sim(c->params)(a, c->params, s.stream);
+        a.hist_bins = c->hist_bins;
+        a.hist_counts = s.d_hist_counts;
+        a.hist_weights = s.d_hist_weights;
+        pick_sim(c->params, c->hist_bins != 0)(a, c->params, s.stream);
     }
     ++c->launches;
     TP3_CUDA(c, cudaGetLastError());
@@ -604,11 +625,77 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_out);
         cudaFree(s.d_merged);
         cudaFree(s.d_fe_ranf_states);
+        cudaFree(s.d_hist_counts);
+        cudaFree(s.d_hist_weights);
         if (s.merge_stream) cudaStreamDestroy(s.merge_stream);
         if (s.chunk_done) cudaEventDestroy(s.chunk_done);
         if (s.merge_done) cudaEventDestroy(s.merge_done);
     }
     delete c;
+}
+
+// ---- per-event observables (tp3.h) ---------------------------------------------------------------------
+int tp3_histograms_reset(tp3_ctx* c) {
+    if (!c) return TP3_E_INVALID;
+    const size_t n = (size_t)TP3_HIST_OBSERVABLES * c->hist_bins;
+    for (auto& s : c->devs) {
+        if (!s.d_hist_counts) continue;
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        TP3_CUDA(c, cudaMemsetAsync(s.d_hist_counts, 0, n * sizeof(unsigned long long), s.stream));
+        TP3_CUDA(c, cudaMemsetAsync(s.d_hist_weights, 0, n * sizeof(double), s.stream));
+    }
+    return TP3_OK;
+}
+
+int tp3_histograms_enable(tp3_ctx* c, uint32_t num_bins) {
+    if (!c) return TP3_E_INVALID;
+    if (num_bins > TP3_HIST_MAX_BINS) {
+        c->err = "tp3_histograms_enable: at most " + std::to_string(TP3_HIST_MAX_BINS) + " bins";
+        return TP3_E_INVALID;
+    }
+    if (num_bins && ((c->params.flags & TP3_FASTER_EVGEN) || c->params.kernel != TP3_KERNEL_FAST)) {
+        c->err = "per-event observables need the fast kernel with the default event generator";
+        return TP3_E_INVALID;
+    }
+    for (auto& s : c->devs) {
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        cudaFree(s.d_hist_counts);
+        cudaFree(s.d_hist_weights);
+        s.d_hist_counts = nullptr;
+        s.d_hist_weights = nullptr;
+        if (num_bins) {
+            const size_t n = (size_t)TP3_HIST_OBSERVABLES * num_bins;
+            TP3_CUDA(c, cudaMalloc(&s.d_hist_counts, n * sizeof(unsigned long long)));
+            TP3_CUDA(c, cudaMalloc(&s.d_hist_weights, n * sizeof(double)));
+        }
+    }
+    c->hist_bins = num_bins;
+    return tp3_histograms_reset(c);
+}
+
+int tp3_histograms_fetch(tp3_ctx* c, uint64_t* counts, double* weights) {
+    if (!c || !counts || !weights) return TP3_E_INVALID;
+    if (!c->hist_bins) {
+        c->err = "tp3_histograms_fetch: histograms are not enabled";
+        return TP3_E_INVALID;
+    }
+    const size_t n = (size_t)TP3_HIST_OBSERVABLES * c->hist_bins;
+    std::vector<unsigned long long> hc(n);
+    std::vector<double> hw(n);
+    std::fill(counts, counts + n, 0);
+    std::fill(weights, weights + n, 0.0);
+    for (auto& s : c->devs) {  // device order: the sum does not depend on how the work was timed
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        TP3_CUDA(c, cudaMemcpyAsync(hc.data(), s.d_hist_counts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaMemcpyAsync(hw.data(), s.d_hist_weights, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        for (size_t i = 0; i < n; ++i) {
+            counts[i] += hc[i];
+            weights[i] += hw[i];
+        }
+    }
+    return TP3_OK;
 }
 
 int tp3_set_stream(tp3_ctx* c, int slot, void* stream) {

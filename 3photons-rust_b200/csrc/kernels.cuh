@@ -49,6 +49,10 @@ struct SimArgs {
     tp3_acc* out;                      // [n_batches]
     uint32_t ranf_base[kRanfLag];      // seeded round 0 (ranf.rs:28-66), slot order
     int32_t ranf_seed;
+    // per-event observables (tp3.h): device histograms [TP3_HIST_OBSERVABLES][hist_bins], or null
+    uint32_t hist_bins;
+    unsigned long long* hist_counts;
+    double* hist_weights;
 };
 
 struct DumpArgs {
@@ -198,17 +202,62 @@ template <class F, int RNG> struct RngTick {
 
 template <class F> __device__ __forceinline__ F shfl_xor_t(F v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
+// Per-event observables (tp3.h): the histograms of a CTA live in dynamic shared memory, weights[6 nb] (f64) then
+// counts[6 nb] (u32: a CTA sees < 2^32 events), and are added to the device histograms when the CTA ends.
+__device__ __forceinline__ int hist_bin(double t, int nb) {  // t in [0, 1] up to rounding
+    const int b = (int)(t * (double)nb);
+    return min(max(b, 0), nb - 1);
+}
+template <class F, bool SORT>
+__device__ __forceinline__ void hist_fill(const F e[3][4], const F m[5], const PhysParams<F>& P, uint32_t* hc, double* hw, int nb) {
+    F w = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w += m[k] * P.sigma_contribs[k];
+    F en[3] = {e[0][3], e[1][3], e[2][3]}, px[3] = {e[0][0], e[1][0], e[2][0]};
+    if (SORT) {  // evgen.rs:109-118
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = a + 1; b < 3; ++b) {
+                const bool sw = en[b] > en[a];
+                const F ea = en[a], eb = en[b], xa = px[a], xb = px[b];
+                en[a] = sw ? eb : ea; en[b] = sw ? ea : eb;
+                px[a] = sw ? xb : xa; px[b] = sw ? xa : xb;
+            }
+    }
+    const double inv = 2.0 / (double)P.e_total;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int bx = hist_bin((double)en[k] * inv, nb);
+        const int bc = hist_bin(0.5 + 0.5 * ((double)px[k] / (double)en[k]), nb);
+        atomicAdd(hc + k * nb + bx, 1u);
+        atomicAdd(hw + k * nb + bx, (double)w);
+        atomicAdd(hc + (3 + k) * nb + bc, 1u);
+        atomicAdd(hw + (3 + k) * nb + bc, (double)w);
+    }
+}
+
 // Number of events of batch `slot` of the launch.
 __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
     return (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
 }
 
-template <class F, int RNG, bool SORT, bool LITERAL>
+template <class F, int RNG, bool SORT, bool LITERAL, bool HIST = false>
 __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
     __shared__ BlockSmem<F> sm;
+    extern __shared__ __align__(16) unsigned char hist_raw[];
     using Word = typename RawWord<F, RNG>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     fastmath_load(&sm.fm);
+    const int hist_n = HIST ? TP3_HIST_OBSERVABLES * (int)a.hist_bins : 0;
+    double* const hist_w = reinterpret_cast<double*>(hist_raw);            // weights first: 8-byte aligned
+    uint32_t* const hist_c = reinterpret_cast<uint32_t*>(hist_w + hist_n);
+    if (HIST) {
+        for (int i = threadIdx.x; i < hist_n; i += kThreads) {
+            hist_w[i] = 0.0;
+            hist_c[i] = 0u;
+        }
+    }
     __syncthreads();
     typename Pair<F>::type(*queue)[kQueue] = sm.w[warp].queue;
 
@@ -290,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
             F m[5];
             me_fast<F>(e, P, m);
             acc.integrate(m, P.sigma_contribs);
+            if (HIST) hist_fill<F, SORT>(e, m, P, hist_c, hist_w, (int)a.hist_bins);
 #else
             acc.spm2[0] += e[0][0] + e[1][1] + e[2][2];
 #endif
@@ -306,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
         F m[5];
         me_fast<F>(e, P, m);
         acc.integrate(m, P.sigma_contribs);
+        if (HIST) hist_fill<F, SORT>(e, m, P, hist_c, hist_w, (int)a.hist_bins);
     }
 
     // ResultsAccumulator of the batch: xor-shuffle tree over the 32 lane-partials (deterministic)
@@ -337,6 +388,16 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
     }
     __syncwarp();
   }
+    if (HIST) {  // CTA histograms -> device histograms
+        __syncthreads();
+        for (int i = threadIdx.x; i < hist_n; i += kThreads) {
+            const uint32_t n = hist_c[i];
+            if (n) {
+                atomicAdd(a.hist_counts + i, (unsigned long long)n);
+                atomicAdd(a.hist_weights + i, hist_w[i]);
+            }
+        }
+    }
 }
 
 // Parity hook: same streams, same event -> lane mapping, per-event outputs instead of sums.

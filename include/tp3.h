@@ -105,6 +105,27 @@ int  tp3_synchronize(tp3_ctx* ctx);
 /* Number of kernel launches issued by this context so far. */
 uint64_t tp3_launch_count(const tp3_ctx* ctx);
 
+/* ---- per-event observables (the reference's empty hook) ---------------------------------------------
+ * The reference parses `num_bins` (config.rs:45-46,102) and marks, without implementing them, the places
+ * where the FORTRAN code filled and normalised its histograms (main.rs:117-122,133).  This fills them in the
+ * fused kernel: every selected event adds its weight  w = m . sigma_contribs  (the quantity
+ * ResultsAccumulator::integrate adds to sigma, resacc.rs:126-128) to one bin of each of
+ * TP3_HIST_OBSERVABLES distributions, photons in the event's order (decreasing energy unless
+ * TP3_NO_PHOTON_SORTING, evgen.rs:109-118):
+ *    observable k     (k = 0,1,2):  x_k    = 2 E_k / e_total       in [0, 1]
+ *    observable 3 + k (k = 0,1,2):  cos(theta_k) = p_x,k / E_k     in [-1, 1]   (the beam is along X, evgen.rs:66-72)
+ * with num_bins uniform bins over the stated range, bin = min(num_bins - 1, floor(t * num_bins)), t the value
+ * mapped to [0, 1].  Histograms accumulate over all simulate calls of the context (all devices) until reset.
+ * Event counts are exact; the weight sums are accumulated with floating-point atomics (order not fixed: equal
+ * to ~1e-13 relative between runs).  Available for the fast kernel with the default event generator. */
+#define TP3_HIST_OBSERVABLES 6
+#define TP3_HIST_MAX_BINS 1024
+/* num_bins = 0 switches the epilogue off again. */
+int  tp3_histograms_enable(tp3_ctx* ctx, uint32_t num_bins);
+int  tp3_histograms_reset(tp3_ctx* ctx);
+/* counts / weights: [TP3_HIST_OBSERVABLES][num_bins], summed over the devices; synchronises. */
+int  tp3_histograms_fetch(tp3_ctx* ctx, uint64_t* counts, double* weights);
+
 /* ---- parity hooks ------------------------------------------------------------------ */
 /* Raw integer random stream of batch `batch`, in the order the reference consumes it,
  * produced by the SAME per-warp/per-lane stream code the simulation kernel uses.

@@ -50,6 +50,9 @@ pub struct tp3_ctx {
     _private: [u8; 0],
 }
 
+pub const TP3_HIST_OBSERVABLES: usize = 6;
+pub const TP3_HIST_MAX_BINS: u32 = 1024;
+
 extern "C" {
     pub fn tp3_abi_version() -> c_int;
     pub fn tp3_create(params: *const tp3_params, n_dev: c_int, dev_ids: *const c_int, out: *mut *mut tp3_ctx) -> c_int;
@@ -64,6 +67,10 @@ extern "C" {
                                out_merged: *mut tp3_acc) -> c_int;
     pub fn tp3_synchronize(ctx: *mut tp3_ctx) -> c_int;
     pub fn tp3_launch_count(ctx: *const tp3_ctx) -> u64;
+    /// Per-event observables, the hook main.rs:117-122,133 leaves empty: [TP3_HIST_OBSERVABLES][num_bins] histograms.
+    pub fn tp3_histograms_enable(ctx: *mut tp3_ctx, num_bins: u32) -> c_int;
+    pub fn tp3_histograms_reset(ctx: *mut tp3_ctx) -> c_int;
+    pub fn tp3_histograms_fetch(ctx: *mut tp3_ctx, counts: *mut u64, weights: *mut f64) -> c_int;
     pub fn tp3_rng_dump(ctx: *mut tp3_ctx, batch: u64, n_words: u32, out_words: *mut u64) -> c_int;
     pub fn tp3_events_dump(ctx: *mut tp3_ctx, batch: u64, n: u32, momenta: *mut f64, kept: *mut i32, m2_sums: *mut f64) -> c_int;
     pub fn tp3_peak_probe(ctx: *mut tp3_ctx, which: c_int, tflops: *mut f64) -> c_int;

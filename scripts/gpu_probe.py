@@ -18,3 +18,15 @@ for features, kernel in [("", 0), ("", 1), ("no-photon-sorting", 0), ("standard-
             best = min(best, time.perf_counter() - t0)
         ev = n_batches * 10000
         print(f"features={features!r:28} kernel={kernel} {ev/best:.4g} events/s ({best*1e3:.1f} ms) selected_frac={acc.selected_events/ev:.6f}", flush=True)
+# per-event observable epilogue (tp3_histograms_enable): cost relative to the plain kernel
+cfg = pkg.Configuration.parse(text, "")
+with pkg.Simulator(cfg, 0) as sim:
+    for bins in (0, 200, 1024):
+        sim.histograms_enable(bins)
+        sim.simulate_merged(0, 2000)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            sim.simulate_merged(0, n_batches)
+            best = min(best, time.perf_counter() - t0)
+        print(f"histograms bins={bins:5d} {n_batches * 10000 / best:.4g} events/s", flush=True)

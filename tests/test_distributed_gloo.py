@@ -47,10 +47,14 @@ def _worker(rank, world, port, valeurs_text, q):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     cfg = tp3.Configuration.parse(valeurs_text).with_num_events(N_EVENTS)
     fin = tp3.run_simulation_distributed(cfg, _oracle_range_simulator(tp3, valeurs_text, N_EVENTS), world, rank, dist, "cpu")
+    # per-event observable histograms are reduced the same way (synthetic per-rank content here)
+    local = tp3.Histograms(4, [[rank + 1 + b for b in range(4)] for _ in range(tp3.HIST_OBSERVABLES)],
+                           [[0.5 * (rank + 1) * (b + 1) for b in range(4)] for _ in range(tp3.HIST_OBSERVABLES)])
+    total = tp3.reduce_histograms(local, world, rank, dist, "cpu")
     if rank == 0:
-        q.put((fin.selected_events, fin.sigma, fin.res_data()))
+        q.put((fin.selected_events, fin.sigma, fin.res_data(), total.counts, total.weights))
     else:
-        assert fin is None
+        assert fin is None and total is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,11 +69,14 @@ def test_sharded_run_is_bit_identical_to_single_process(tp3, oracle, valeurs_tex
     procs = [ctx.Process(target=_worker, args=(r, world, port, valeurs_text, q)) for r in range(world)]
     for p in procs:
         p.start()
-    sel, sigma, res = q.get(timeout=120)
+    sel, sigma, res, hist_counts, hist_weights = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert (sel, sigma, res) == (single.selected_events, single.sigma, single.res_data())
+    ranks = world * (world + 1) // 2  # sum of (rank + 1)
+    assert hist_counts == [[ranks + world * b for b in range(4)]] * tp3.HIST_OBSERVABLES
+    assert hist_weights == [[0.5 * ranks * (b + 1) for b in range(4)]] * tp3.HIST_OBSERVABLES
     # and the fold agrees with the oracle's own whole-run text
     from numdiff import compare
     assert compare(res, oracle.run(valeurs_text, "", num_events=N_EVENTS).res_data) == []

@@ -411,6 +411,74 @@ def test_faster_evgen_default_run_matches_golden(tp3, valeurs_text, features):
     assert compare(fin.stdout(), golden("stdout.log-features_faster-evgen"), rel=1e-5) == []
 
 
+# ------------------------------------------------------------------------------ per-event observables
+def _oracle_histograms(oracle, tp3, valeurs_text, features, n_events, bins):
+    """numpy restatement of include/tp3.h "per-event observables" on the oracle's per-event output."""
+    import numpy as np
+    mom, kept, m2 = oracle.events(valeurs_text, features, n_events)
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    mom = np.array(mom).reshape(n_events, 3, 4)
+    sel = np.array(kept) == 1
+    w = np.array(m2).reshape(n_events, 5)[sel] @ np.array(list(cfg.params().sigma_contribs))
+    e, x = mom[sel][:, :, 3], mom[sel][:, :, 0]
+    counts, weights = [], []
+    for t in [2.0 * e[:, k] / cfg.raw.e_total for k in range(3)] + [0.5 + 0.5 * x[:, k] / e[:, k] for k in range(3)]:
+        b = np.clip(np.floor(t * bins).astype(int), 0, bins - 1)
+        counts.append(np.bincount(b, minlength=bins))
+        weights.append(np.bincount(b, weights=w, minlength=bins))
+    return cfg, np.array(counts), np.array(weights), int(sel.sum())
+
+
+@pytest.mark.parametrize("features", ["", "no-photon-sorting", "standard-random", "f32"])
+def test_histograms_match_oracle_events(tp3, oracle, valeurs_text, features):
+    """the histogram hook the reference leaves empty (main.rs:117-122,133), filled in the fused
+    kernel.  Event counts per bin are exact (a value within rounding of a bin edge may move one event: slack 2 per
+    observable in f64), weight sums agree to 1e-10 of the bin's scale; totals equal the accumulator's."""
+    import numpy as np
+    nb, bins = 6, 200
+    cfg, want_c, want_w, n_sel = _oracle_histograms(oracle, tp3, valeurs_text, features, nb * 10000, bins)
+    with tp3.Simulator(cfg) as sim:
+        sim.histograms_enable(bins)
+        merged = tp3.fold(sim.simulate_batches(0, nb), cfg.flags)
+        h = sim.histograms_fetch()
+        sim.simulate_batches(0, nb)          # histograms accumulate over calls ...
+        twice = sim.histograms_fetch()
+        sim.histograms_reset()               # ... until reset
+        zero = sim.histograms_fetch()
+        sim.histograms_enable(0)             # and the epilogue can be switched off again
+        assert bytes(sim.simulate_batches(0, 1)) == bytes(sim.simulate_batches(0, 1))
+    got_c, got_w = np.array(h.counts), np.array(h.weights)
+    f32 = "f32" in features
+    if not f32:
+        assert merged.selected_events == n_sel
+    for o in range(tp3.HIST_OBSERVABLES):
+        assert got_c[o].sum() == merged.selected_events
+        assert abs(got_w[o].sum() - merged.sigma) <= (1e-12 if not f32 else 1e-5) * abs(merged.sigma)
+        moved = np.abs(got_c[o] - want_c[o]).sum()
+        assert moved <= (2 if not f32 else 400), f"observable {o}: {moved} events in other bins"
+        same = got_c[o] == want_c[o]
+        scale = np.abs(want_w[o]).max()
+        tol = (1e-10 if not f32 else 2e-4) * scale
+        assert np.all(np.abs(got_w[o] - want_w[o])[same] <= tol), f"observable {o}"
+    assert np.array_equal(np.array(twice.counts), 2 * got_c)
+    assert np.allclose(np.array(twice.weights), 2 * got_w, rtol=1e-12, atol=0)
+    assert not np.any(np.array(zero.counts)) and not np.any(np.array(zero.weights))
+    assert len(h.differential(3)) == bins and abs(sum(h.differential(0)) / bins - merged.sigma) <= 1e-5 * abs(merged.sigma)
+
+
+def test_histograms_refused_where_unsupported(tp3, valeurs_text):
+    cfg = tp3.Configuration.parse(valeurs_text, "faster-evgen")
+    with tp3.Simulator(cfg) as sim:
+        with pytest.raises(tp3.Tp3Error):
+            sim.histograms_enable(200)
+    cfg = tp3.Configuration.parse(valeurs_text, "")
+    with tp3.Simulator(cfg) as sim:
+        with pytest.raises(tp3.Tp3Error):
+            sim.histograms_enable(100000)
+        with pytest.raises(tp3.Tp3Error):
+            sim.histograms_fetch()
+
+
 def test_whole_program_cli_surface(tp3, valeurs_text, tmp_path):
     """tp3_run = main.rs:75-145: valeurs in, stdout text + res.data / res.times / pil.mc out."""
     (tmp_path / "valeurs").write_text(valeurs_text)

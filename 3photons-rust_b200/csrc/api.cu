@@ -40,6 +40,15 @@ struct DeviceSlot {
     double* d_hist_weights = nullptr;
     uint32_t* d_fe_ranf_states = nullptr;  // faster-evgen: [n][57] batch start states from the host scheduler
     size_t fe_states_cap = 0;
+    // faster-evgen scan workspace (fe_scan.cuh), kept between calls: grows to the largest pass, freed with the context
+    void* d_fe_bnd = nullptr;
+    size_t fe_bnd_cap = 0;
+    uint64_t* d_fe_maps = nullptr;
+    size_t fe_maps_cap = 0;
+    uint8_t *d_fe_seg_exit = nullptr, *d_fe_seg_state = nullptr;
+    uint32_t* d_fe_seg_count = nullptr;
+    uint64_t* d_fe_seg_events = nullptr;
+    size_t fe_seg_cap = 0;
     // last launch
     uint64_t last_first = 0, last_n = 0;
 };
@@ -293,20 +302,18 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n,
         TP3_CUDA(c, cudaMalloc(&s.d_fe_ranf_states, n_bnd * 57 * sizeof(uint32_t)));
         s.fe_states_cap = n_bnd;
     }
-    FeBoundary* d_bnd = nullptr;
-    TP3_CUDA(c, cudaMalloc(&d_bnd, n_bnd * sizeof(FeBoundary)));
+    if (s.fe_bnd_cap < n_bnd) {
+        cudaFree(s.d_fe_bnd);
+        s.d_fe_bnd = nullptr;
+        s.fe_bnd_cap = 0;
+        TP3_CUDA(c, cudaMalloc(&s.d_fe_bnd, n_bnd * sizeof(FeBoundary)));
+        s.fe_bnd_cap = n_bnd;
+    }
+    FeBoundary* d_bnd = static_cast<FeBoundary*>(s.d_fe_bnd);
     // event index of the last boundary wanted, and of the first one a following call for the next batches would want
     const uint64_t last_target = (first + n - 1) * (uint64_t)TP3_EVENT_BATCH_SIZE + (uint64_t)(split - 1) * part_len;
     const uint64_t next_first = (first + n) * (uint64_t)TP3_EVENT_BATCH_SIZE;
-    uint64_t* d_maps = nullptr;
-    uint8_t *d_seg_exit = nullptr, *d_seg_state = nullptr;
-    uint32_t* d_seg_count = nullptr;
-    uint64_t* d_seg_events = nullptr;
-    size_t maps_cap = 0, seg_cap = 0;
     int rc = TP3_OK;
-    auto cleanup = [&]() {
-        cudaFree(d_bnd); cudaFree(d_maps); cudaFree(d_seg_exit); cudaFree(d_seg_state); cudaFree(d_seg_count); cudaFree(d_seg_events);
-    };
     auto check = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess && rc == TP3_OK) {
             c->err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -323,18 +330,27 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n,
         uint32_t seg_rounds = 64;
         while (seg_rounds < (uint32_t)kFeMaxSegRounds && n_rounds / (2 * seg_rounds) >= (uint64_t)s.sm_count * 4 * 8 * 32) seg_rounds *= 2;
         const uint64_t n_seg = (n_rounds + seg_rounds - 1) / seg_rounds;
-        if (maps_cap < n_rounds || seg_cap < n_seg) {
-            cudaFree(d_maps); cudaFree(d_seg_exit); cudaFree(d_seg_state); cudaFree(d_seg_count); cudaFree(d_seg_events);
-            d_maps = nullptr; d_seg_exit = d_seg_state = nullptr; d_seg_count = nullptr; d_seg_events = nullptr;
-            maps_cap = seg_cap = 0;
-            if (!check(cudaMalloc(&d_maps, n_rounds * 8), "cudaMalloc maps")) break;
-            if (!check(cudaMalloc(&d_seg_exit, n_seg * 9), "cudaMalloc")) break;
-            if (!check(cudaMalloc(&d_seg_state, n_seg), "cudaMalloc")) break;
-            if (!check(cudaMalloc(&d_seg_count, n_seg * 9 * 4), "cudaMalloc")) break;
-            if (!check(cudaMalloc(&d_seg_events, n_seg * 8), "cudaMalloc")) break;
-            maps_cap = n_rounds;
-            seg_cap = n_seg;
+        if (s.fe_maps_cap < n_rounds) {
+            cudaFree(s.d_fe_maps);
+            s.d_fe_maps = nullptr;
+            s.fe_maps_cap = 0;
+            if (!check(cudaMalloc(&s.d_fe_maps, n_rounds * 8), "cudaMalloc maps")) break;
+            s.fe_maps_cap = n_rounds;
         }
+        if (s.fe_seg_cap < n_seg) {
+            cudaFree(s.d_fe_seg_exit); cudaFree(s.d_fe_seg_state); cudaFree(s.d_fe_seg_count); cudaFree(s.d_fe_seg_events);
+            s.d_fe_seg_exit = s.d_fe_seg_state = nullptr; s.d_fe_seg_count = nullptr; s.d_fe_seg_events = nullptr;
+            s.fe_seg_cap = 0;
+            if (!check(cudaMalloc(&s.d_fe_seg_exit, n_seg * 9), "cudaMalloc")) break;
+            if (!check(cudaMalloc(&s.d_fe_seg_state, n_seg), "cudaMalloc")) break;
+            if (!check(cudaMalloc(&s.d_fe_seg_count, n_seg * 9 * 4), "cudaMalloc")) break;
+            if (!check(cudaMalloc(&s.d_fe_seg_events, n_seg * 8), "cudaMalloc")) break;
+            s.fe_seg_cap = n_seg;
+        }
+        uint64_t* const d_maps = s.d_fe_maps;
+        uint8_t *const d_seg_exit = s.d_fe_seg_exit, *const d_seg_state = s.d_fe_seg_state;
+        uint32_t* const d_seg_count = s.d_fe_seg_count;
+        uint64_t* const d_seg_events = s.d_fe_seg_events;
         const unsigned map_blocks = (unsigned)((n_seg + 127) / 128), seg_blocks = (unsigned)((n_seg + 127) / 128);
         if (f32) fe_round_maps_kernel<float><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, seg_rounds, d_maps);
         else fe_round_maps_kernel<double><<<map_blocks, 128, 0, s.stream>>>(s.d_ranf_table, c->scan_round, n_rounds, seg_rounds, d_maps);
@@ -394,7 +410,6 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n,
     if (timing)
         std::fprintf(stderr, "[tp3 fe scan] batches %llu split %u passes %d: maps+segments %.2f ms, host chain %.2f ms, boundaries %.2f ms, states %.2f ms\n",
                      (unsigned long long)n, split, passes, t_maps, t_chain, t_bnd, t_states);
-    cleanup();
     return rc;
 }
 
@@ -625,6 +640,12 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_out);
         cudaFree(s.d_merged);
         cudaFree(s.d_fe_ranf_states);
+        cudaFree(s.d_fe_bnd);
+        cudaFree(s.d_fe_maps);
+        cudaFree(s.d_fe_seg_exit);
+        cudaFree(s.d_fe_seg_state);
+        cudaFree(s.d_fe_seg_count);
+        cudaFree(s.d_fe_seg_events);
         cudaFree(s.d_hist_counts);
         cudaFree(s.d_hist_weights);
         if (s.merge_stream) cudaStreamDestroy(s.merge_stream);

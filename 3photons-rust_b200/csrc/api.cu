@@ -275,9 +275,9 @@ void fe_host_states(tp3_ctx* c, uint64_t first, uint64_t n, std::vector<uint32_t
 }
 
 
-// ---- faster-evgen + RANF: batch start states by a scan over per-round transition maps (fe_scan.cuh) ----------
-// Fills s.d_fe_ranf_states[0..n) for batches [first, first + n) of the sequential stream, entirely on the device
-// (the host only chains ~1 segment map per 1024 rounds).
+// ---- faster-evgen + RANF: start states by a scan over per-round transition maps (fe_scan.cuh) --------------------
+// Fills s.d_fe_ranf_states for batches [first, first + n) of the sequential stream, on the device: the host only
+// chains one small map per segment (64 to 2048 rounds) between two kernels of a pass.
 // `split` boundaries per batch (1, or 32 with part_len 313): n * split generator states in batch-major order.
 int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t split) {
     const bool f32 = c->params.flags & TP3_F32;

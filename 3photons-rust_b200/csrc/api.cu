@@ -109,11 +109,11 @@ void launch_sim(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
     const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
     simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, 0, st>>>(a, phys_params<F>(p));
 }
-// Fast kernel with the per-event observable epilogue: CTA histograms in dynamic shared memory (12 bytes per bin).
+// Fast kernel with the per-event observable epilogue: the CTA's event counts in dynamic shared memory (4 bytes per bin).
 template <class F, int RNG, bool SORT>
 void launch_sim_hist(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
     const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
-    const size_t dyn = (size_t)TP3_HIST_OBSERVABLES * a.hist_bins * (sizeof(double) + sizeof(uint32_t));
+    const size_t dyn = (size_t)TP3_HIST_OBSERVABLES * a.hist_bins * sizeof(uint32_t);
     auto kernel = simulate_kernel<F, RNG, SORT, false, true>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  // an error shows up at the launch
     kernel<<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, dyn, st>>>(a, phys_params<F>(p));
@@ -663,7 +663,7 @@ int tp3_histograms_reset(tp3_ctx* c) {
         if (!s.d_hist_counts) continue;
         TP3_CUDA(c, cudaSetDevice(s.dev));
         TP3_CUDA(c, cudaMemsetAsync(s.d_hist_counts, 0, n * sizeof(unsigned long long), s.stream));
-        TP3_CUDA(c, cudaMemsetAsync(s.d_hist_weights, 0, n * sizeof(double), s.stream));
+        TP3_CUDA(c, cudaMemsetAsync(s.d_hist_weights, 0, n * kHistReplicas * sizeof(double), s.stream));
     }
     return TP3_OK;
 }
@@ -688,7 +688,7 @@ int tp3_histograms_enable(tp3_ctx* c, uint32_t num_bins) {
         if (num_bins) {
             const size_t n = (size_t)TP3_HIST_OBSERVABLES * num_bins;
             TP3_CUDA(c, cudaMalloc(&s.d_hist_counts, n * sizeof(unsigned long long)));
-            TP3_CUDA(c, cudaMalloc(&s.d_hist_weights, n * sizeof(double)));
+            TP3_CUDA(c, cudaMalloc(&s.d_hist_weights, n * kHistReplicas * sizeof(double)));
         }
     }
     c->hist_bins = num_bins;
@@ -703,17 +703,19 @@ int tp3_histograms_fetch(tp3_ctx* c, uint64_t* counts, double* weights) {
     }
     const size_t n = (size_t)TP3_HIST_OBSERVABLES * c->hist_bins;
     std::vector<unsigned long long> hc(n);
-    std::vector<double> hw(n);
+    std::vector<double> hw(n * kHistReplicas);
     std::fill(counts, counts + n, 0);
     std::fill(weights, weights + n, 0.0);
     for (auto& s : c->devs) {  // device order: the sum does not depend on how the work was timed
         TP3_CUDA(c, cudaSetDevice(s.dev));
         TP3_CUDA(c, cudaMemcpyAsync(hc.data(), s.d_hist_counts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-        TP3_CUDA(c, cudaMemcpyAsync(hw.data(), s.d_hist_weights, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaMemcpyAsync(hw.data(), s.d_hist_weights, n * kHistReplicas * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         TP3_CUDA(c, cudaStreamSynchronize(s.stream));
         for (size_t i = 0; i < n; ++i) {
             counts[i] += hc[i];
-            weights[i] += hw[i];
+            double w = 0;
+            for (int r = 0; r < kHistReplicas; ++r) w += hw[(size_t)r * n + i];  // replica order
+            weights[i] += w;
         }
     }
     return TP3_OK;

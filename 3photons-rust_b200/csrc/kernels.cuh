@@ -49,10 +49,10 @@ struct SimArgs {
     tp3_acc* out;                      // [n_batches]
     uint32_t ranf_base[kRanfLag];      // seeded round 0 (ranf.rs:28-66), slot order
     int32_t ranf_seed;
-    // per-event observables (tp3.h): device histograms [TP3_HIST_OBSERVABLES][hist_bins], or null
+    // per-event observables (tp3.h): device histograms, or null
     uint32_t hist_bins;
-    unsigned long long* hist_counts;
-    double* hist_weights;
+    unsigned long long* hist_counts;   // [TP3_HIST_OBSERVABLES][hist_bins]
+    double* hist_weights;              // [kHistReplicas][TP3_HIST_OBSERVABLES][hist_bins]
 };
 
 struct DumpArgs {
@@ -202,14 +202,18 @@ template <class F, int RNG> struct RngTick {
 
 template <class F> __device__ __forceinline__ F shfl_xor_t(F v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// Per-event observables (tp3.h): the histograms of a CTA live in dynamic shared memory, weights[6 nb] (f64) then
-// counts[6 nb] (u32: a CTA sees < 2^32 events), and are added to the device histograms when the CTA ends.
+// Per-event observables (tp3.h).  Event counts: u32 histograms of the CTA in dynamic shared memory (native shared
+// atomics; a CTA sees < 2^32 events), added to the device histograms when the CTA ends.  Weight sums: f64 reductions
+// straight to one of kHistReplicas device copies in L2 (fire-and-forget RED.ADD.F64; a shared-memory f64 add would be a
+// compare-and-swap loop), the copies are summed when the histograms are fetched.
+constexpr int kHistReplicas = 64;
 __device__ __forceinline__ int hist_bin(double t, int nb) {  // t in [0, 1] up to rounding
     const int b = (int)(t * (double)nb);
     return min(max(b, 0), nb - 1);
 }
 template <class F, bool SORT>
 __device__ __forceinline__ void hist_fill(const F e[3][4], const F m[5], const PhysParams<F>& P, uint32_t* hc, double* hw, int nb) {
+    // hc: the CTA's counts (shared), hw: this CTA's replica of the device weights (global)
     F w = 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) w += m[k] * P.sigma_contribs[k];
@@ -229,7 +233,7 @@ __device__ __forceinline__ void hist_fill(const F e[3][4], const F m[5], const P
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int bx = hist_bin((double)en[k] * inv, nb);
-        const int bc = hist_bin(0.5 + 0.5 * ((double)px[k] / (double)en[k]), nb);
+        const int bc = hist_bin(0.5 + 0.5 * (double)(px[k] * rcp_t(en[k])), nb);  // reciprocal: <= 1 ulp from the quotient
         atomicAdd(hc + k * nb + bx, 1u);
         atomicAdd(hw + k * nb + bx, (double)w);
         atomicAdd(hc + (3 + k) * nb + bc, 1u);
@@ -250,13 +254,10 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     fastmath_load(&sm.fm);
     const int hist_n = HIST ? TP3_HIST_OBSERVABLES * (int)a.hist_bins : 0;
-    double* const hist_w = reinterpret_cast<double*>(hist_raw);            // weights first: 8-byte aligned
-    uint32_t* const hist_c = reinterpret_cast<uint32_t*>(hist_w + hist_n);
+    uint32_t* const hist_c = reinterpret_cast<uint32_t*>(hist_raw);
+    double* const hist_w = HIST ? a.hist_weights + (size_t)(blockIdx.x % kHistReplicas) * hist_n : nullptr;
     if (HIST) {
-        for (int i = threadIdx.x; i < hist_n; i += kThreads) {
-            hist_w[i] = 0.0;
-            hist_c[i] = 0u;
-        }
+        for (int i = threadIdx.x; i < hist_n; i += kThreads) hist_c[i] = 0u;
     }
     __syncthreads();
     typename Pair<F>::type(*queue)[kQueue] = sm.w[warp].queue;
@@ -392,10 +393,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
         __syncthreads();
         for (int i = threadIdx.x; i < hist_n; i += kThreads) {
             const uint32_t n = hist_c[i];
-            if (n) {
-                atomicAdd(a.hist_counts + i, (unsigned long long)n);
-                atomicAdd(a.hist_weights + i, hist_w[i]);
-            }
+            if (n) atomicAdd(a.hist_counts + i, (unsigned long long)n);
         }
     }
 }

@@ -116,8 +116,8 @@ uint64_t tp3_launch_count(const tp3_ctx* ctx);
  *    observable 3 + k (k = 0,1,2):  cos(theta_k) = p_x,k / E_k     in [-1, 1]   (the beam is along X, evgen.rs:66-72)
  * with num_bins uniform bins over the stated range, bin = min(num_bins - 1, floor(t * num_bins)), t the value
  * mapped to [0, 1].  Histograms accumulate over all simulate calls of the context (all devices) until reset.
- * Event counts are exact; the weight sums are accumulated with floating-point atomics (order not fixed: equal
- * to ~1e-13 relative between runs).  Available for the fast kernel with the default event generator. */
+ * Event counts are exact; the weight sums are accumulated with floating-point reductions (order not fixed:
+ * equal to ~1e-13 relative between runs).  Available for the fast kernel with the default event generator. */
 #define TP3_HIST_OBSERVABLES 6
 #define TP3_HIST_MAX_BINS 1024
 /* num_bins = 0 switches the epilogue off again. */

@@ -134,6 +134,11 @@ template <class F, int RNG> DumpFn pick_dump2(bool sort, bool literal) {
     if (sort) return literal ? launch_dump<F, RNG, true, true> : launch_dump<F, RNG, true, false>;
     return literal ? launch_dump<F, RNG, false, true> : launch_dump<F, RNG, false, false>;
 }
+// f32 fast kernel, two events per lane in packed FP32 arithmetic (f32x2.cuh)
+template <int RNG> void launch_sim_x2(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
+    const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
+    simulate_kernel_x2<RNG><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, 0, st>>>(a, phys_params<f2>(p));
+}
 template <class F, int RNG> SimFn pick_sim_hist2(bool sort) { return sort ? launch_sim_hist<F, RNG, true> : launch_sim_hist<F, RNG, false>; }
 SimFn pick_sim(const tp3_params& p, bool hist = false) {
     const bool f32 = p.flags & TP3_F32, xo = p.flags & TP3_STANDARD_RANDOM;
@@ -142,6 +147,8 @@ SimFn pick_sim(const tp3_params& p, bool hist = false) {
         if (f32) return xo ? pick_sim_hist2<float, RNG_XOSHIRO>(sort) : pick_sim_hist2<float, RNG_RANF>(sort);
         return xo ? pick_sim_hist2<double, RNG_XOSHIRO>(sort) : pick_sim_hist2<double, RNG_RANF>(sort);
     }
+    if (f32 && !lit && !std::getenv("TP3_F32_SCALAR"))  // (the one-event-per-lane f32 kernel stays for A/B runs and tests)
+        return xo ? launch_sim_x2<RNG_XOSHIRO> : launch_sim_x2<RNG_RANF>;
     if (f32) return xo ? pick_sim2<float, RNG_XOSHIRO>(sort, lit) : pick_sim2<float, RNG_RANF>(sort, lit);
     return xo ? pick_sim2<double, RNG_XOSHIRO>(sort, lit) : pick_sim2<double, RNG_RANF>(sort, lit);
 }

@@ -13,6 +13,7 @@
 
 #include "../../include/tp3.h"
 #include "physics.cuh"
+#include "f32x2.cuh"
 #include "rng.cuh"
 
 namespace tp3 {
@@ -25,6 +26,9 @@ namespace tp3 {
 #endif
 #ifndef TP3_TICK_AT
 #define TP3_TICK_AT 1
+#endif
+#ifndef TP3_X2_MIN_CTAS
+#define TP3_X2_MIN_CTAS 5   // f32 two-events-per-lane kernel: 96 registers (a few spills) beat 128 registers at 4 CTAs per SM
 #endif
 #ifndef TP3_WARPS
 #define TP3_WARPS 4
@@ -76,11 +80,11 @@ template <class F> struct Pair;
 template <> struct Pair<double> { using type = double2; };
 template <> struct Pair<float> { using type = float2; };
 
-template <class F> struct WarpSmem {
+template <class F, int Q = kQueue> struct WarpSmem {
     RanfWarpSmem ranf;
     // survivors' momenta as (X,Y) and (Z,E) pairs per photon, pair-major: consecutive slots are
     // consecutive 16-byte (f64) words, so the 128-bit accesses of a warp are conflict free
-    alignas(16) typename Pair<F>::type queue[6][kQueue];
+    alignas(16) typename Pair<F>::type queue[6][Q];
 };
 template <class F> struct BlockSmem {
     FastMathSmem fm;
@@ -94,7 +98,7 @@ template <class F, int RNG> struct WarpRng;
 template <class F> struct WarpRng<F, RNG_RANF> {
     RanfWarpStream s;
     int n;
-    __device__ void init(const SimArgs& a, WarpSmem<F>* sm, uint64_t batch, uint64_t /*slot*/, int n_ev, int lane) {
+    template <class WS> __device__ void init(const SimArgs& a, WS* sm, uint64_t batch, uint64_t /*slot*/, int n_ev, int lane) {
         n = n_ev;
         if (a.jump_seeding) {
             // rng.jump() = reseed with seed + 123456 per batch (ranf.rs:136-140), i32 wrapping
@@ -134,7 +138,7 @@ template <class F> struct WarpRng<F, RNG_RANF> {
 template <class F, class Lane> struct XoshiroWarpRng {
     Lane g;
     int lo, hi, n;
-    __device__ void init(const SimArgs& a, WarpSmem<F>*, uint64_t, uint64_t slot, int n_ev, int lane) {
+    template <class WS> __device__ void init(const SimArgs& a, WS*, uint64_t, uint64_t slot, int n_ev, int lane) {
         n = n_ev;
         lo = lane * kLaneEvents;
         hi = min(n_ev, lo + kLaneEvents);
@@ -395,6 +399,162 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
             const uint32_t n = hist_c[i];
             if (n) atomicAdd(a.hist_counts + i, (unsigned long long)n);
         }
+    }
+}
+
+// ---- f32, two events per lane (f32x2.cuh) --------------------------------------------------------------------------
+// Same streams, same event physics and the same batch sums as simulate_kernel<float, RNG, ., false> (up to the order
+// of the additions), but every lane carries the events of two warp iterations through the generation, the cuts and the
+// matrix elements in packed FP32 arithmetic.
+constexpr int kQueue2 = 128;  // < 64 pending + <= 64 new survivors
+
+template <int RNG>
+__global__ void __launch_bounds__(kThreads, TP3_X2_MIN_CTAS) simulate_kernel_x2(const SimArgs a, const PhysParams<f2> P) {
+    using F = float;
+    using Word = typename RawWord<F, RNG>::type;
+    __shared__ WarpSmem<F, kQueue2> smw[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2(*queue)[kQueue2] = smw[warp].queue;
+    const FastMathSmem* const fm = nullptr;  // the f32 elementary functions are SFU instructions, no tables
+
+    WarpRng<F, RNG> rng;
+    const uint64_t slot0 = ((uint64_t)blockIdx.x * kWarps + warp) * a.batches_per_warp;
+    for (uint32_t bi = 0; bi < a.batches_per_warp; ++bi) {
+        const uint64_t slot = slot0 + bi;
+        if (slot >= a.n_batches) break;
+        const int n_ev = batch_len(a, slot);
+        if (bi == 0 || !rng.next_batch(a, n_ev, lane)) rng.init(a, &smw[warp], a.first_batch + slot, slot, n_ev, lane);
+
+        f2 spm2[5], vars[5], sigma(0.0f), variance(0.0f);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) spm2[k] = vars[k] = f2(0.0f);
+        uint32_t selected = 0;
+        // resacc.rs:121-129 for the two events of a lane; `valid` masks the drain's last, half-filled step
+        auto integrate = [&](const f2 (&e)[3][4], m2 valid) {
+            f2 m[5];
+            me_fast<f2>(e, P, m);
+            f2 w(0.0f);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                m[k] = select(valid, m[k], f2(0.0f));
+                spm2[k] += m[k];
+                vars[k] += m[k] * m[k];
+                w += m[k] * P.sigma_contribs[k];
+            }
+            sigma += w;
+            variance += w * w;
+            selected += (uint32_t)valid.x + (uint32_t)valid.y;
+        };
+        auto pop = [&](int slot_a, int slot_b, f2 (&e)[3][4]) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float2 xa = queue[2 * k][slot_a], za = queue[2 * k + 1][slot_a];
+                const float2 xb = queue[2 * k][slot_b], zb = queue[2 * k + 1][slot_b];
+                e[k][0] = f2(xa.x, xb.x); e[k][1] = f2(xa.y, xb.y); e[k][2] = f2(za.x, zb.x); e[k][3] = f2(za.y, zb.y);
+            }
+        };
+
+        int q_head = 0, q_count = 0;  // survivor queue (warp-uniform)
+        const int n_it = rng.iterations();
+        for (int it = 0; it < n_it; it += 2) {
+            Word w0[12], w1[12];
+            rng.draws(it, lane, w0);
+            const bool have_b = it + 1 < n_it;
+            if (have_b) {  // same call sequence as the one-event kernel: refill, then the next iteration's draws
+                rng.begin_next(lane);
+                rng.template tick<1>(lane); rng.template tick<2>(lane); rng.template tick<3>(lane); rng.template tick<4>(lane);
+                rng.template tick<5>(lane); rng.template tick<6>(lane); rng.template tick<7>(lane);
+                rng.draws(it + 1, lane, w1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) w1[j] = w0[j];
+            }
+            const bool more = it + 2 < n_it;
+            if (more) rng.begin_next(lane);
+            RngTick<F, RNG> tick{rng, lane, more};
+            f2 u[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) u[j] = f2(WarpRng<F, RNG>::uniform(w0[j], (j & 3) == 1), WarpRng<F, RNG>::uniform(w1[j], (j & 3) == 1));
+            f2 p[3][4];
+            gen_event<f2, false, false>(u, P.e_total, fm, p, tick);
+            const m2 ok = keep_event<f2, false, false>(p, P);
+            const bool keep_a = ok.x && rng.event_of(it, lane) >= 0;
+            const bool keep_b = ok.y && have_b && rng.event_of(it + 1, lane) >= 0;
+            // evcut.rs:42-96 as predicate masks; the survivors of both iterations are compacted into the queue
+            const unsigned mask_a = __ballot_sync(0xffffffffu, keep_a), mask_b = __ballot_sync(0xffffffffu, keep_b);
+            const unsigned below = (1u << lane) - 1u;
+            if (keep_a) {
+                const int s = (q_head + q_count + __popc(mask_a & below)) & (kQueue2 - 1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    queue[2 * k][s] = make_float2(p[k][0].lo(), p[k][1].lo());
+                    queue[2 * k + 1][s] = make_float2(p[k][2].lo(), p[k][3].lo());
+                }
+            }
+            q_count += __popc(mask_a);
+            if (keep_b) {
+                const int s = (q_head + q_count + __popc(mask_b & below)) & (kQueue2 - 1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    queue[2 * k][s] = make_float2(p[k][0].hi(), p[k][1].hi());
+                    queue[2 * k + 1][s] = make_float2(p[k][2].hi(), p[k][3].hi());
+                }
+            }
+            q_count += __popc(mask_b);
+            __syncwarp();
+            if (q_count >= 64) {
+                f2 e[3][4];
+                pop((q_head + lane) & (kQueue2 - 1), (q_head + 32 + lane) & (kQueue2 - 1), e);
+                __syncwarp();
+                q_head = (q_head + 64) & (kQueue2 - 1);
+                q_count -= 64;
+                integrate(e, m2{true, true});
+            }
+        }
+        if (q_count > 0) {  // drain (warp-uniform condition; fewer than 64 events)
+            f2 e[3][4];
+            pop((q_head + lane) & (kQueue2 - 1), (q_head + 32 + lane) & (kQueue2 - 1), e);
+            // lanes without an event still hold finite momenta of earlier events or zeros: give them a harmless event
+            const m2 valid{lane < q_count, 32 + lane < q_count};
+            const f2 one(1.0f), zero(0.0f);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                e[k][0] = select(valid, e[k][0], k == 0 ? one : zero);
+                e[k][1] = select(valid, e[k][1], k == 1 ? one : zero);
+                e[k][2] = select(valid, e[k][2], k == 2 ? one : zero);
+                e[k][3] = select(valid, e[k][3], one + one);
+            }
+            integrate(e, valid);
+        }
+
+        // ResultsAccumulator of the batch: the two halves, then the xor-shuffle tree over the 32 lane-partials
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            v[k] = spm2[k].lo() + spm2[k].hi();
+            v[5 + k] = vars[k].lo() + vars[k].hi();
+        }
+        v[10] = sigma.lo() + sigma.hi();
+        v[11] = variance.lo() + variance.hi();
+        uint32_t n = selected;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) v[k] += shfl_xor_t(v[k], off);
+            n += __shfl_xor_sync(0xffffffffu, n, off);
+        }
+        if (lane == 0) {
+            tp3_acc* o = a.out + slot;
+            o->selected_events = n;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                o->spm2[k] = (double)v[k];
+                o->vars[k] = (double)v[5 + k];
+            }
+            o->sigma = (double)v[10];
+            o->variance = (double)v[11];
+        }
+        __syncwarp();
     }
 }
 

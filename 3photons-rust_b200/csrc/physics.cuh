@@ -27,6 +27,12 @@ template <> struct Num<float> {
     static constexpr float RAC8 = 2.0f * 1.41421356237309504880f;
 };
 
+// Result type of a comparison, and "is this (warp-uniform) parameter positive": bool / the value itself for the
+// scalar Floats; the two-events-per-lane type of f32x2.cuh supplies its own.
+template <class F> struct MaskOf { using type = bool; };
+__device__ __forceinline__ bool uniform_positive(double x) { return x > 0.0; }
+__device__ __forceinline__ bool uniform_positive(float x) { return x > 0.0f; }
+
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
 __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __forceinline__ double log_t(double x) { return log(x); }
@@ -86,7 +92,7 @@ __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, 
     for (int c = 0; c < 4; ++c) r[c] = (q[0][c] + q[1][c]) + q[2][c];
     const F m2 = r[3] * r[3] - ((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
     F alpha, m, beta;
-    if (LITERAL) {
+    if constexpr (LITERAL) {
         alpha = e_total / m2;
         m = sqrt_t(m2);
         beta = (F)1 / (m + r[3]);
@@ -101,7 +107,7 @@ __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, 
     for (int k = 0; k < 3; ++k) {
         const F rq = (q[k][0] * r[0] + q[k][1] * r[1]) + q[k][2] * r[2];
         p[k][3] = alpha * (r[3] * q[k][3] - rq);
-        if (LITERAL) {
+        if constexpr (LITERAL) {
             const F b = beta * rq - q[k][3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) p[k][c] = alpha * (m * q[k][c] + b * r[c]);
@@ -111,7 +117,7 @@ __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, 
             for (int c = 0; c < 3; ++c) p[k][c] = am * q[k][c] + ab * r[c];
         }
     }
-    if (SORT) {
+    if constexpr (SORT) {
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -140,7 +146,7 @@ __device__ __forceinline__ void raw_photon(const F* u, const FastMathSmem* fm, F
     const F c = (F)2 * u[0] - (F)1;
     const F e = u[2] * u[3];
     F sphi, cphi, st, en;
-    if (LITERAL) {
+    if constexpr (LITERAL) {
         sincos_t(Num<F>::TWO_PI * u[1], &sphi, &cphi);
         st = sqrt_t((F)1 - c * c);
         en = -log_t(e + Num<F>::MIN_POSITIVE);
@@ -209,14 +215,14 @@ __device__ __forceinline__ void gen_event_faster(const F u9[9], const F xy[3][2]
 // The beam is along X: p(e-) = (-E/2, 0, 0, E/2) (evgen.rs:66-69), so p_gamma . p_e = -X E/2 and
 // the common factor E/2 drops out of evcut.rs:52-62 and :80-92.
 template <class F, bool SORT, bool LITERAL>
-__device__ __forceinline__ bool keep_event(const F p[3][4], const PhysParams<F>& P) {
+__device__ __forceinline__ typename MaskOf<F>::type keep_event(const F p[3][4], const PhysParams<F>& P) {
     // All comparisons are evaluated (no short circuit: they are independent, a chain of && would serialise them)
-    bool ok;
-    if (SORT) ok = !(p[2][3] < P.e_min);
+    typename MaskOf<F>::type ok;
+    if constexpr (SORT) ok = !(p[2][3] < P.e_min);
     else ok = (p[0][3] >= P.e_min) & (p[1][3] >= P.e_min) & (p[2][3] >= P.e_min);  // event.rs:96-105 (min E < e_min rejects)
 #pragma unroll
     for (int k = 0; k < 3; ++k) ok = ok & !(abs_t(p[k][0]) > P.acut * p[k][3]);
-    if (LITERAL) {
+    if constexpr (LITERAL) {
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -235,12 +241,12 @@ __device__ __forceinline__ bool keep_event(const F p[3][4], const PhysParams<F>&
             ok = ok & !(omb * (p[i][3] * p[j][3]) > P.e_total * (he - p[k][3]));
         }
     }
-    if (P.sincut > (F)0) {  // |n_x| < sincut |n|  (uniform branch; the default sincut is 0)
+    if (uniform_positive(P.sincut)) {  // |n_x| < sincut |n|  (uniform branch; the default sincut is 0)
         const F nx = p[0][1] * p[1][2] - p[0][2] * p[1][1];
         const F ny = p[0][2] * p[1][0] - p[0][0] * p[1][2];
         const F nz = p[0][0] * p[1][1] - p[0][1] * p[1][0];
         const F nn = sqrt_t((nx * nx + ny * ny) + nz * nz);
-        ok = ok && !(abs_t(nx) < P.sincut * nn);
+        ok = ok & !(abs_t(nx) < P.sincut * nn);
     }
     return ok;
 }
@@ -336,6 +342,17 @@ template <class F> __device__ void me_literal(const F p[3][4], const PhysParams<
 //   m2 = g_b-^2 8 e^2     * ( |sum_k s_0k^2 s_ij^2|^2 + |sum_k s_1k^2 s_ij^2|^2 )
 //   m3 + i m4 = -16 e^2 g_a g_b+ * sum_k ( P_k^2 W_k + Q_k^2 conj W_k ),  W_k = s_ij^2 u_k conj(U) / D, U = u_0 u_1 u_2
 // (ij = the two photons other than k).  The common powers of h^2 are pulled out of the sums.
+// photon along -Z (spinor.rs:42-46): xx = 0, fx = sqrt(2E)  =>  A = 0, c = 0, g = 2E.
+// Reached in f32 (E + Z rounds to 0 about once per 1e7 events), never observed in f64.
+template <class F> __device__ __forceinline__ void degenerate_fix(F& A, Cplx<F>& g, F& X, F& Y, F E) {
+    if (!(A > Num<F>::MIN_POSITIVE)) {
+        A = 0;
+        g = {E + E, (F)0};
+        X = 0;
+        Y = 0;
+    }
+}
+
 template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], const PhysParams<F>& P, F m[5]) {
     const F e = P.e_total;
     F A[3], Ep[3], Em[3];       // A_k, E_k + X_k, E_k - X_k
@@ -351,14 +368,7 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
         const F iA = rcp_t(A[k]);
         g[k].re = (X * X - Y * Y) * iA;
         g[k].im = ((X + X) * Y) * iA;
-        // photon along -Z (spinor.rs:42-46): xx = 0, fx = sqrt(2E)  =>  A = 0, c = 0, g = 2E.
-        // Reached in f32 (E + Z rounds to 0 about once per 1e7 events), never observed in f64.
-        if (!(A[k] > Num<F>::MIN_POSITIVE)) {
-            A[k] = 0;
-            g[k] = {E + E, (F)0};
-            X = 0;
-            Y = 0;
-        }
+        degenerate_fix(A[k], g[k], X, Y, E);
         cx[k] = X;
         cy[k] = Y;
         tk[k] = {A[k] + g[k].re, g[k].im};

@@ -328,6 +328,26 @@ def test_default_run_f32(tp3, valeurs_text, features, suffix):
         assert abs(g - w) <= F32_REL_RUN * abs(w) + 1e-4 * abs(w), f"line {ln}: {g} vs {w}"
 
 
+@pytest.mark.parametrize("features", ["f32", "standard-random,f32", "f32,no-photon-sorting", "f32,multi-threading,faster-threading"])
+def test_f32_two_events_per_lane_equals_one_event_per_lane(tp3, valeurs_text, features, monkeypatch):
+    """The shipped f32 kernel carries two events per lane in packed FP32 arithmetic (f32x2.cuh, FFMA2 / FMUL2 / FADD2);
+    the one-event-per-lane instantiation of the generic kernel stays behind TP3_F32_SCALAR.  Same streams, same event
+    physics: the event selection may differ only where a cut is decided within rounding, the sums by the order of
+    the additions.  A ragged last batch (77 events: odd number of warp iterations, half-filled last step)."""
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    nb = 12
+    with tp3.Simulator(cfg) as sim:
+        packed = sim.simulate_batches(3, nb, 77)
+    monkeypatch.setenv("TP3_F32_SCALAR", "1")
+    with tp3.Simulator(cfg) as sim:
+        scalar = sim.simulate_batches(3, nb, 77)
+    for b in range(nb):
+        assert abs(packed[b].selected_events - scalar[b].selected_events) <= 1, f"batch {b}"
+        g, w = acc_fields(packed[b]), acc_fields(scalar[b])
+        for k in (0, 1, 2, 5, 6, 7, 10, 11):
+            assert abs(g[k] - w[k]) <= 3e-4 * abs(w[k]), f"batch {b} field {k}: {g[k]} vs {w[k]}"
+
+
 # ------------------------------------------------------------------------------ faster-evgen
 @pytest.mark.parametrize("features", ["faster-evgen", "faster-evgen,no-photon-sorting", "faster-evgen,standard-random",
                                       "faster-evgen,multi-threading,faster-threading",

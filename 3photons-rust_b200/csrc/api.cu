@@ -489,6 +489,12 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
             return TP3_E_INVALID;
         }
     }
+    // Reach of the jump-ahead tables: 5 byte digits = 2^40 RANF rounds (12e4 / 55 rounds per batch; ~0.32 per event under
+    // faster-evgen) resp. 2^40 xoshiro batch strides.
+    if (first + n > ((c->params.flags & TP3_STANDARD_RANDOM) ? (1ull << 40) : 300000000ull)) {
+        c->err = "batch index beyond the reach of the jump-ahead tables (3e8 batches with RANF, 2^40 with xoshiro)";
+        return TP3_E_INVALID;
+    }
     const bool faster = c->params.flags & TP3_FASTER_EVGEN;
     const bool seq_faster = faster && !(c->params.flags & TP3_FASTER_THREADING);
     std::vector<uint32_t> fe_ranf;

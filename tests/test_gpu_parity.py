@@ -287,6 +287,14 @@ def test_bad_arguments_are_reported(sims, tp3):
         sim.simulate_batches(0, 1, 10001)
     with pytest.raises(tp3.Tp3Error):
         sims("multi-threading,faster-threading").simulate_batches(6190, 20)  # RANF jump() seeds leave [0,1e9)
+    with pytest.raises(tp3.Tp3Error):
+        sim.simulate_batches(300_000_000, 1)  # beyond the 2^40 rounds the RANF jump-ahead table reaches
+    with pytest.raises(tp3.Tp3Error):
+        sims("standard-random").simulate_batches(1 << 40, 1)
+    # the last batches within reach still work (and are positioned: two calls, same bits)
+    far = sim.simulate_batches(299_999_998, 2)
+    assert bytes(far) == bytes(sim.simulate_batches(299_999_998, 2))
+    assert all(6900 < a.selected_events < 7300 for a in far)
 
 
 # -------------------------------------------------------------------- whole runs vs goldens

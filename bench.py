@@ -259,6 +259,8 @@ def main():
     if rank == 0:
         achieved = value / world * FLOP_PER_EVENT / 1e12  # per GPU, to compare with a per-GPU peak
         f32 = "f32" in args.features
+        # bytes per launch, from the committed ncu capture of exactly this launch shape (default features, 1e6 batches)
+        ncu_traffic = 58501888 if (not args.features and args.kernel == "fast" and nb // world == 1000000) else None
         line = {
             "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -274,7 +276,11 @@ def main():
                             "argument block (SimArgs 312 B + PhysParams 104 B) of the 8 chunk launches per GPU"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64" if not f32 else "fp32", "achieved": achieved, "peak": peak_tflops,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": ncu_traffic,
+                         "traffic_note": "DRAM bytes of one launch of the default f64 kernel over 1e6 batches, ncu --set full "
+                                         "(profiles/r01_bench_kernel_1e10_events.txt): 0.28 MB read (the jump table) + 58.2 MB "
+                                         "written of the 104 MB of per-batch accumulators (the rest is still in L2 when the "
+                                         "kernel ends); the bound is the FP64 pipe, not HBM",
                          "peak_source": "measured live: tp3_peak_probe (8 independent FMA chains per thread, all SMs)",
                          "flop_per_event": FLOP_PER_EVENT},
             "cpu_baseline": cpu,

@@ -279,6 +279,31 @@ int oracle_events(const char* valeurs_text, uint32_t feature_mask, uint32_t n, d
     return ft.f32 ? go(0.0f, Ranf<float>()) : go(0.0, Ranf<double>());
 }
 
+// finalize (resacc.rs:142-223) + the text surfaces (resfin.rs:66-194, output.rs:30-177) applied to GIVEN sums: lets the
+// tests cross-check the product's host formatting against this restatement on values the golden runs never produce.
+int oracle_finalize_text(const char* valeurs_text, uint32_t feature_mask, const oracle_acc* sums, char* res_data_buf,
+                         size_t res_data_cap, char* stdout_buf, size_t stdout_cap) {
+    Features ft = features_from_mask(feature_mask);
+    auto go = [&](auto fzero) -> int {
+        using F = decltype(fzero);
+        Config<F> cfg;
+        if (!load_config<F>(valeurs_text, cfg).empty()) return 1;
+        Accumulator<F> acc(cfg, event_weight<F>(cfg.e_total));
+        acc.selected_events = sums->selected_events;
+        for (int k = 0; k < 5; ++k) {
+            acc.spm2[k] = (F)sums->spm2[k];
+            acc.vars[k] = (F)sums->vars[k];
+        }
+        acc.sigma = (F)sums->sigma;
+        acc.variance = (F)sums->variance;
+        FinalResults<F> fin = finalize(cfg, acc);
+        copy_text(config_echo(cfg) + "IBegin\n" + eric(cfg, fin) + fawzi(cfg, fin), stdout_buf, stdout_cap);
+        copy_text(res_data(cfg, fin), res_data_buf, res_data_cap);
+        return 0;
+    };
+    return ft.f32 ? go(0.0f) : go(0.0);
+}
+
 // Host-side constants for a configuration (coupling.rs:23-33, evgen.rs:60-62, resacc.rs:59-117),
 // out = {g_a, g_beta_p, g_beta_m, ev_weight, norm_weight, sigma_contribs[5]}
 int oracle_constants(const char* valeurs_text, uint32_t feature_mask, double* out) {

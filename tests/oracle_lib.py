@@ -41,6 +41,8 @@ def lib():
         L.oracle_events.restype = C.c_int
         L.oracle_events.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_double)]
+        L.oracle_finalize_text.restype = C.c_int
+        L.oracle_finalize_text.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Acc), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.oracle_constants.restype = C.c_int
         L.oracle_constants.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_double)]
         _lib = L
@@ -94,3 +96,13 @@ def constants(valeurs_text, features=""):
     rc = lib().oracle_constants(valeurs_text.encode(), mask(features), out)
     assert rc == 0
     return list(out)
+
+
+def finalize_text(valeurs_text, features, acc):
+    """(res.data text, stdout text) of the oracle's finalize + writers applied to the given sums (an Acc)."""
+    rd = C.create_string_buffer(1 << 14)
+    so = C.create_string_buffer(1 << 14)
+    mine = Acc.from_buffer_copy(bytes(acc))  # same 104-byte layout as the product's tp3_acc
+    rc = lib().oracle_finalize_text(valeurs_text.encode(), mask(features), C.byref(mine), rd, len(rd), so, len(so))
+    assert rc == 0
+    return rd.value.decode(), so.value.decode()

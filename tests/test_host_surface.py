@@ -108,6 +108,47 @@ def test_finalize_and_text_from_oracle_sums(tp3, oracle, valeurs_text, features,
     assert compare(fin.stdout(), golden("stdout.log-features_" + suffix), **out_tol) == []
 
 
+@pytest.mark.parametrize("features", ["", "f32"])
+def test_finalize_and_text_randomised_against_oracle(tp3, oracle, valeurs_text, features):
+    """The two independent restatements of finalize + the Rust-compatible number formatting (host.cpp, the product;
+    oracle_text.hpp, the checker) must print the same text for sums the golden runs never produce: every decade,
+    both signs, exact powers of ten, values that round up into the next decade, zero."""
+    import random
+    rnd = random.Random(20240607)
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    n = cfg.num_events
+
+    def value(scale_pow):
+        kind = rnd.random()
+        if kind < 0.1:
+            return 0.0
+        if kind < 0.2:
+            return rnd.choice([-1.0, 1.0]) * 10.0 ** rnd.randint(-12, 12)                    # exact powers of ten
+        if kind < 0.3:
+            return rnd.choice([-1.0, 1.0]) * (10.0 ** rnd.randint(-8, 8)) * (1 - 1e-15)      # rounds up into the next decade
+        return rnd.choice([-1.0, 1.0]) * rnd.uniform(1.0, 10.0) * 10.0 ** (scale_pow + rnd.randint(-9, 9))
+
+    for case in range(400):
+        acc = tp3.Acc()
+        acc.selected_events = rnd.randint(1, n)
+        for k in range(5):
+            acc.spm2[k] = value(3) if k >= 3 else abs(value(3))
+            acc.vars[k] = abs(value(6)) + acc.spm2[k] ** 2 / n   # keeps the variances non-negative, as real sums are
+        acc.sigma = abs(value(0)) + 1e-300
+        acc.variance = abs(value(-6)) + acc.sigma ** 2 / n
+        if "f32" in features:  # the sums of an f32 run are f32 values
+            import struct
+            for name in ("sigma", "variance"):
+                setattr(acc, name, struct.unpack("f", struct.pack("f", getattr(acc, name)))[0])
+            for k in range(5):
+                acc.spm2[k] = struct.unpack("f", struct.pack("f", acc.spm2[k]))[0]
+                acc.vars[k] = struct.unpack("f", struct.pack("f", min(acc.vars[k], 3e38)))[0]
+        fin = tp3.finalize(cfg, acc)
+        want_rd, want_so = oracle.finalize_text(valeurs_text, features, acc)
+        assert fin.res_data() == want_rd, f"case {case}"
+        assert fin.stdout() == want_so, f"case {case}"
+
+
 def test_batch_layout_and_sharding(tp3):
     assert tp3.batch_layout(10_000_000) == (1000, 10000)
     assert tp3.batch_layout(10_001) == (2, 1)

@@ -277,7 +277,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "fp64" if not f32 else "fp32", "achieved": achieved, "peak": peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": ncu_traffic,
-                         "traffic_note": "DRAM bytes of one launch of the default f64 kernel over 1e6 batches, ncu --set full "
+                         "traffic_note": None if ncu_traffic is None else
+                                         "DRAM bytes of one launch of the default f64 kernel over 1e6 batches, ncu --set full "
                                          "(profiles/r01_bench_kernel_1e10_events.txt): 0.28 MB read (the jump table) + 58.2 MB "
                                          "written of the 104 MB of per-batch accumulators (the rest is still in L2 when the "
                                          "kernel ends); the bound is the FP64 pipe, not HBM",

@@ -107,8 +107,9 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
 
 template <class F, int RNG, bool SORT, bool LITERAL>
 void launch_sim(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
-    const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
-    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, 0, st>>>(a, phys_params<F>(p));
+    constexpr int warps = sim_warps(LITERAL, false);
+    const uint64_t per_cta = (uint64_t)warps * a.batches_per_warp;
+    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), 32 * warps, 0, st>>>(a, phys_params<F>(p));
 }
 // Fast kernel with the per-event observable epilogue: the CTA's event counts in dynamic shared memory (4 bytes per bin).
 template <class F, int RNG, bool SORT>

@@ -97,6 +97,7 @@ __device__ __forceinline__ void sincos_scaled_t(f2 t, const FastMathSmem* fm, f2
 }
 
 // me_fast's photon-along-(-Z) case (spinor.rs:42-46), per half
+__device__ __forceinline__ bool any_degenerate(const f2*) { return true; }  // the fix is applied per half, branch-free
 __device__ __forceinline__ void degenerate_fix(f2& A, Cplx<f2>& g, f2& X, f2& Y, f2 E) {
     const m2 ok = A > f2(Num<float>::MIN_POSITIVE);
     if (ok.x && ok.y) return;  // (about one event in 1e7)

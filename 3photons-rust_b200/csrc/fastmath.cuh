@@ -19,10 +19,26 @@ namespace tp3 {
 
 #include "fastmath_tables.inc"
 
+#ifndef TP3_COEFF_IMM
+#define TP3_COEFF_IMM 1
+#endif
+#if TP3_COEFF_IMM
+// Polynomial coefficients as literals: ptxas materialises them in uniform registers (UMOV pairs), and a DFMA whose
+// third source is a uniform register reads two register pairs from the vector register file instead of three.
+// (As __constant__ arrays they were loaded into vector registers with LDC.64 once per event and every Horner step
+// became a three-register DFMA: 3 cycles instead of 2 on B200, profiles/r01_micro_fp64_operands.txt.)
+#define TP3_COEFF_ARRAYS                                   \
+    constexpr double kLog1p[5] = {TP3_LOG1P_COEFFS};       \
+    constexpr double kNegLn2 = TP3_NEG_LN2;                \
+    constexpr double kRotSin[3] = {TP3_ROT_SIN_COEFFS};    \
+    constexpr double kRotCos[3] = {TP3_ROT_COS_COEFFS};
+#else
+#define TP3_COEFF_ARRAYS
 __constant__ double kLog1p[5] = {TP3_LOG1P_COEFFS};
 __constant__ double kNegLn2 = TP3_NEG_LN2;
 __constant__ double kRotSin[3] = {TP3_ROT_SIN_COEFFS};
 __constant__ double kRotCos[3] = {TP3_ROT_COS_COEFFS};
+#endif
 
 struct FastMathSmem {
     double2 log_tab[128];
@@ -81,6 +97,7 @@ __device__ __forceinline__ double fast_sqrt(double x) {
 
 // -log(x) for finite normal x > 0
 __device__ __forceinline__ double fast_neg_log(double x, const FastMathSmem* sm) {
+    TP3_COEFF_ARRAYS
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int k = (hi >> 20) - 1023;
     const double2 t = sm->log_tab[(hi >> 13) & 127];
@@ -98,6 +115,7 @@ __device__ __forceinline__ double fast_neg_log(double x, const FastMathSmem* sm)
 // 2 pi u = 2 pi (k + d) / 256 with k = rint(t), |d| <= 1/2 (exact), so the rotation angle is at most pi/256 and
 // degree-5 / degree-6 Taylor polynomials are exact to 1e-17; no quadrant logic, 12 FP64 instructions.
 __device__ __forceinline__ void fast_sincos_256(double t, const FastMathSmem* sm, double& s, double& c) {
+    TP3_COEFF_ARRAYS
     const double kf = rint(t);
     const int k = __double2int_rn(t) & 255;
     const double2 sc = sm->sincos_tab[k];

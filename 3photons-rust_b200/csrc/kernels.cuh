@@ -31,13 +31,26 @@ namespace tp3 {
 #define TP3_X2_MIN_CTAS 5   // f32 two-events-per-lane kernel: 96 registers (a few spills) beat 128 registers at 4 CTAs per SM
 #endif
 #ifndef TP3_WARPS
-#define TP3_WARPS 4
+#define TP3_WARPS 4         // warps (batches) per CTA of the kernels that share per-CTA state: histogram epilogue, literal, f32 x2, dump
+#endif
+#ifndef TP3_FAST_WARPS
+#define TP3_FAST_WARPS 1    // warps per CTA of the plain fast kernel: one-warp CTAs free their SM slot as soon as their batches are
+#endif                      // done instead of waiting for the slowest of four warps (+2 %, profiles/r01_ab_variants.txt)
+#ifndef TP3_FAST_MIN_CTAS
+#define TP3_FAST_MIN_CTAS (16 / TP3_FAST_WARPS)   // 16 warps per SM at 128 registers
+#endif
+#ifndef TP3_ACC_SMEM
+#define TP3_ACC_SMEM 0      // 1: the lanes' 12 partial sums live in shared memory (frees 24 registers in the event loop; slower)
+#endif
+#ifndef TP3_P3_CONS
+#define TP3_P3_CONS 1       // 1: the survivor queue holds two photons, the third is rebuilt from 4-momentum conservation
 #endif
 constexpr int kWarps = TP3_WARPS;        // batches per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kBatch = TP3_EVENT_BATCH_SIZE;
 constexpr int kLaneEvents = (kBatch + 31) / 32;  // xoshiro: contiguous events per lane (313)
 constexpr int kQueue = 64;               // survivor queue slots per warp (< 32 pending + <= 32 new)
+constexpr int kQueuePhotons = TP3_P3_CONS ? 2 : 3;
 
 enum RngKind { RNG_RANF = 0, RNG_XOSHIRO = 1 };
 
@@ -80,16 +93,22 @@ template <class F> struct Pair;
 template <> struct Pair<double> { using type = double2; };
 template <> struct Pair<float> { using type = float2; };
 
-template <class F, int Q = kQueue> struct WarpSmem {
+template <class F, int Q = kQueue, int NP = kQueuePhotons> struct WarpSmem {
     RanfWarpSmem ranf;
     // survivors' momenta as (X,Y) and (Z,E) pairs per photon, pair-major: consecutive slots are
     // consecutive 16-byte (f64) words, so the 128-bit accesses of a warp are conflict free
-    alignas(16) typename Pair<F>::type queue[6][Q];
+    alignas(16) typename Pair<F>::type queue[2 * NP][Q];
 };
-template <class F> struct BlockSmem {
+template <class F, int W = kWarps> struct BlockSmem {
     FastMathSmem fm;
-    WarpSmem<F> w[kWarps];
+    WarpSmem<F> w[W];
+#if TP3_ACC_SMEM
+    F acc[W][12][32];  // field-major: a warp's access to one field is one conflict-free wavefront (two for f64)
+#endif
 };
+// Warps per CTA / minimum resident CTAs of simulate_kernel: the plain fast kernel runs as one-warp CTAs.
+__host__ __device__ constexpr int sim_warps(bool literal, bool hist) { return (literal || hist) ? kWarps : TP3_FAST_WARPS; }
+__host__ __device__ constexpr int sim_min_ctas(bool literal, bool hist) { return literal ? 2 : hist ? TP3_MIN_CTAS : TP3_FAST_MIN_CTAS; }
 
 // Per-warp random source: hands each lane the 12 raw words of "its" event of iteration `it`.
 template <class F, int RNG> struct WarpRng;
@@ -185,6 +204,43 @@ template <class F> struct LaneAcc {
         sigma += w;
         variance += w * w;
     }
+    __device__ __forceinline__ void fields(F v[12]) const {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            v[k] = spm2[k];
+            v[5 + k] = vars[k];
+        }
+        v[10] = sigma;
+        v[11] = variance;
+    }
+};
+
+// The same sums kept in the warp's shared memory: 12 load-add-store per matrix-element step instead of 24 live registers.
+template <class F> struct SmemLaneAcc {
+    F (*a)[32];
+    int lane;
+    uint32_t selected;
+    __device__ void clear() {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a[k][lane] = 0;
+        selected = 0;
+    }
+    __device__ __forceinline__ void integrate(const F m[5], const F sc[5]) {
+        selected += 1;
+        F w = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            a[k][lane] += m[k];
+            a[5 + k][lane] += m[k] * m[k];
+            w += m[k] * sc[k];
+        }
+        a[10][lane] += w;
+        a[11][lane] += w * w;
+    }
+    __device__ __forceinline__ void fields(F v[12]) const {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v[k] = a[k][lane];
+    }
 };
 
 // Tick hook handed to gen_event: step K of the pipelined refill, if there is a next iteration.
@@ -245,17 +301,41 @@ __device__ __forceinline__ void hist_fill(const F e[3][4], const F m[5], const P
     }
 }
 
+// Survivor queue of a warp: momenta as (X,Y) and (Z,E) pairs per photon.  With TP3_P3_CONS only photons 0 and 1 are
+// stored; photon 2 is what 4-momentum conservation leaves (the transform of evgen.rs:94-106 maps the photons' total
+// momentum to (0,0,0,e_total) up to rounding error, the same identity the pair cuts and |s_ij|^2 already rely on).
+template <class F, class Q> __device__ __forceinline__ void queue_push(Q queue, int slot, const F p[3][4]) {
+#pragma unroll
+    for (int k = 0; k < kQueuePhotons; ++k) {
+        queue[2 * k][slot] = {p[k][0], p[k][1]};
+        queue[2 * k + 1][slot] = {p[k][2], p[k][3]};
+    }
+}
+template <class F, class Q> __device__ __forceinline__ void queue_pop(Q queue, int slot, F e_total, F e[3][4]) {
+#pragma unroll
+    for (int k = 0; k < kQueuePhotons; ++k) {
+        const typename Pair<F>::type xy = queue[2 * k][slot], ze = queue[2 * k + 1][slot];
+        e[k][0] = xy.x; e[k][1] = xy.y; e[k][2] = ze.x; e[k][3] = ze.y;
+    }
+    if (kQueuePhotons == 2) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) e[2][c] = -(e[0][c] + e[1][c]);
+        e[2][3] = (e_total - e[0][3]) - e[1][3];
+    }
+}
+
 // Number of events of batch `slot` of the launch.
 __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
     return (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
 }
 
 template <class F, int RNG, bool SORT, bool LITERAL, bool HIST = false>
-__global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
-    __shared__ BlockSmem<F> sm;
+__global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LITERAL, HIST)) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
+    constexpr int kWarps = sim_warps(LITERAL, HIST), kThreads = 32 * kWarps;  // this kernel's CTA shape
+    __shared__ BlockSmem<F, kWarps> sm;
     extern __shared__ __align__(16) unsigned char hist_raw[];
     using Word = typename RawWord<F, RNG>::type;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = kWarps == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     fastmath_load(&sm.fm);
     const int hist_n = HIST ? TP3_HIST_OBSERVABLES * (int)a.hist_bins : 0;
     uint32_t* const hist_c = reinterpret_cast<uint32_t*>(hist_raw);
@@ -280,7 +360,11 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
     const int n_ev = batch_len(a, slot);
     if (bi == 0 || !rng.next_batch(a, n_ev, lane)) rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
 
+#if TP3_ACC_SMEM
+    SmemLaneAcc<F> acc{sm.acc[warp], lane, 0};
+#else
     LaneAcc<F> acc;
+#endif
     acc.clear();
     int q_head = 0, q_count = 0;  // survivor queue (warp-uniform)
     const int n_it = rng.iterations();
@@ -319,11 +403,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
         const unsigned mask = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int slot = (q_head + q_count + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                queue[2 * k][slot] = {p[k][0], p[k][1]};
-                queue[2 * k + 1][slot] = {p[k][2], p[k][3]};
-            }
+            queue_push<F>(queue, slot, p);
         }
         q_count += __popc(mask);
         __syncwarp();
@@ -332,11 +412,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
         if (q_count >= 32) {
             const int slot = (q_head + lane) & (kQueue - 1);
             F e[3][4];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const typename Pair<F>::type xy = queue[2 * k][slot], ze = queue[2 * k + 1][slot];
-                e[k][0] = xy.x; e[k][1] = xy.y; e[k][2] = ze.x; e[k][3] = ze.y;
-            }
+            queue_pop<F>(queue, slot, P.e_total, e);
             __syncwarp();
             q_head = (q_head + 32) & (kQueue - 1);
             q_count -= 32;
@@ -353,11 +429,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
     if (!LITERAL && lane < q_count) {  // drain
         const int slot = (q_head + lane) & (kQueue - 1);
         F e[3][4];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const typename Pair<F>::type xy = queue[2 * k][slot], ze = queue[2 * k + 1][slot];
-            e[k][0] = xy.x; e[k][1] = xy.y; e[k][2] = ze.x; e[k][3] = ze.y;
-        }
+        queue_pop<F>(queue, slot, P.e_total, e);
         F m[5];
         me_fast<F>(e, P, m);
         acc.integrate(m, P.sigma_contribs);
@@ -366,13 +438,7 @@ __global__ void __launch_bounds__(kThreads, LITERAL ? 2 : TP3_MIN_CTAS) simulate
 
     // ResultsAccumulator of the batch: xor-shuffle tree over the 32 lane-partials (deterministic)
     F v[12];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        v[k] = acc.spm2[k];
-        v[5 + k] = acc.vars[k];
-    }
-    v[10] = acc.sigma;
-    v[11] = acc.variance;
+    acc.fields(v);
     uint32_t n = acc.selected;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -412,7 +478,7 @@ template <int RNG>
 __global__ void __launch_bounds__(kThreads, TP3_X2_MIN_CTAS) simulate_kernel_x2(const SimArgs a, const PhysParams<f2> P) {
     using F = float;
     using Word = typename RawWord<F, RNG>::type;
-    __shared__ WarpSmem<F, kQueue2> smw[kWarps];
+    __shared__ WarpSmem<F, kQueue2, 3> smw[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2(*queue)[kQueue2] = smw[warp].queue;
     const FastMathSmem* const fm = nullptr;  // the f32 elementary functions are SFU instructions, no tables

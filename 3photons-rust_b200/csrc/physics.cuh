@@ -344,6 +344,9 @@ template <class F> __device__ void me_literal(const F p[3][4], const PhysParams<
 // (ij = the two photons other than k).  The common powers of h^2 are pulled out of the sums.
 // photon along -Z (spinor.rs:42-46): xx = 0, fx = sqrt(2E)  =>  A = 0, c = 0, g = 2E.
 // Reached in f32 (E + Z rounds to 0 about once per 1e7 events), never observed in f64.
+#ifndef TP3_DEGENERATE_VOTE
+#define TP3_DEGENERATE_VOTE 0   // 1: the fix-up behind a warp vote + uniform branch (measured 0.5 % slower than the predicated moves)
+#endif
 template <class F> __device__ __forceinline__ void degenerate_fix(F& A, Cplx<F>& g, F& X, F& Y, F E) {
     if (!(A > Num<F>::MIN_POSITIVE)) {
         A = 0;
@@ -353,6 +356,13 @@ template <class F> __device__ __forceinline__ void degenerate_fix(F& A, Cplx<F>&
     }
 }
 
+// TP3_DEGENERATE_VOTE: apply the spinor.rs:42-46 fix-up only if some lane of the (converged part of the) warp needs it
+// (in f64 none ever has), behind one vote + a uniform branch instead of predicated moves.  Measured slightly slower than
+// the predicated form (profiles/r01_ab_variants.txt), so it is off; the packed f32 type always applies the fix per half.
+template <class F> __device__ __forceinline__ bool any_degenerate(const F A[3]) {
+    return __any_sync(__activemask(), !(A[0] > Num<F>::MIN_POSITIVE) | !(A[1] > Num<F>::MIN_POSITIVE) | !(A[2] > Num<F>::MIN_POSITIVE));
+}
+
 template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], const PhysParams<F>& P, F m[5]) {
     const F e = P.e_total;
     F A[3], Ep[3], Em[3];       // A_k, E_k + X_k, E_k - X_k
@@ -360,7 +370,7 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
     F cx[3], cy[3];                     // c_k = X_k + i Y_k
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        F X = p[k][0], Y = p[k][1];
+        const F X = p[k][0], Y = p[k][1];
         const F Z = p[k][2], E = p[k][3];
         Ep[k] = E + X;
         Em[k] = E - X;
@@ -368,9 +378,18 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
         const F iA = rcp_t(A[k]);
         g[k].re = (X * X - Y * Y) * iA;
         g[k].im = ((X + X) * Y) * iA;
-        degenerate_fix(A[k], g[k], X, Y, E);
         cx[k] = X;
         cy[k] = Y;
+    }
+#if TP3_DEGENERATE_VOTE
+    if (any_degenerate(A))
+#endif
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) degenerate_fix(A[k], g[k], cx[k], cy[k], p[k][3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
         tk[k] = {A[k] + g[k].re, g[k].im};
         ub[k] = {A[k] - g[k].re, -g[k].im};
     }

@@ -102,6 +102,7 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
     q.g_beta_p = (F)p.g_beta_p;
     q.g_beta_m = (F)p.g_beta_m;
     for (int k = 0; k < 5; ++k) q.sigma_contribs[k] = (F)p.sigma_contribs[k];
+    q.fc = FastCoef TP3_FAST_COEF_INIT;
     return q;
 }
 
@@ -983,7 +984,7 @@ int tp3_fastmath_probe(tp3_ctx* c, int which, uint32_t n, const double* in, doub
     TP3_CUDA(c, cudaMalloc(&d_out, (size_t)n * 8));
     cudaError_t e = cudaMemcpyAsync(d_in, in, (size_t)n * 8, cudaMemcpyHostToDevice, s.stream);
     if (e == cudaSuccess) {
-        fastmath_probe_kernel<<<148, 256, 0, s.stream>>>(which, n, d_in, d_out);
+        fastmath_probe_kernel<<<148, 256, 0, s.stream>>>(which, n, d_in, d_out, FastCoef TP3_FAST_COEF_INIT);
         ++c->launches;
         e = cudaGetLastError();
     }

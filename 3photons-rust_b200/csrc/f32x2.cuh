@@ -80,7 +80,7 @@ __device__ __forceinline__ bool uniform_positive(f2 x) { return x.lo() > 0.0f; }
 __device__ __forceinline__ f2 rcp_t(f2 x) { return f2(rcp_t(x.lo()), rcp_t(x.hi())); }
 __device__ __forceinline__ f2 sqrt_t(f2 x) { return f2(sqrt_t(x.lo()), sqrt_t(x.hi())); }
 __device__ __forceinline__ f2 sqrt_pos_t(f2 x) { return f2(sqrt_pos_t(x.lo()), sqrt_pos_t(x.hi())); }
-__device__ __forceinline__ f2 neg_log_t(f2 x, const FastMathSmem* fm) { return f2(neg_log_t(x.lo(), fm), neg_log_t(x.hi(), fm)); }
+__device__ __forceinline__ f2 neg_log_t(f2 x, const FastMath fm) { return f2(neg_log_t(x.lo(), fm), neg_log_t(x.hi(), fm)); }
 __device__ __forceinline__ void sqrt_rsqrt_t(f2 x, f2* s, f2* rs) {
     float s0, r0, s1, r1;
     sqrt_rsqrt_t(x.lo(), &s0, &r0);
@@ -88,7 +88,7 @@ __device__ __forceinline__ void sqrt_rsqrt_t(f2 x, f2* s, f2* rs) {
     *s = f2(s0, s1);
     *rs = f2(r0, r1);
 }
-__device__ __forceinline__ void sincos_scaled_t(f2 t, const FastMathSmem* fm, f2* s, f2* c) {
+__device__ __forceinline__ void sincos_scaled_t(f2 t, const FastMath fm, f2* s, f2* c) {
     float s0, c0, s1, c1;
     sincos_scaled_t(t.lo(), fm, &s0, &c0);
     sincos_scaled_t(t.hi(), fm, &s1, &c1);

@@ -132,7 +132,7 @@ template <> struct XoLane<float> {
 // The events of one lane, in lock-step with the other lanes of the warp (which walk other streams): 9 numbers,
 // 6 numbers, then one 2-number re-roll per step while any lane still has a point outside the unit disc.
 template <class F, class Gen>
-__device__ __forceinline__ void fe_simulate(Gen& gen, int n_ev, const PhysParams<F>& P, const FastMathSmem* fm, bool warp_reduce,
+__device__ __forceinline__ void fe_simulate(Gen& gen, int n_ev, const PhysParams<F>& P, const FastMath fm, bool warp_reduce,
                                             tp3_acc* out) {
     const int lane = threadIdx.x & 31;
     LaneAcc<F> acc;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kFeThreads) faster_evgen_kernel(const FeArgs a
             gen.load(a.ranf_states + unit * 57);
         }
         __syncwarp();
-        fe_simulate<F, RanfLane<F>>(gen, n_ev, P, &fm, split, out);
+        fe_simulate<F, RanfLane<F>>(gen, n_ev, P, FastMath{&fm, &P.fc}, split, out);
     } else {
         XoLane<F> gen;
         const uint64_t* s = a.xo_states + 4 * (live ? slot : 0);
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kFeThreads) faster_evgen_kernel(const FeArgs a
         gen.g.s1 = (decltype(gen.g.s0))s[1];
         gen.g.s2 = (decltype(gen.g.s0))s[2];
         gen.g.s3 = (decltype(gen.g.s0))s[3];
-        fe_simulate<F, XoLane<F>>(gen, n_ev, P, &fm, split, out);
+        fe_simulate<F, XoLane<F>>(gen, n_ev, P, FastMath{&fm, &P.fc}, split, out);
     }
 }
 

@@ -20,9 +20,23 @@ namespace tp3 {
 #include "fastmath_tables.inc"
 
 #ifndef TP3_COEFF_IMM
-#define TP3_COEFF_IMM 1
+#define TP3_COEFF_IMM 2
 #endif
-#if TP3_COEFF_IMM
+// The polynomial coefficients of -log and sin/cos.  A DFMA whose three sources are three different register pairs issues
+// every 3 cycles on B200 instead of every 2 (the vector register file delivers one 64-bit operand per cycle,
+// profiles/r01_micro_fp64_operands.txt), so a Horner step wants its coefficient in a UNIFORM register:
+//   2  kernel parameters (PhysParams::fc): loaded once with LDCU into uniform registers, like the physics parameters
+//   1  literals: ptxas rebuilds them in vector registers with two IMAD.MOV per coefficient and event
+//   0  __constant__ arrays: loaded into vector registers with LDC.64 once per event
+struct FastCoef {
+    double log1p[5], neg_ln2, rot_sin[3], rot_cos[3];
+};
+#define TP3_FAST_COEF_INIT {{TP3_LOG1P_COEFFS}, TP3_NEG_LN2, {TP3_ROT_SIN_COEFFS}, {TP3_ROT_COS_COEFFS}}
+#if TP3_COEFF_IMM == 2
+#define TP3_COEFF_ARRAYS                                                                                   \
+    const double *const kLog1p = fm.fc->log1p, *const kRotSin = fm.fc->rot_sin, *const kRotCos = fm.fc->rot_cos; \
+    const double kNegLn2 = fm.fc->neg_ln2;
+#elif TP3_COEFF_IMM == 1
 // Polynomial coefficients as literals: ptxas materialises them in uniform registers (UMOV pairs), and a DFMA whose
 // third source is a uniform register reads two register pairs from the vector register file instead of three.
 // (As __constant__ arrays they were loaded into vector registers with LDC.64 once per event and every Horner step
@@ -43,6 +57,11 @@ __constant__ double kRotCos[3] = {TP3_ROT_COS_COEFFS};
 struct FastMathSmem {
     double2 log_tab[128];
     double2 sincos_tab[256];  // {sin, cos}(2 pi k / 256)
+};
+// What the elementary functions need: the CTA's tables and the coefficients (a kernel parameter)
+struct FastMath {
+    const FastMathSmem* sm;
+    const FastCoef* fc;
 };
 
 __device__ __forceinline__ void fastmath_load(FastMathSmem* sm) {
@@ -96,7 +115,8 @@ __device__ __forceinline__ double fast_sqrt(double x) {
 }
 
 // -log(x) for finite normal x > 0
-__device__ __forceinline__ double fast_neg_log(double x, const FastMathSmem* sm) {
+__device__ __forceinline__ double fast_neg_log(double x, const FastMath fm) {
+    const FastMathSmem* const sm = fm.sm;
     TP3_COEFF_ARRAYS
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int k = (hi >> 20) - 1023;
@@ -114,7 +134,8 @@ __device__ __forceinline__ double fast_neg_log(double x, const FastMathSmem* sm)
 // sin(2 pi u), cos(2 pi u) given t = 256 u in [0, 256]: table of 256 directions + rotation by the remainder.
 // 2 pi u = 2 pi (k + d) / 256 with k = rint(t), |d| <= 1/2 (exact), so the rotation angle is at most pi/256 and
 // degree-5 / degree-6 Taylor polynomials are exact to 1e-17; no quadrant logic, 12 FP64 instructions.
-__device__ __forceinline__ void fast_sincos_256(double t, const FastMathSmem* sm, double& s, double& c) {
+__device__ __forceinline__ void fast_sincos_256(double t, const FastMath fm, double& s, double& c) {
+    const FastMathSmem* const sm = fm.sm;
     TP3_COEFF_ARRAYS
     const double kf = rint(t);
     const int k = __double2int_rn(t) & 255;

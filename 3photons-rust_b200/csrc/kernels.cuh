@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
 #pragma unroll
         for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
         F p[3][4];
-        gen_event<F, kSort, LITERAL>(u, P.e_total, &sm.fm, p, tick);  // lanes past the end compute on valid but unused draws
+        gen_event<F, kSort, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);  // lanes past the end compute on valid but unused draws
         tick.template at<4>();
         const bool keep = rng.event_of(it, lane) >= 0 && keep_event<F, kSort, LITERAL>(p, P);
         tick.template at<5>();
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, TP3_X2_MIN_CTAS) simulate_kernel_x2(
     __shared__ WarpSmem<F, kQueue2, 3> smw[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2(*queue)[kQueue2] = smw[warp].queue;
-    const FastMathSmem* const fm = nullptr;  // the f32 elementary functions are SFU instructions, no tables
+    const FastMath fm{nullptr, nullptr};  // the f32 elementary functions are SFU instructions, no tables
 
     WarpRng<F, RNG> rng;
     const uint64_t slot0 = ((uint64_t)blockIdx.x * kWarps + warp) * a.batches_per_warp;
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
         for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
         F p[3][4];
         NoTick no_tick;
-        gen_event<F, SORT, LITERAL>(u, P.e_total, &sm.fm, p, no_tick);
+        gen_event<F, SORT, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);
         const bool k = keep_event<F, SORT, LITERAL>(p, P);
         F m[5] = {0, 0, 0, 0, 0};
         if (k) {
@@ -746,17 +746,18 @@ template <class F> __global__ void __launch_bounds__(kMergeThreads) merge_kernel
 }
 
 // Parity hook for the hand-written FP64 functions (fastmath.cuh): out[i] = f_which(in[i]).
-__global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __restrict__ in, double* __restrict__ out) {
-    __shared__ FastMathSmem fm;
-    fastmath_load(&fm);
+__global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __restrict__ in, double* __restrict__ out, const FastCoef fc) {
+    __shared__ FastMathSmem fms;
+    fastmath_load(&fms);
+    const FastMath fm{&fms, &fc};
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double x = in[i];
         double a = 0, b = 0;
         switch (which) {
-            case 0: a = fast_neg_log(x, &fm); break;
-            case 1: fast_sincos_256(256.0 * x, &fm, a, b); break;
-            case 2: fast_sincos_256(256.0 * x, &fm, b, a); break;
+            case 0: a = fast_neg_log(x, fm); break;
+            case 1: fast_sincos_256(256.0 * x, fm, a, b); break;
+            case 2: fast_sincos_256(256.0 * x, fm, b, a); break;
             case 3: a = fast_sqrt(x); break;
             case 4: a = fast_rcp(x); break;
             case 5: fast_sqrt_rsqrt(x, b, a); break;

@@ -49,15 +49,15 @@ __device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
 // orders of magnitude looser than that, and the f32 literal kernel keeps the IEEE libdevice functions.
 __device__ __forceinline__ double rcp_t(double x) { return fast_rcp(x); }
 __device__ __forceinline__ float rcp_t(float x) { return __fdividef(1.0f, x); }
-__device__ __forceinline__ double neg_log_t(double x, const FastMathSmem* sm) { return fast_neg_log(x, sm); }
-__device__ __forceinline__ float neg_log_t(float x, const FastMathSmem*) { return -__logf(x); }
+__device__ __forceinline__ double neg_log_t(double x, const FastMath sm) { return fast_neg_log(x, sm); }
+__device__ __forceinline__ float neg_log_t(float x, const FastMath) { return -__logf(x); }
 // The azimuth uniform arrives pre-scaled by an exact power of two: 256 u in f64 (table + rotation), 4 u in f32
 // (quarter turns for the SFU path).
 template <class F> struct PhiScale;
 template <> struct PhiScale<double> { static constexpr double value = 256.0; };
 template <> struct PhiScale<float> { static constexpr float value = 4.0f; };
-__device__ __forceinline__ void sincos_scaled_t(double t, const FastMathSmem* fm, double* s, double* c) { fast_sincos_256(t, fm, *s, *c); }
-__device__ __forceinline__ void sincos_scaled_t(float t, const FastMathSmem*, float* s, float* c) {
+__device__ __forceinline__ void sincos_scaled_t(double t, const FastMath fm, double* s, double* c) { fast_sincos_256(t, fm, *s, *c); }
+__device__ __forceinline__ void sincos_scaled_t(float t, const FastMath, float* s, float* c) {
     const float qf = rintf(t);
     const int q = __float2int_rn(t);
     const float x = (t - qf) * 1.57079632679489661923f;  // |x| <= pi/4: the SFU's most accurate range
@@ -80,6 +80,7 @@ template <class F> struct PhysParams {
     F e_total, acut, bcut, e_min, sincut;
     F g_a, g_beta_p, g_beta_m;
     F sigma_contribs[5];
+    FastCoef fc;  // coefficients of the hand-written FP64 functions (fastmath.cuh); unused by the f32 kernels
 };
 
 // ------------------------------------------------------------------ event generation
@@ -142,7 +143,7 @@ struct NoTick {
 
 // One photon of generate_raw (evgen.rs:182-206): u = (cos_theta, phi, r, r') uniforms -> q = (X, Y, Z, E)
 template <class F, bool LITERAL>
-__device__ __forceinline__ void raw_photon(const F* u, const FastMathSmem* fm, F q[4]) {
+__device__ __forceinline__ void raw_photon(const F* u, const FastMath fm, F q[4]) {
     const F c = (F)2 * u[0] - (F)1;
     const F e = u[2] * u[3];
     F sphi, cphi, st, en;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void raw_photon(const F* u, const FastMathSmem* fm, F
 // u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187). In the fast
 // variant the phi slot holds PhiScale<F>::value * u (an exact power-of-two scaling) instead of u.
 template <class F, bool SORT, bool LITERAL, class Tick>
-__device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMathSmem* fm, F p[3][4], Tick& tick) {
+__device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMath fm, F p[3][4], Tick& tick) {
     F q[3][4];
     raw_photon<F, LITERAL>(u, fm, q[0]);
     tick.template at<1>();
@@ -193,7 +194,7 @@ __device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMa
 // because it decides how many random numbers the event consumes).
 template <class F, bool SORT>
 __device__ __forceinline__ void gen_event_faster(const F u9[9], const F xy[3][2], const F r2[3], F e_total,
-                                                 const FastMathSmem* fm, F p[3][4]) {
+                                                 const FastMath fm, F p[3][4]) {
     F q[3][4];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

@@ -91,7 +91,11 @@ namespace {
         }                                                                                                \
     } while (0)
 
+template <class F> struct ScalarOf { using type = F; };
+template <> struct ScalarOf<f2> { using type = float; };
+
 template <class F> PhysParams<F> phys_params(const tp3_params& p) {
+    using S = typename ScalarOf<F>::type;  // host arithmetic in the run's Float (this file is built with -ffp-contract=off)
     PhysParams<F> q;
     q.e_total = (F)p.e_total;
     q.acut = (F)p.acut;
@@ -102,6 +106,15 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
     q.g_beta_p = (F)p.g_beta_p;
     q.g_beta_m = (F)p.g_beta_m;
     for (int k = 0; k < 5; ++k) q.sigma_contribs[k] = (F)p.sigma_contribs[k];
+    {
+        const S e = (S)p.e_total, ga = (S)p.g_a, gp = (S)p.g_beta_p, gm = (S)p.g_beta_m, e2 = e * e;
+        q.k_m0 = (F)((ga * ga) * (S)8);
+        q.k_m1 = (F)((gp * gp) * (((S)8 * e2) * e2));
+        q.k_m2 = (F)((gm * gm) * (((S)4 * e2) * e2));
+        q.k_mix = (F)((-(ga * gp)) * e2);
+        q.omb = (F)((S)1 - (S)p.bcut);
+        q.he = (F)((S)0.5 * e);
+    }
     q.fc = FastCoef TP3_FAST_COEF_INIT;
     return q;
 }

@@ -30,8 +30,10 @@ namespace tp3 {
 //   0  __constant__ arrays: loaded into vector registers with LDC.64 once per event
 struct FastCoef {
     double log1p[5], neg_ln2, rot_sin[3], rot_cos[3];
+    double u_scale, u_bias, phi_scale, phi_bias;  // RANF word -> uniform (u32_times): 1e-9, -(2^52 1e-9), 256e-9, -(2^52 256e-9)
 };
-#define TP3_FAST_COEF_INIT {{TP3_LOG1P_COEFFS}, TP3_NEG_LN2, {TP3_ROT_SIN_COEFFS}, {TP3_ROT_COS_COEFFS}}
+#define TP3_FAST_COEF_INIT {{TP3_LOG1P_COEFFS}, TP3_NEG_LN2, {TP3_ROT_SIN_COEFFS}, {TP3_ROT_COS_COEFFS}, \
+                            1e-9, -4503599627370496.0 * 1e-9, 256e-9, -4503599627370496.0 * 256e-9}
 #if TP3_COEFF_IMM == 2
 #define TP3_COEFF_ARRAYS                                                                                   \
     const double *const kLog1p = fm.fc->log1p, *const kRotSin = fm.fc->rot_sin, *const kRotCos = fm.fc->rot_cos; \
@@ -154,6 +156,12 @@ __device__ __forceinline__ void fast_sincos_256(double t, const FastMath fm, dou
 __device__ __forceinline__ double u32_times(uint32_t n, double scale) {
     const double d = __hiloint2double(0x43300000, (int)n);
     return fma(d, scale, -4503599627370496.0 * scale);
+}
+
+// The same with scale and -(2^52 * scale) supplied by the caller (kernel parameters: uniform registers, loaded once,
+// instead of four immediates rebuilt for every event).
+__device__ __forceinline__ double u32_times(uint32_t n, double scale, double neg_bias) {
+    return fma(__hiloint2double(0x43300000, (int)n), scale, neg_bias);
 }
 
 }  // namespace tp3

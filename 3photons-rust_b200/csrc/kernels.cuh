@@ -146,8 +146,8 @@ template <class F> struct WarpRng<F, RNG_RANF> {
         return true;
     }
     // ranf.rs:99: (n as Float) * 1e-9; `phi` asks for PhiScale<F>::value * u instead (an exact scaling)
-    __device__ static F uniform(uint32_t w, bool phi) {
-        if (sizeof(F) == 8) return (F)u32_times(w, phi ? 256e-9 : 1e-9);
+    __device__ static F uniform(uint32_t w, bool phi, const FastCoef& fc) {
+        if (sizeof(F) == 8) return (F)(phi ? u32_times(w, fc.phi_scale, fc.phi_bias) : u32_times(w, fc.u_scale, fc.u_bias));
         const float u = (float)(int)w * 1e-9f;
         return (F)(phi ? 4.0f * u : u);
     }
@@ -176,10 +176,10 @@ template <class F, class Lane> struct XoshiroWarpRng {
     template <int K> __device__ __forceinline__ void tick(int) {}
 };
 template <> struct WarpRng<double, RNG_XOSHIRO> : XoshiroWarpRng<double, Xoshiro256Lane> {
-    __device__ static double uniform(uint64_t w, bool phi) { return (phi ? 256.0 : 1.0) * to_uniform_xo(w); }
+    __device__ static double uniform(uint64_t w, bool phi, const FastCoef&) { return (phi ? 256.0 : 1.0) * to_uniform_xo(w); }
 };
 template <> struct WarpRng<float, RNG_XOSHIRO> : XoshiroWarpRng<float, Xoshiro128Lane> {
-    __device__ static float uniform(uint32_t w, bool phi) { return (phi ? 4.0f : 1.0f) * to_uniform_xo(w); }
+    __device__ static float uniform(uint32_t w, bool phi, const FastCoef&) { return (phi ? 4.0f : 1.0f) * to_uniform_xo(w); }
 };
 
 template <class F> struct LaneAcc {
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
         RngTick<F, RNG> tick{rng, lane, more};
         F u[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
+        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1, P.fc);
         F p[3][4];
         gen_event<F, kSort, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);  // lanes past the end compute on valid but unused draws
         tick.template at<4>();
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, TP3_X2_MIN_CTAS) simulate_kernel_x2(
             RngTick<F, RNG> tick{rng, lane, more};
             f2 u[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) u[j] = f2(WarpRng<F, RNG>::uniform(w0[j], (j & 3) == 1), WarpRng<F, RNG>::uniform(w1[j], (j & 3) == 1));
+            for (int j = 0; j < 12; ++j) u[j] = f2(WarpRng<F, RNG>::uniform(w0[j], (j & 3) == 1, P.fc), WarpRng<F, RNG>::uniform(w1[j], (j & 3) == 1, P.fc));
             f2 p[3][4];
             gen_event<f2, false, false>(u, P.e_total, fm, p, tick);
             const m2 ok = keep_event<f2, false, false>(p, P);
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
             for (int j = 0; j < 12; ++j) d.words[(size_t)e * 12 + j] = (uint64_t)w[j];
         if (!d.momenta) continue;
         F u[12];
-        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1);
+        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1, P.fc);
         F p[3][4];
         NoTick no_tick;
         gen_event<F, SORT, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);

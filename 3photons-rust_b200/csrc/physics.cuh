@@ -80,6 +80,13 @@ template <class F> struct PhysParams {
     F e_total, acut, bcut, e_min, sincut;
     F g_a, g_beta_p, g_beta_m;
     F sigma_contribs[5];
+    // Products of the parameters above that me_fast / keep_event would otherwise recompute for every event in vector
+    // FP64 (the compiler does not hoist all of them); same operations, same order, done once on the host in F:
+    F k_m0;    // (g_a g_a) 8
+    F k_m1;    // (g_beta_p g_beta_p) ((8 e^2) e^2)
+    F k_m2;    // (g_beta_m g_beta_m) ((4 e^2) e^2)
+    F k_mix;   // (-(g_a g_beta_p)) e^2
+    F omb, he; // 1 - bcut, e / 2
     FastCoef fc;  // coefficients of the hand-written FP64 functions (fastmath.cuh); unused by the f32 kernels
 };
 
@@ -235,7 +242,7 @@ __device__ __forceinline__ typename MaskOf<F>::type keep_event(const F p[3][4], 
         // p_i.p_j (3-vectors) = E_i E_j - (p_i + p_j)^2 / 2 = E_i E_j - e (e - 2 E_k) / 2 by momentum conservation
         // (the transform of evgen.rs:94-106 conserves the total 4-momentum (0,0,0,e) to rounding error), so
         // "cos > bcut" reads (1 - bcut) E_i E_j > e (e/2 - E_k): 3 FP64 instructions per pair instead of 6.
-        const F omb = (F)1 - P.bcut, he = (F)0.5 * P.e_total;
+        const F omb = P.omb, he = P.he;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int i = (k == 0) ? 1 : 0, j = (k == 2) ? 1 : 2;
@@ -418,11 +425,10 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
     }
     const F Dn = (T[0] * T[1]) * T[2];  // D = e^6 * Dn
     const F iDn = rcp_t(Dn);
-    const F e2 = e * e;
     // m0 = g_a^2 * 8 e^2 * e^4 sum(T S2) / (e^6 Dn)
-    m[0] = (P.g_a * P.g_a) * (F)8 * ((T[0] * S2[0] + T[1] * S2[1] + T[2] * S2[2]) * iDn);
+    m[0] = P.k_m0 * ((T[0] * S2[0] + T[1] * S2[1] + T[2] * S2[2]) * iDn);
     // m1 = g_b+^2 * 8 e^2 * e^2 sum(R^2 S2)
-    m[1] = (P.g_beta_p * P.g_beta_p) * ((F)8 * e2 * e2) * (R[0] * R[0] * S2[0] + R[1] * R[1] * S2[1] + R[2] * R[2] * S2[2]);
+    m[1] = P.k_m1 * (R[0] * R[0] * S2[0] + R[1] * R[1] * S2[1] + R[2] * R[2] * S2[2]);
     // m2: s_0k^2 = (e/2)(t_k + 2 c_k), s_1k^2 = (e/2)(t_k - 2 c_k) with t_k = A_k + g_k, and
     // |Sa + Sb|^2 + |Sa - Sb|^2 = 2 (|Sa|^2 + |Sb|^2) for Sa = sum t_k s2_k, Sb = sum 2 c_k s2_k
     Cplx<F> Sa = cmul(tk[0], s2[0]), Sb = cmul(Cplx<F>{cx[0], cy[0]}, s2[0]);
@@ -431,7 +437,7 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
         Sa = cmac(Sa, tk[k], s2[k]);
         Sb = cmac(Sb, Cplx<F>{cx[k], cy[k]}, s2[k]);
     }
-    m[2] = (P.g_beta_m * P.g_beta_m) * ((F)4 * e2 * e2) * (cnorm(Sa) + (F)4 * cnorm(Sb));
+    m[2] = P.k_m2 * (cnorm(Sa) + (F)4 * cnorm(Sb));
     // mixed: u_k = -(e/2) ub_k, U = -(e/2)^3 Ub, W_k = s2_k u_k conj(U) / D = s2_k ub_k conj(Ub) (e/2)^4 / (e^6 Dn)
     const Cplx<F> Ub = cmul(cmul(ub[0], ub[1]), ub[2]);
     const Cplx<F> Uc = {Ub.re, -Ub.im};
@@ -443,7 +449,7 @@ template <class F> __device__ __forceinline__ void me_fast(const F p[3][4], cons
         im += D2[k] * w.im;
     }
     // P_k^2 = e^2 (E+X)^2: total factor -16 e^2 g_a g_b+ * e^2 * (e/2)^4 / e^6 = -g_a g_b+ e^2
-    const F cm = -(P.g_a * P.g_beta_p) * e2 * iDn;
+    const F cm = P.k_mix * iDn;
     m[3] = cm * re;
     m[4] = cm * im;
 }

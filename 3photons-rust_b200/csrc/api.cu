@@ -91,6 +91,9 @@ namespace {
         }                                                                                                \
     } while (0)
 
+// bench.py counts these bytes as the host->device payload of a launch (e2e.h2d_bytes_per_step)
+static_assert(sizeof(SimArgs) == 312 && sizeof(PhysParams<double>) == 280, "update the kernel-argument byte count in bench.py");
+
 template <class F> struct ScalarOf { using type = F; };
 template <> struct ScalarOf<f2> { using type = float; };
 

@@ -155,8 +155,8 @@ template <class F, int RNG> DumpFn pick_dump2(bool sort, bool literal) {
 }
 // f32 fast kernel, two events per lane in packed FP32 arithmetic (f32x2.cuh)
 template <int RNG> void launch_sim_x2(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
-    const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
-    simulate_kernel_x2<RNG><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, 0, st>>>(a, phys_params<f2>(p));
+    const uint64_t per_cta = (uint64_t)x2_warps(RNG) * a.batches_per_warp;
+    simulate_kernel_x2<RNG><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), 32 * x2_warps(RNG), 0, st>>>(a, phys_params<f2>(p));
 }
 template <class F, int RNG> SimFn pick_sim_hist2(bool sort) { return sort ? launch_sim_hist<F, RNG, true> : launch_sim_hist<F, RNG, false>; }
 SimFn pick_sim(const tp3_params& p, bool hist = false) {

@@ -22,7 +22,10 @@
 
 namespace tp3 {
 
-constexpr int kFeThreads = 128;
+#ifndef TP3_FE_THREADS
+#define TP3_FE_THREADS 128
+#endif
+constexpr int kFeThreads = TP3_FE_THREADS;
 
 struct FeArgs {
     uint64_t first_batch;
@@ -201,7 +204,7 @@ __device__ __forceinline__ void fe_simulate(Gen& gen, int n_ev, const PhysParams
 }
 
 template <class F, int RNG>
-__global__ void __launch_bounds__(kFeThreads) faster_evgen_kernel(const FeArgs a, const PhysParams<F> P) {
+__global__ void __launch_bounds__(kFeThreads, 512 / kFeThreads) faster_evgen_kernel(const FeArgs a, const PhysParams<F> P) {
     __shared__ FastMathSmem fm;
     __shared__ uint32_t ranf_state[RNG == RNG_RANF ? kFeRow * kFeThreads : 1];
     fastmath_load(&fm);

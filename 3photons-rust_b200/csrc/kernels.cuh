@@ -27,9 +27,9 @@ namespace tp3 {
 #ifndef TP3_TICK_AT
 #define TP3_TICK_AT 1
 #endif
-#ifndef TP3_X2_MIN_CTAS
-#define TP3_X2_MIN_CTAS 5   // f32 two-events-per-lane kernel: 96 registers (a few spills) beat 128 registers at 4 CTAs per SM
-#endif
+// f32 two-events-per-lane kernel: 20 warps per SM (96 registers with a few spills beat 128 registers at 16 warps), as
+// one-warp CTAs with RANF (+2.7 %) and four-warp CTAs with xoshiro (one-warp CTAs: -0.5 %); profiles/r01_ab_variants.txt
+__host__ __device__ constexpr int x2_warps(int rng) { return rng == 0 ? 1 : 4; }
 #ifndef TP3_WARPS
 #define TP3_WARPS 4         // warps (batches) per CTA of the kernels that share per-CTA state: histogram epilogue, literal, f32 x2, dump
 #endif
@@ -475,11 +475,12 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
 constexpr int kQueue2 = 128;  // < 64 pending + <= 64 new survivors
 
 template <int RNG>
-__global__ void __launch_bounds__(kThreads, TP3_X2_MIN_CTAS) simulate_kernel_x2(const SimArgs a, const PhysParams<f2> P) {
+__global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simulate_kernel_x2(const SimArgs a, const PhysParams<f2> P) {
+    constexpr int kWarps = x2_warps(RNG);  // this kernel's CTA shape
     using F = float;
     using Word = typename RawWord<F, RNG>::type;
     __shared__ WarpSmem<F, kQueue2, 3> smw[kWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = kWarps == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     float2(*queue)[kQueue2] = smw[warp].queue;
     const FastMath fm{nullptr, nullptr};  // the f32 elementary functions are SFU instructions, no tables
 

@@ -160,8 +160,17 @@ __device__ __forceinline__ double u32_times(uint32_t n, double scale) {
 
 // The same with scale and -(2^52 * scale) supplied by the caller (kernel parameters: uniform registers, loaded once,
 // instead of four immediates rebuilt for every event).
+#ifndef TP3_U32_I2F
+#define TP3_U32_I2F 1
+#endif
 __device__ __forceinline__ double u32_times(uint32_t n, double scale, double neg_bias) {
+#if TP3_U32_I2F
+    // I2F.F64 (XU pipe: one 32-bit register read) + a two-operand DMUL, literally ranf.rs:99.  The single-FMA form below
+    // needs two moves to build the register pair and reads three register pairs (3 cycles of the register file).
+    return (double)(int)n * scale;
+#else
     return fma(__hiloint2double(0x43300000, (int)n), scale, neg_bias);
+#endif
 }
 
 }  // namespace tp3

@@ -3,7 +3,7 @@
 // Why not CUDA's libdevice versions: ncu on the first kernel (profiles/r01_v1_fast_f64_ranf.txt)
 // showed only 31 % of the issue slots going to the FP64 pipe; log()/sincospi()/sqrt() spend more
 // instructions on UMOV pairs (64-bit immediates), integer fix-ups and slow-path branches than on
-// DFMAs.  Here every coefficient lives in constant memory (DFMA reads c[bank][off] directly), there
+// DFMAs.  Here the coefficients are kernel parameters (uniform registers, see TP3_COEFF_IMM below), there
 // are no special-case branches (the operands of this kernel are known to be finite and normal), and
 // the argument reductions use what we know about the inputs:
 //   neg_log      x in (0, 2): 128-entry table of (1/c, -log c) in shared memory + degree-6 log1p
@@ -153,9 +153,16 @@ __device__ __forceinline__ void fast_sincos_256(double t, const FastMath fm, dou
 // (double)n * scale for 0 <= n < 2^32 with ONE FMA and no I2F: the word n dropped into the low half
 // of 2^52 is exactly 2^52 + n, and fma(2^52 + n, scale, -(2^52 * scale)) rounds the exact product
 // n * scale once — bit-identical to the conversion followed by a multiply (2^52 * scale is exact).
+#ifndef TP3_U32_I2F_LITERAL
+#define TP3_U32_I2F_LITERAL 0
+#endif
 __device__ __forceinline__ double u32_times(uint32_t n, double scale) {
+#if TP3_U32_I2F_LITERAL
+    return (double)(int)n * scale;
+#else
     const double d = __hiloint2double(0x43300000, (int)n);
     return fma(d, scale, -4503599627370496.0 * scale);
+#endif
 }
 
 // The same with scale and -(2^52 * scale) supplied by the caller (kernel parameters: uniform registers, loaded once,

@@ -104,16 +104,24 @@ __device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs)
 }
 // sqrt(x), x >= 0; x is biased by 1e-300 so that 0 gives 1e-150 (0 for every use in this kernel) instead of
 // 0 * inf; the nonzero arguments here are >= 4e-9 and unchanged by the bias
+#ifndef TP3_SQRT_RESIDUAL
+#define TP3_SQRT_RESIDUAL 1
+#endif
 __device__ __forceinline__ double fast_sqrt(double x) {
     x += 1e-300;
     const double y = mufu_rsqrt(x);
     double g = x * y;
     const double h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);  // ~40 good bits
+#if TP3_SQRT_RESIDUAL
+    // second step on the residual x - g^2 with the SEED-accurate h = 1/(2 sqrt x): the correction is 2^-40 of the
+    // result, so 20 good bits of h are enough, and the refinement of h (one DFMA) is not needed
+    return fma(fma(-g, g, x), h, g);
+#else
     const double h1 = fma(h, r, h);
-    r = fma(-g, h1, 0.5);
-    return fma(g, r, g);
+    return fma(g, fma(-g, h1, 0.5), g);
+#endif
 }
 
 // -log(x) for finite normal x > 0

@@ -93,7 +93,11 @@ template <class F> struct PhysParams {
 // ------------------------------------------------------------------ event generation
 // Conformal transform of RAMBO to the total energy + optional sort (evgen.rs:94-118):
 // q[k] = raw (X, Y, Z, E) of photon k  ->  p[k] = (X, Y, Z, E), optionally sorted by decreasing E.
-template <class F, bool SORT, bool LITERAL>
+// CONS3: the third photon is what 4-momentum conservation leaves, p_2 = (0,0,0,e_total) - p_0 - p_1, instead of the
+// transform of q_2 (3 additions instead of 9 multiply-adds for the E and X the cuts need).  The transform conserves the
+// total momentum to rounding error, so the two differ by ~1e-16 e_total; the pair cuts, |s_ij|^2 and the survivor queue of
+// the fused kernel already rely on the same identity.
+template <class F, bool SORT, bool LITERAL, bool CONS3 = false>
 __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, F p[3][4]) {
     F r[4];
 #pragma unroll
@@ -112,7 +116,7 @@ __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, 
     }
     const F am = alpha * m;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < (CONS3 ? 2 : 3); ++k) {
         const F rq = (q[k][0] * r[0] + q[k][1] * r[1]) + q[k][2] * r[2];
         p[k][3] = alpha * (r[3] * q[k][3] - rq);
         if constexpr (LITERAL) {
@@ -124,6 +128,11 @@ __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, 
 #pragma unroll
             for (int c = 0; c < 3; ++c) p[k][c] = am * q[k][c] + ab * r[c];
         }
+    }
+    if constexpr (CONS3) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[2][c] = -(p[0][c] + p[1][c]);
+        p[2][3] = (e_total - p[0][3]) - p[1][3];
     }
     if constexpr (SORT) {
 #pragma unroll
@@ -141,6 +150,13 @@ __device__ __forceinline__ void conformal_transform(const F q[3][4], F e_total, 
     }
 }
 
+
+#ifndef TP3_CONS3
+#define TP3_CONS3 1
+#endif
+// Third photon from momentum conservation: the f64 fast paths only (in f32 the rounding error of the sum is 1e-7 e_total)
+template <class F, bool LITERAL> struct Cons3 { static constexpr bool value = false; };
+template <> struct Cons3<double, false> { static constexpr bool value = TP3_CONS3 != 0; };
 
 // Hook called between the stages of an event so that independent work of the same warp (the next
 // iteration's random numbers) can be interleaved with the FP64 chains; NoTick does nothing.
@@ -193,7 +209,7 @@ __device__ __forceinline__ void gen_event(const F u[12], F e_total, const FastMa
     tick.template at<2>();
     raw_photon<F, LITERAL>(u + 8, fm, q[2]);
     tick.template at<3>();
-    conformal_transform<F, SORT, LITERAL>(q, e_total, p);
+    conformal_transform<F, SORT, LITERAL, Cons3<F, LITERAL>::value>(q, e_total, p);
 }
 
 // `faster-evgen` raw generation (evgen.rs:143-173): cos_theta and exp(-E) from 9 uniforms, the azimuth
@@ -216,7 +232,7 @@ __device__ __forceinline__ void gen_event_faster(const F u9[9], const F xy[3][2]
         q[k][2] = en * c;
         q[k][3] = en;
     }
-    conformal_transform<F, SORT, false>(q, e_total, p);
+    conformal_transform<F, SORT, false, Cons3<F, false>::value>(q, e_total, p);
 }
 
 // ------------------------------------------------------------------------------ cuts

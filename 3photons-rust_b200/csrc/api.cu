@@ -92,7 +92,7 @@ namespace {
     } while (0)
 
 // bench.py counts these bytes as the host->device payload of a launch (e2e.h2d_bytes_per_step)
-static_assert(sizeof(SimArgs) == 312 && sizeof(PhysParams<double>) == 280, "update the kernel-argument byte count in bench.py");
+static_assert(sizeof(SimArgs) == 312 && sizeof(PhysParams<double>) == 296, "update the kernel-argument byte count in bench.py");
 
 template <class F> struct ScalarOf { using type = F; };
 template <> struct ScalarOf<f2> { using type = float; };
@@ -115,7 +115,7 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
         q.k_m1 = (F)((gp * gp) * (((S)8 * e2) * e2));
         q.k_m2 = (F)((gm * gm) * (((S)4 * e2) * e2));
         q.k_mix = (F)((-(ga * gp)) * e2);
-        q.omb = (F)((S)1 - (S)p.bcut);
+        q.omb_e = (F)(((S)1 - (S)p.bcut) / e);
         q.he = (F)((S)0.5 * e);
     }
     q.fc = FastCoef TP3_FAST_COEF_INIT;

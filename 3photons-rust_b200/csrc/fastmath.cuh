@@ -31,9 +31,10 @@ namespace tp3 {
 struct FastCoef {
     double log1p[5], neg_ln2, rot_sin[3], rot_cos[3];
     double u_scale, u_bias, phi_scale, phi_bias;  // RANF word -> uniform (u32_times): 1e-9, -(2^52 1e-9), 256e-9, -(2^52 256e-9)
+    double u_scale2, u_scale_sq;                  // 2e-9 (cos_theta = 2u - 1 in one FMA), 1e-18 (r r' from the integers)
 };
 #define TP3_FAST_COEF_INIT {{TP3_LOG1P_COEFFS}, TP3_NEG_LN2, {TP3_ROT_SIN_COEFFS}, {TP3_ROT_COS_COEFFS}, \
-                            1e-9, -4503599627370496.0 * 1e-9, 256e-9, -4503599627370496.0 * 256e-9}
+                            1e-9, -4503599627370496.0 * 1e-9, 256e-9, -4503599627370496.0 * 256e-9, 2e-9, 1e-18}
 #if TP3_COEFF_IMM == 2
 #define TP3_COEFF_ARRAYS                                                                                   \
     const double *const kLog1p = fm.fc->log1p, *const kRotSin = fm.fc->rot_sin, *const kRotCos = fm.fc->rot_cos; \

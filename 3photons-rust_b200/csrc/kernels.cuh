@@ -39,6 +39,9 @@ __host__ __device__ constexpr int x2_warps(int rng) { return rng == 0 ? 1 : 4; }
 #ifndef TP3_FAST_MIN_CTAS
 #define TP3_FAST_MIN_CTAS (16 / TP3_FAST_WARPS)   // 16 warps per SM at 128 registers
 #endif
+#ifndef TP3_GEN_FROM_INTS
+#define TP3_GEN_FROM_INTS 1 // f64 RANF fast kernel: cos_theta, phi and r r' straight from the stream integers (6 FP64 fewer per event)
+#endif
 #ifndef TP3_ACC_SMEM
 #define TP3_ACC_SMEM 0      // 1: the lanes' 12 partial sums live in shared memory (frees 24 registers in the event loop; slower)
 #endif
@@ -380,11 +383,18 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
 #endif
         if (more) rng.begin_next(lane);
         RngTick<F, RNG> tick{rng, lane, more};
-        F u[12];
+        F p[3][4];  // lanes past the end compute on valid but unused draws
+        if constexpr (TP3_GEN_FROM_INTS && sizeof(F) == 8 && RNG == RNG_RANF && !LITERAL) {
+            double d[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1, P.fc);
-        F p[3][4];
-        gen_event<F, kSort, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);  // lanes past the end compute on valid but unused draws
+            for (int j = 0; j < 12; ++j) d[j] = (double)(int)w[j];
+            gen_event_ints<kSort>(d, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);
+        } else {
+            F u[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1, P.fc);
+            gen_event<F, kSort, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);
+        }
         tick.template at<4>();
         const bool keep = rng.event_of(it, lane) >= 0 && keep_event<F, kSort, LITERAL>(p, P);
         tick.template at<5>();
@@ -650,11 +660,17 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
         if (d.words)
             for (int j = 0; j < 12; ++j) d.words[(size_t)e * 12 + j] = (uint64_t)w[j];
         if (!d.momenta) continue;
-        F u[12];
-        for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1, P.fc);
         F p[3][4];
         NoTick no_tick;
-        gen_event<F, SORT, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);
+        if constexpr (TP3_GEN_FROM_INTS && sizeof(F) == 8 && RNG == RNG_RANF && !LITERAL) {  // as in simulate_kernel
+            double d[12];
+            for (int j = 0; j < 12; ++j) d[j] = (double)(int)w[j];
+            gen_event_ints<SORT>(d, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);
+        } else {
+            F u[12];
+            for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1, P.fc);
+            gen_event<F, SORT, LITERAL>(u, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);
+        }
         const bool k = keep_event<F, SORT, LITERAL>(p, P);
         F m[5] = {0, 0, 0, 0, 0};
         if (k) {

@@ -86,7 +86,7 @@ template <class F> struct PhysParams {
     F k_m1;    // (g_beta_p g_beta_p) ((8 e^2) e^2)
     F k_m2;    // (g_beta_m g_beta_m) ((4 e^2) e^2)
     F k_mix;   // (-(g_a g_beta_p)) e^2
-    F omb, he; // 1 - bcut, e / 2
+    F omb_e, he; // (1 - bcut) / e, e / 2
     FastCoef fc;  // coefficients of the hand-written FP64 functions (fastmath.cuh); unused by the f32 kernels
 };
 
@@ -192,10 +192,44 @@ __device__ __forceinline__ void raw_photon(const F* u, const FastMath fm, F q[4]
         en = neg_log_t(e + Num<F>::MIN_POSITIVE, fm);
 #endif
     }
-    q[0] = en * (st * sphi);
-    q[1] = en * (st * cphi);
+    if constexpr (LITERAL) {
+        q[0] = en * (st * sphi);
+        q[1] = en * (st * cphi);
+    } else {  // one multiplication less
+        const F es = en * st;
+        q[0] = es * sphi;
+        q[1] = es * cphi;
+    }
     q[2] = en * c;
     q[3] = en;
+}
+
+// The same for the f64 RANF fast path, straight from the stream integers d_j = (double)n_j (ranf.rs:99 would first
+// scale each to u_j = 1e-9 d_j): cos_theta = 2e-9 d_0 - 1 in one FMA, 256 phi-turns = 256e-9 d_1, and
+// r r' = 1e-18 (d_2 d_3) with one multiplication less.  Each differs from the reference's expression by one rounding.
+__device__ __forceinline__ void raw_photon_ints(const double* d, const FastMath fm, double q[4]) {
+    const double c = fma(d[0], fm.fc->u_scale2, -1.0);
+    const double e = fma(d[2] * d[3], fm.fc->u_scale_sq, Num<double>::MIN_POSITIVE);
+    double sphi, cphi;
+    fast_sincos_256(d[1] * fm.fc->phi_scale, fm, sphi, cphi);
+    const double st = fast_sqrt(fma(-c, c, 1.0));
+    const double en = fast_neg_log(e, fm);
+    const double es = en * st;
+    q[0] = es * sphi;
+    q[1] = es * cphi;
+    q[2] = en * c;
+    q[3] = en;
+}
+template <bool SORT, class Tick>
+__device__ __forceinline__ void gen_event_ints(const double d[12], double e_total, const FastMath fm, double p[3][4], Tick& tick) {
+    double q[3][4];
+    raw_photon_ints(d, fm, q[0]);
+    tick.template at<1>();
+    raw_photon_ints(d + 4, fm, q[1]);
+    tick.template at<2>();
+    raw_photon_ints(d + 8, fm, q[2]);
+    tick.template at<3>();
+    conformal_transform<double, SORT, false, Cons3<double, false>::value>(q, e_total, p);
 }
 
 // u[12]: uniforms in the reference's draw order (per photon: cos_theta, phi, r, r'; evgen.rs:182-187). In the fast
@@ -258,11 +292,11 @@ __device__ __forceinline__ typename MaskOf<F>::type keep_event(const F p[3][4], 
         // p_i.p_j (3-vectors) = E_i E_j - (p_i + p_j)^2 / 2 = E_i E_j - e (e - 2 E_k) / 2 by momentum conservation
         // (the transform of evgen.rs:94-106 conserves the total 4-momentum (0,0,0,e) to rounding error), so
         // "cos > bcut" reads (1 - bcut) E_i E_j > e (e/2 - E_k): 3 FP64 instructions per pair instead of 6.
-        const F omb = P.omb, he = P.he;
+        // divided by e: (1 - bcut)/e E_i E_j + E_k > e/2 — a multiply, one FMA and a compare per pair
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int i = (k == 0) ? 1 : 0, j = (k == 2) ? 1 : 2;
-            ok = ok & !(omb * (p[i][3] * p[j][3]) > P.e_total * (he - p[k][3]));
+            ok = ok & !(fma_t(p[i][3] * p[j][3], P.omb_e, p[k][3]) > P.he);
         }
     }
     if (uniform_positive(P.sincut)) {  // |n_x| < sincut |n|  (uniform branch; the default sincut is 0)

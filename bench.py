@@ -270,10 +270,10 @@ def main():
                        "features": args.features or "default (f64, RANF, photon sorting)", "kernel": args.kernel,
                        "l2": "not applicable: no input tensors; the kernel reads a 281 KB jump table and writes 104 B per batch"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": world * 8 * (312 + 280),
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": world * 8 * (312 + 296),
                     "d2h_bytes_per_step": world * acc_bytes,
                     "note": "tp3_simulate_merged into a host tp3_acc + finalize(); the only host->device payload is the kernel "
-                            "argument block (SimArgs 312 B + PhysParams 280 B, sizes pinned by a static_assert in api.cu) of the 8 chunk launches per GPU"},
+                            "argument block (SimArgs 312 B + PhysParams 296 B, sizes pinned by a static_assert in api.cu) of the 8 chunk launches per GPU"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64" if not f32 else "fp32", "achieved": achieved, "peak": peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": ncu_traffic,

@@ -260,7 +260,7 @@ def main():
         achieved = value / world * FLOP_PER_EVENT / 1e12  # per GPU, to compare with a per-GPU peak
         f32 = "f32" in args.features
         # bytes per launch, from the committed ncu capture of exactly this launch shape (default features, 1e6 batches)
-        ncu_traffic = 58154240 if (not args.features and args.kernel == "fast" and nb // world == 1000000) else None
+        ncu_traffic = 58799360 if (not args.features and args.kernel == "fast" and nb // world == 1000000) else None
         line = {
             "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -279,11 +279,11 @@ def main():
                          "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": ncu_traffic,
                          "traffic_note": None if ncu_traffic is None else
                                          "DRAM bytes of one launch of the default f64 kernel over 1e6 batches, ncu --set full "
-                                         "(profiles/r01_bench_kernel_1e10_events.txt): 0.29 MB read (the jump table) + 57.9 MB "
+                                         "(profiles/r01_bench_kernel_1e10_events.txt): 0.27 MB read (the jump table) + 58.5 MB "
                                          "written of the 104 MB of per-batch accumulators (the rest is still in L2 when the "
                                          "kernel ends); the bound is the FP64 pipe, not HBM",
                          "pipe_note": None if f32 else
-                                      "ncu on this launch: FP64 pipe 72.6 % active; the kernel sits at 98.6 % of the bound set by the "
+                                      "ncu on this launch: FP64 pipe 69.3 % active; the kernel sits at 97.6 % of the bound set by the "
                                       "vector register file (one 64-bit operand per cycle: a three-register DFMA issues every 3 "
                                       "cycles, profiles/r01_final2_fast_f64_ranf.txt, DESIGN.md section 4d)",
                          "peak_source": "measured live: tp3_peak_probe (8 independent FMA chains per thread, all SMs)",

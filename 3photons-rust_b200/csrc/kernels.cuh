@@ -1,12 +1,13 @@
 // The fused per-batch kernel (replaces the closure of src/main.rs:103-128 and everything it
 // calls) plus the small parity/seeding kernels.
 //
-// Work decomposition: ONE WARP = ONE BATCH of <= 10 000 events (src/scheduling/mod.rs:21), four
-// batches per 128-thread CTA.  A warp regenerates its batch's random stream from one jump-ahead
-// (rng.cuh), runs generation + cuts on 32 events per iteration, compacts the survivors (70.8 % at
-// the default cuts) into a shared-memory queue and evaluates the matrix elements only on full
-// warps, then folds its 13 sums with shuffles and writes one 104-byte accumulator.  There is no
-// CTA-level barrier after the prologue, so warps never wait for each other.
+// Work decomposition: ONE WARP = ONE BATCH of <= 10 000 events (src/scheduling/mod.rs:21) = ONE CTA for the plain fast
+// kernel (16 one-warp CTAs per SM; the histogram / literal / f32-xoshiro kernels keep four warps per CTA).  A warp
+// regenerates its batch's random stream from one jump-ahead (rng.cuh), runs generation + cuts on 32 events per iteration,
+// compacts the survivors (70.8 % at the default cuts) into a shared-memory queue and evaluates the matrix elements only
+// on full warps, then folds its 13 sums with shuffles and writes one 104-byte accumulator.  There is no CTA-level
+// barrier after the prologue, so warps never wait for each other.  What bounds it (the vector register file) and what
+// follows from that is in DESIGN.md section 4d.
 #pragma once
 
 #include <cstdint>

@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "faster_evgen.cuh"
 #include "fe_scan.cuh"
+#include "fe_scan_xo.cuh"
 
 using namespace tp3;
 
@@ -50,6 +51,11 @@ struct DeviceSlot {
     uint32_t* d_fe_seg_count = nullptr;
     uint64_t* d_fe_seg_events = nullptr;
     size_t fe_seg_cap = 0;
+    // faster-evgen + xoshiro scan workspace (fe_scan_xo.cuh)
+    uint32_t* d_xo_scan = nullptr;  // exit A | exit B | count | mismatch flag
+    size_t xo_scan_cap = 0;
+    void* d_xo_bnd = nullptr;
+    size_t xo_bnd_cap = 0;
     // last launch
     uint64_t last_first = 0, last_n = 0;
 };
@@ -193,8 +199,11 @@ void build_xoshiro_tables(tp3_ctx* c) {
         for (int i = 0; i < 4; ++i) c->xo_base[i] = g.s[i];
         mod = xoshiro_min_poly(g, 256);
     }
-    // per-batch generator: G = x^(12 * 10000) (sequential stream) or jump() = x^(2^(deg/2))
-    Gf2Poly G = jump ? gf2_x_pow(1, deg / 2, mod) : gf2_x_pow((uint64_t)kDrawsPerEvent * kBatch, 0, mod);
+    // per-batch generator: G = x^(12 * 10000) (sequential stream) or jump() = x^(2^(deg/2)); under sequential faster-evgen
+    // batches have no fixed stride and the tables step by kXoSegUnit outputs for the scan of fe_scan_xo.cuh instead
+    const bool seq_faster = (c->params.flags & TP3_FASTER_EVGEN) && !jump;
+    Gf2Poly G = jump ? gf2_x_pow(1, deg / 2, mod)
+                     : gf2_x_pow(seq_faster ? (uint64_t)kXoSegUnit : (uint64_t)kDrawsPerEvent * kBatch, 0, mod);
     c->xo_digits = 5;  // 2^40 batches
     c->xo_digit_polys.assign((size_t)c->xo_digits * 256 * 4, 0);
     Gf2Poly unit = G;
@@ -439,6 +448,108 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n,
     return rc;
 }
 
+// ---- faster-evgen + xoshiro: batch start states by coalescing segment walks (fe_scan_xo.cuh) -----------------------
+// Fills s.d_xo_states[0 .. n) for batches [first, first + n) of the sequential stream and leaves the context's generator
+// (c->fe_xo, the same bookkeeping as the host walk) at the start of batch first + n, so that consecutive calls continue.
+int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
+    const bool f32 = c->params.flags & TP3_F32;
+    if (!c->fe_ready || c->fe_pos > first) {  // (re)start from the seeded generator
+        for (int i = 0; i < 4; ++i) c->fe_xo[i] = c->xo_base[i];
+        c->fe_pos = 0;
+        c->fe_ready = true;
+    }
+    const uint64_t lead = first - c->fe_pos;                                   // batches to pass over before `first`
+    const uint64_t e_last = (lead + n) * (uint64_t)TP3_EVENT_BATCH_SIZE;       // event index (from the base) where batch first + n starts
+    const uint64_t n_bnd = n + 1;                                              // starts of batches first .. first + n
+    if (s.xo_states_cap < n_bnd) {
+        if (s.d_xo_states) TP3_CUDA(c, cudaFree(s.d_xo_states));
+        s.d_xo_states = nullptr;
+        s.xo_states_cap = 0;
+        TP3_CUDA(c, cudaMalloc(&s.d_xo_states, n_bnd * 4 * sizeof(uint64_t)));
+        s.xo_states_cap = n_bnd;
+    }
+    if (s.xo_bnd_cap < n_bnd) {
+        cudaFree(s.d_xo_bnd);
+        s.d_xo_bnd = nullptr;
+        s.xo_bnd_cap = 0;
+        TP3_CUDA(c, cudaMalloc(&s.d_xo_bnd, n_bnd * sizeof(XoBoundary)));
+        s.xo_bnd_cap = n_bnd;
+    }
+    const uint64_t b0 = c->fe_xo[0], b1 = c->fe_xo[1], b2 = c->fe_xo[2], b3 = c->fe_xo[3];
+    double margin = 1.004;  // 16.64 outputs per event on average; the count is checked and the scan extended if short
+    for (int attempt = 0; attempt < 8; ++attempt, margin *= 1.02) {
+        const uint64_t outputs = (uint64_t)((double)(e_last + 1) * 16.65 * margin) + 65536;
+        // one lane per segment: as long as possible (the entry walk and the jump-ahead are per segment) while the device stays full
+        uint32_t seg_units = 64;
+        while (seg_units > 2 && outputs / ((uint64_t)seg_units * kXoSegUnit) < (uint64_t)s.sm_count * 4 * 128 * 2) seg_units /= 2;
+        const uint64_t seg_len = (uint64_t)seg_units * kXoSegUnit;
+        const uint64_t n_seg = (outputs + seg_len - 1) / seg_len + 1;
+        if (n_seg * seg_units >= (1ull << (8 * c->xo_digits))) {
+            c->err = "faster-evgen scan beyond the reach of the xoshiro jump tables";
+            return TP3_E_INVALID;
+        }
+        if (s.xo_scan_cap < 3 * n_seg + 1) {
+            cudaFree(s.d_xo_scan);
+            s.d_xo_scan = nullptr;
+            s.xo_scan_cap = 0;
+            TP3_CUDA(c, cudaMalloc(&s.d_xo_scan, (3 * n_seg + 1) * sizeof(uint32_t)));
+            s.xo_scan_cap = 3 * n_seg + 1;
+        }
+        uint32_t *exit_a = s.d_xo_scan, *exit_b = s.d_xo_scan + n_seg, *count = s.d_xo_scan + 2 * n_seg, *flag = s.d_xo_scan + 3 * n_seg;
+        const unsigned blocks = (unsigned)((n_seg + 127) / 128);
+        auto walk = [&](const uint32_t* prev, const uint32_t* check, uint32_t* out_exit) {
+            if (f32) xo_walk_kernel<float><<<blocks, 128, 0, s.stream>>>(b0, b1, b2, b3, n_seg, seg_units, s.d_xo_digit_polys, c->xo_digits, prev, check, out_exit, count, flag);
+            else xo_walk_kernel<double><<<blocks, 128, 0, s.stream>>>(b0, b1, b2, b3, n_seg, seg_units, s.d_xo_digit_polys, c->xo_digits, prev, check, out_exit, count, flag);
+            ++c->launches;
+        };
+        walk(nullptr, nullptr, exit_a);  // pass A
+        bool settled = false;
+        for (int pass = 0; pass < 64 && !settled; ++pass) {  // pass B until the exits reproduce themselves
+            TP3_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.stream));
+            walk(exit_a, exit_a, exit_b);
+            uint32_t mismatch = 1;
+            TP3_CUDA(c, cudaMemcpyAsync(&mismatch, flag, sizeof mismatch, cudaMemcpyDeviceToHost, s.stream));
+            TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+            settled = mismatch == 0;
+            if (!settled) std::swap(exit_a, exit_b);
+        }
+        if (!settled) {
+            c->err = "faster-evgen xoshiro scan did not settle";
+            return TP3_E_CUDA;
+        }
+        std::vector<uint32_t> h_count(n_seg);
+        TP3_CUDA(c, cudaMemcpyAsync(h_count.data(), count, n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        // the segment of every wanted event index (multi_threading.rs:59-64 finds these by walking event by event)
+        std::vector<XoBoundary> bnd(n_bnd);
+        uint64_t cum = 0, j = 0;
+        for (uint64_t g = 0; g < n_seg && j < n_bnd; ++g) {
+            const uint64_t next = cum + h_count[g];
+            while (j < n_bnd && (lead + j) * (uint64_t)TP3_EVENT_BATCH_SIZE < next) {
+                bnd[j].seg = g;
+                bnd[j].skip = (uint32_t)((lead + j) * (uint64_t)TP3_EVENT_BATCH_SIZE - cum);
+                bnd[j].pad = 0;
+                ++j;
+            }
+            cum = next;
+        }
+        if (j < n_bnd) continue;  // the estimate was short: scan further
+        TP3_CUDA(c, cudaMemcpyAsync(s.d_xo_bnd, bnd.data(), n_bnd * sizeof(XoBoundary), cudaMemcpyHostToDevice, s.stream));
+        const unsigned bblocks = (unsigned)((n_bnd + 127) / 128);
+        const XoBoundary* d_bnd = static_cast<const XoBoundary*>(s.d_xo_bnd);
+        if (f32) xo_boundary_states_kernel<float><<<bblocks, 128, 0, s.stream>>>(b0, b1, b2, b3, seg_units, s.d_xo_digit_polys, c->xo_digits, exit_a, d_bnd, n_bnd, s.d_xo_states);
+        else xo_boundary_states_kernel<double><<<bblocks, 128, 0, s.stream>>>(b0, b1, b2, b3, seg_units, s.d_xo_digit_polys, c->xo_digits, exit_a, d_bnd, n_bnd, s.d_xo_states);
+        ++c->launches;
+        TP3_CUDA(c, cudaGetLastError());
+        TP3_CUDA(c, cudaMemcpyAsync(c->fe_xo, s.d_xo_states + 4 * n, 32, cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // bnd dies with this scope; fe_xo is read by the next call
+        c->fe_pos = first + n;
+        return TP3_OK;
+    }
+    c->err = "faster-evgen xoshiro scan: event count estimate failed";
+    return TP3_E_CUDA;
+}
+
 template <class F, int RNG> void launch_fe(const FeArgs& a, const tp3_params& p, cudaStream_t st) {
     const uint64_t units = a.n_batches * a.split;
     faster_evgen_kernel<F, RNG><<<(unsigned)((units + kFeThreads - 1) / kFeThreads), kFeThreads, 0, st>>>(a, phys_params<F>(p));
@@ -527,6 +638,9 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         fe_split = n <= (1ull << 20) ? 32 : 1;
         if (const char* e = std::getenv("TP3_FE_SPLIT")) fe_split = std::atoi(e) == 32 ? 32 : 1;  // test hook
         rc = fe_device_states_ranf(c, s, first, n, fe_split);
+        if (rc) return rc;
+    } else if (seq_faster && (c->params.flags & TP3_STANDARD_RANDOM) && !std::getenv("TP3_FE_HOST_SCAN")) {
+        rc = fe_device_states_xo(c, s, first, n);
         if (rc) return rc;
     } else if (seq_faster) {
         fe_host_states(c, first, n, fe_ranf, fe_xo);
@@ -669,6 +783,8 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_xo_digit_polys);
         cudaFree(s.d_xo_lane_polys);
         cudaFree(s.d_xo_states);
+        cudaFree(s.d_xo_scan);
+        cudaFree(s.d_xo_bnd);
         cudaFree(s.d_out);
         cudaFree(s.d_merged);
         cudaFree(s.d_fe_ranf_states);

@@ -411,6 +411,31 @@ def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, fea
         assert_acc_close(got, want, rel, what="split 32 vs host walk")
 
 
+@pytest.mark.parametrize("features,first,nb", [("faster-evgen,standard-random", 0, 300), ("faster-evgen,standard-random", 1990, 130),
+                                               ("faster-evgen,standard-random,f32", 7, 64)])
+def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, monkeypatch):
+    """xoshiro has no rounds to hang transition maps on: the batch start states of the sequential stream come from
+    coalescing segment walks on the GPU (fe_scan_xo.cuh: pass A guesses every segment's exit, pass B re-walks from the
+    implied entries and verifies, pass C walks to the wanted event indices).  Cross-check against the reference's own
+    method, the event-by-event walk kept on the host behind TP3_FE_HOST_SCAN: identical bits, for a range that starts at
+    the beginning, one that the scan has to reach first, continued and restarted calls, and a ragged last batch."""
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    monkeypatch.delenv("TP3_FE_HOST_SCAN", raising=False)
+    with tp3.Simulator(cfg) as sim:
+        dev = sim.simulate_batches(first, nb, 1234)
+        dev_next = sim.simulate_batches(first + nb - 1, 20)  # the full batch the ragged one stood for, then continues
+        dev_again = sim.simulate_batches(first + 5, 20)       # restarts the scan
+    monkeypatch.setenv("TP3_FE_HOST_SCAN", "1")
+    with tp3.Simulator(cfg) as sim:
+        host = sim.simulate_batches(first, nb, 1234)
+        host_next = sim.simulate_batches(first + nb - 1, 20)
+        host_again = sim.simulate_batches(first + 5, 20)
+    assert bytes(dev) == bytes(host)
+    assert bytes(dev_next) == bytes(host_next)
+    assert bytes(dev_again) == bytes(host_again)
+    assert sum(a.selected_events for a in dev) > 0
+
+
 def test_faster_evgen_f32_batches(sims, oracle, valeurs_text):
     nb = 8
     features = "faster-evgen,f32"

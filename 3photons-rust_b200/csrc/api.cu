@@ -452,7 +452,11 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n,
 // ---- faster-evgen + xoshiro: batch start states by coalescing segment walks (fe_scan_xo.cuh) -----------------------
 // Fills s.d_xo_states[0 .. n) for batches [first, first + n) of the sequential stream and leaves the context's generator
 // (c->fe_xo, the same bookkeeping as the host walk) at the start of batch first + n, so that consecutive calls continue.
-int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
+// `split` = 32 also locates the 32 lane starts inside every batch (events 10000 b + 313 l), batch-major, so that a warp
+// can share a batch as in the RANF path; pass C then walks from a segment entry once per LANE start, which only pays
+// with short segments (4096 outputs = 246 events on average): used for runs too small to fill the GPU with one thread
+// per batch.
+int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t split) {
     const bool f32 = c->params.flags & TP3_F32;
     if (!c->fe_ready || c->fe_pos > first) {  // (re)start from the seeded generator
         for (int i = 0; i < 4; ++i) c->fe_xo[i] = c->xo_base[i];
@@ -461,7 +465,10 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
     }
     const uint64_t lead = first - c->fe_pos;                                   // batches to pass over before `first`
     const uint64_t e_last = (lead + n) * (uint64_t)TP3_EVENT_BATCH_SIZE;       // event index (from the base) where batch first + n starts
-    const uint64_t n_bnd = n + 1;                                              // starts of batches first .. first + n
+    const uint64_t n_bnd = n * split + 1;                                      // lane / batch starts of batches first .. first + n - 1, then the start of batch first + n
+    auto target = [&](uint64_t j) {  // event index (from the base) of boundary j
+        return j == n * split ? e_last : (lead + j / split) * (uint64_t)TP3_EVENT_BATCH_SIZE + (j % split) * (uint64_t)kLaneEvents;
+    };
     if (s.xo_states_cap < n_bnd) {
         if (s.d_xo_states) TP3_CUDA(c, cudaFree(s.d_xo_states));
         s.d_xo_states = nullptr;
@@ -483,6 +490,7 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
         // one lane per segment: as long as possible (the entry walk and the jump-ahead are per segment) while the device stays full
         uint32_t seg_units = 64;
         while (seg_units > 2 && outputs / ((uint64_t)seg_units * kXoSegUnit) < (uint64_t)s.sm_count * 4 * 128 * 2) seg_units /= 2;
+        if (split > 1) seg_units = 2;
         const uint64_t seg_len = (uint64_t)seg_units * kXoSegUnit;
         const uint64_t n_seg = (outputs + seg_len - 1) / seg_len + 1;
         if (n_seg * seg_units >= (1ull << (8 * c->xo_digits))) {
@@ -526,9 +534,9 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
         uint64_t cum = 0, j = 0;
         for (uint64_t g = 0; g < n_seg && j < n_bnd; ++g) {
             const uint64_t next = cum + h_count[g];
-            while (j < n_bnd && (lead + j) * (uint64_t)TP3_EVENT_BATCH_SIZE < next) {
+            while (j < n_bnd && target(j) < next) {  // targets increase with j
                 bnd[j].seg = g;
-                bnd[j].skip = (uint32_t)((lead + j) * (uint64_t)TP3_EVENT_BATCH_SIZE - cum);
+                bnd[j].skip = (uint32_t)(target(j) - cum);
                 bnd[j].pad = 0;
                 ++j;
             }
@@ -542,7 +550,7 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n) {
         else xo_boundary_states_kernel<double><<<bblocks, 128, 0, s.stream>>>(b0, b1, b2, b3, seg_units, s.d_xo_digit_polys, c->xo_digits, exit_a, d_bnd, n_bnd, s.d_xo_states);
         ++c->launches;
         TP3_CUDA(c, cudaGetLastError());
-        TP3_CUDA(c, cudaMemcpyAsync(c->fe_xo, s.d_xo_states + 4 * n, 32, cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaMemcpyAsync(c->fe_xo, s.d_xo_states + 4 * (n_bnd - 1), 32, cudaMemcpyDeviceToHost, s.stream));
         TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // bnd dies with this scope; fe_xo is read by the next call
         c->fe_pos = first + n;
         return TP3_OK;
@@ -641,7 +649,10 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         rc = fe_device_states_ranf(c, s, first, n, fe_split);
         if (rc) return rc;
     } else if (seq_faster && (c->params.flags & TP3_STANDARD_RANDOM) && !std::getenv("TP3_FE_HOST_SCAN")) {
-        rc = fe_device_states_xo(c, s, first, n);
+        // one thread per batch fills the GPU from ~76 000 batches on; below that a warp shares a batch (32 lane starts each)
+        fe_split = n <= 65536 ? 32 : 1;
+        if (const char* e = std::getenv("TP3_FE_SPLIT")) fe_split = std::atoi(e) == 32 ? 32 : 1;  // test hook
+        rc = fe_device_states_xo(c, s, first, n, fe_split);
         if (rc) return rc;
     } else if (seq_faster) {
         fe_host_states(c, first, n, fe_ranf, fe_xo);

@@ -34,7 +34,7 @@ struct FeArgs {
     uint32_t jump_seeding;
     uint32_t split;                // 1: one thread per batch; 32: one warp per batch, lane l owns events [313 l, 313 (l + 1))
     const uint32_t* ranf_states;   // [n_batches * split][57]: numbers[0..55] + index (sequential mode)
-    const uint64_t* xo_states;     // [n_batches][4]
+    const uint64_t* xo_states;     // [n_batches * split][4]
     tp3_acc* out;
     int32_t ranf_seed;
 };
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kFeThreads, 512 / kFeThreads) faster_evgen_ker
         fe_simulate<F, RanfLane<F>>(gen, n_ev, P, FastMath{&fm, &P.fc}, split, out);
     } else {
         XoLane<F> gen;
-        const uint64_t* s = a.xo_states + 4 * (live ? slot : 0);
+        const uint64_t* s = a.xo_states + 4 * (live ? (split ? unit : slot) : 0);  // split: [n_batches * 32][4], batch-major
         gen.g.s0 = (decltype(gen.g.s0))s[0];
         gen.g.s1 = (decltype(gen.g.s0))s[1];
         gen.g.s2 = (decltype(gen.g.s0))s[2];

@@ -413,14 +413,19 @@ def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, fea
 
 @pytest.mark.parametrize("features,first,nb", [("faster-evgen,standard-random", 0, 300), ("faster-evgen,standard-random", 1990, 130),
                                                ("faster-evgen,standard-random,f32", 7, 64)])
-def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, monkeypatch):
+@pytest.mark.parametrize("split", [1, 32])
+def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, split, monkeypatch):
     """xoshiro has no rounds to hang transition maps on: the batch start states of the sequential stream come from
     coalescing segment walks on the GPU (fe_scan_xo.cuh: pass A guesses every segment's exit, pass B re-walks from the
     implied entries and verifies, pass C walks to the wanted event indices).  Cross-check against the reference's own
     method, the event-by-event walk kept on the host behind TP3_FE_HOST_SCAN: identical bits, for a range that starts at
-    the beginning, one that the scan has to reach first, continued and restarted calls, and a ragged last batch."""
+    the beginning, one that the scan has to reach first, continued and restarted calls, and a ragged last batch.
+    split = 32 (the default for runs too small to fill the GPU with one thread per batch): the scan also locates the 32
+    lane starts inside every batch and a warp shares the batch — same event selection, sums equal up to the order of the
+    additions."""
     cfg = tp3.Configuration.parse(valeurs_text, features)
     monkeypatch.delenv("TP3_FE_HOST_SCAN", raising=False)
+    monkeypatch.setenv("TP3_FE_SPLIT", str(split))
     with tp3.Simulator(cfg) as sim:
         dev = sim.simulate_batches(first, nb, 1234)
         dev_next = sim.simulate_batches(first + nb - 1, 20)  # the full batch the ragged one stood for, then continues
@@ -430,10 +435,16 @@ def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_t
         host = sim.simulate_batches(first, nb, 1234)
         host_next = sim.simulate_batches(first + nb - 1, 20)
         host_again = sim.simulate_batches(first + 5, 20)
-    assert bytes(dev) == bytes(host)
-    assert bytes(dev_next) == bytes(host_next)
-    assert bytes(dev_again) == bytes(host_again)
     assert sum(a.selected_events for a in dev) > 0
+    if split == 1:
+        assert bytes(dev) == bytes(host)
+        assert bytes(dev_next) == bytes(host_next)
+        assert bytes(dev_again) == bytes(host_again)
+        return
+    rel = 1e-12 if "f32" not in features else 5e-5
+    for got, want in list(zip(dev, host)) + list(zip(dev_next, host_next)) + list(zip(dev_again, host_again)):
+        assert got.selected_events == want.selected_events
+        assert_acc_close(got, want, rel, what="split 32 vs host walk")
 
 
 def test_faster_evgen_f32_batches(sims, oracle, valeurs_text):

@@ -490,7 +490,14 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, u
         // one lane per segment: as long as possible (the entry walk and the jump-ahead are per segment) while the device stays full
         uint32_t seg_units = 64;
         while (seg_units > 2 && outputs / ((uint64_t)seg_units * kXoSegUnit) < (uint64_t)s.sm_count * 4 * 128 * 2) seg_units /= 2;
-        if (split > 1) seg_units = 2;
+        // Lane starts: pass C walks from a segment entry once per 313 events, so segments must be short, but a 4096-output
+        // segment fails to coalesce about once in 800 (event lengths are odd, which slows the merging down: measured 3.7 %
+        // per 2048 outputs) and pass B would run 2-3 times; 8192 outputs (2e-6) is the better trade.
+        if (split > 1) seg_units = 4;
+        if (const char* e = std::getenv("TP3_FE_XO_SEG_UNITS")) {  // test hook: short segments make pass B repeat
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 64) seg_units = (uint32_t)v;
+        }
         const uint64_t seg_len = (uint64_t)seg_units * kXoSegUnit;
         const uint64_t n_seg = (outputs + seg_len - 1) / seg_len + 1;
         if (n_seg * seg_units >= (1ull << (8 * c->xo_digits))) {
@@ -513,7 +520,8 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, u
         };
         walk(nullptr, nullptr, exit_a);  // pass A
         bool settled = false;
-        for (int pass = 0; pass < 64 && !settled; ++pass) {  // pass B until the exits reproduce themselves
+        int passes_b = 0;
+        for (int pass = 0; pass < 64 && !settled; ++pass, ++passes_b) {  // pass B until the exits reproduce themselves
             TP3_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.stream));
             walk(exit_a, exit_a, exit_b);
             uint32_t mismatch = 1;
@@ -526,6 +534,9 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, u
             c->err = "faster-evgen xoshiro scan did not settle";
             return TP3_E_CUDA;
         }
+        if (std::getenv("TP3_FE_TIMING"))
+            std::fprintf(stderr, "[tp3 fe xo scan] batches %llu split %u: %llu segments of %llu outputs, pass B x %d\n", (unsigned long long)n, split,
+                         (unsigned long long)n_seg, (unsigned long long)seg_len, passes_b);
         std::vector<uint32_t> h_count(n_seg);
         TP3_CUDA(c, cudaMemcpyAsync(h_count.data(), count, n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         TP3_CUDA(c, cudaStreamSynchronize(s.stream));

@@ -447,6 +447,27 @@ def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_t
         assert_acc_close(got, want, rel, what="split 32 vs host walk")
 
 
+def test_faster_evgen_xoshiro_scan_repeats_pass_b(tp3, valeurs_text, monkeypatch, capfd):
+    """With 2048-output segments (TP3_FE_XO_SEG_UNITS=1) a segment's exit depends on its entry about once in 2000
+    segments, so over ~25 000 segments pass B has to be repeated with corrected exits: the result must still be the
+    host walk's, bit for bit."""
+    cfg = tp3.Configuration.parse(valeurs_text, "faster-evgen,standard-random")
+    monkeypatch.setenv("TP3_FE_XO_SEG_UNITS", "1")
+    monkeypatch.setenv("TP3_FE_SPLIT", "1")
+    monkeypatch.setenv("TP3_FE_TIMING", "1")
+    monkeypatch.delenv("TP3_FE_HOST_SCAN", raising=False)
+    with tp3.Simulator(cfg) as sim:
+        dev = sim.simulate_batches(0, 300)
+    err = capfd.readouterr().err
+    passes = [int(line.rsplit("x", 1)[1]) for line in err.splitlines() if "[tp3 fe xo scan]" in line]
+    assert passes and max(passes) >= 2, err  # the repeat path was taken
+    monkeypatch.delenv("TP3_FE_XO_SEG_UNITS")
+    monkeypatch.setenv("TP3_FE_HOST_SCAN", "1")
+    with tp3.Simulator(cfg) as sim:
+        host = sim.simulate_batches(0, 300)
+    assert bytes(dev) == bytes(host)
+
+
 def test_faster_evgen_f32_batches(sims, oracle, valeurs_text):
     nb = 8
     features = "faster-evgen,f32"

@@ -4,7 +4,7 @@
 // 221-249), so the stream position of batch b depends on every earlier event; the reference's scheduler thread walks
 // the stream event by event (evgen.rs:257-267, multi_threading.rs:59-64).  xoshiro has no round structure to hang
 // transition maps on (fe_scan.cuh does that for RANF), but walks that start at different positions COALESCE: two walks
-// land on a common event start with probability ~1/16.6 per event and are one walk from there on.  So the stream is
+// land on a common event start with probability ~1/40 per event (measured) and are one walk from there on.  So the stream is
 // cut into segments of L positions and
 //   pass A  one lane per segment walks from the segment start and records where its last event ends (the exit offset
 //           into the next segment) — which, after the first few hundred positions, no longer depends on where it entered;

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 pkg = g.package()
 text = open(os.path.join(g.ROOT, "tests", "golden", "valeurs")).read()
-for features, kernel in [("", 0), ("", 1), ("standard-random", 0), ("f32", 0), ("multi-threading,faster-threading", 0), ("faster-evgen", 0)]:
+for features, kernel in [("", 0), ("", 1), ("standard-random", 0), ("f32", 0), ("multi-threading,faster-threading", 0), ("faster-evgen", 0),
+                         ("faster-evgen,standard-random", 0)]:
     cfg = pkg.Configuration.parse(text, features).with_num_events(25000)
     with pkg.Simulator(cfg, kernel) as sim:
         accs = sim.simulate_batches(0, 3, 5000)
@@ -17,6 +18,9 @@ os.environ["TP3_FE_SPLIT"] = "1"
 cfg = pkg.Configuration.parse(text, "faster-evgen,f32").with_num_events(25000)
 with pkg.Simulator(cfg, 0) as sim:
     print("faster-evgen,f32 split 1", [a.selected_events for a in sim.simulate_batches(0, 3, 5000)], flush=True)
+cfg = pkg.Configuration.parse(text, "faster-evgen,standard-random,f32").with_num_events(25000)
+with pkg.Simulator(cfg, 0) as sim:  # xoshiro scan (fe_scan_xo.cuh), batch starts only
+    print("faster-evgen,standard-random,f32 split 1", [a.selected_events for a in sim.simulate_batches(0, 3, 5000)], flush=True)
 del os.environ["TP3_FE_SPLIT"]
 cfg = pkg.Configuration.parse(text, "").with_num_events(25000)
 with pkg.Simulator(cfg, 0) as sim:

@@ -166,6 +166,11 @@ def lib() -> C.CDLL:
         "tp3_simulate_batches_device": (C.c_int, [vp, u64, u64, u32]),
         "tp3_fetch": (C.c_int, [vp, P(Acc), u64]),
         "tp3_simulate_merged": (C.c_int, [vp, u64, u64, u32, P(Acc)]),
+        "tp3_simulate_merged_device": (C.c_int, [vp, u64, u64, u32, vp]),
+        "tp3_fold_batches": (C.c_int, [P(Acc), u64, u32, P(Acc)]),
+        "tp3_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+        "tp3_get_stat": (C.c_int, [vp, C.c_char_p, P(C.c_int64)]),
+        "tp3_kernel_arg_bytes": (C.c_size_t, []),
         "tp3_synchronize": (C.c_int, [vp]),
         "tp3_launch_count": (u64, [vp]),
         "tp3_histograms_enable": (C.c_int, [vp, u32]),
@@ -199,6 +204,7 @@ ABI_SYMBOLS = [
     "tp3_rng_dump", "tp3_events_dump", "tp3_peak_probe", "tp3_fastmath_probe", "tp3_config_parse", "tp3_params_from_config", "tp3_merge",
     "tp3_finalize", "tp3_format_res_data", "tp3_format_stdout", "tp3_run", "tp3_host_ranf_round",
     "tp3_host_xoshiro_state", "tp3_histograms_enable", "tp3_histograms_reset", "tp3_histograms_fetch",
+    "tp3_simulate_merged_device", "tp3_fold_batches", "tp3_set_option", "tp3_get_stat", "tp3_kernel_arg_bytes",
 ]
 
 
@@ -251,10 +257,13 @@ def merge(into: Acc, other: Acc, flags: int = 0) -> Acc:
 
 
 def fold(accs: Sequence[Acc], flags: int = 0) -> Acc:
-    """Left fold in batch order (sequential.rs:24-36, multi_threading.rs:107-126)."""
-    total = Acc.from_buffer_copy(accs[0])
-    for a in accs[1:]:
-        merge(total, a, flags)
+    """Left fold in batch order (sequential.rs:24-36, multi_threading.rs:107-126): tp3_fold_batches."""
+    n = len(accs)
+    arr = accs if isinstance(accs, C.Array) and accs._type_ is Acc else (Acc * n)(*accs)
+    total = Acc()
+    rc = lib().tp3_fold_batches(arr, n, flags, C.byref(total))
+    if rc != OK:
+        raise Tp3Error(rc, "tp3_fold_batches")
     return total
 
 
@@ -362,8 +371,22 @@ class Simulator:
         self._check(lib().tp3_simulate_merged(self._h, first_batch, n_batches, last_batch_len, C.byref(out)))
         return out
 
+    def simulate_merged_device(self, first_batch: int, n_batches: int, last_batch_len: int, device_ptr: int):
+        """Asynchronous: the merged accumulator as 13 doubles in the caller's device buffer (one ncclReduce operand)."""
+        self._check(lib().tp3_simulate_merged_device(self._h, first_batch, n_batches, last_batch_len, C.c_void_p(device_ptr)))
+
     def synchronize(self):
         self._check(lib().tp3_synchronize(self._h))
+
+    def set_option(self, name: str, value: int):
+        """Test / A-B switches of include/tp3.h (tp3_set_option); nothing is read from the environment."""
+        self._check(lib().tp3_set_option(self._h, name.encode(), int(value)))
+        return self
+
+    def get_stat(self, name: str) -> int:
+        v = C.c_int64()
+        self._check(lib().tp3_get_stat(self._h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     @property
     def launch_count(self) -> int:
@@ -438,13 +461,15 @@ class Histograms:
         return [w / width for w in self.weights[o]]
 
 
-def run_simulation(cfg: Configuration, kernel: int = KERNEL_FAST, devices: Optional[Sequence[int]] = None) -> FinalResults:
-    """scheduling::run_simulation (scheduling/mod.rs:31-59): all batches on the GPU(s), left fold
-    in batch order on the host, finalize."""
+def run_simulation(cfg: Configuration, kernel: int = KERNEL_FAST, devices: Optional[Sequence[int]] = None,
+                   per_batch: bool = False) -> FinalResults:
+    """scheduling::run_simulation (scheduling/mod.rs:31-59): all batches on the GPU(s), left fold in batch order
+    (in the kernel: tp3_simulate_merged; `per_batch`: per-batch accumulators to the host and tp3_fold_batches there,
+    the same bits), finalize."""
     nb, last = batch_layout(cfg.num_events)
     with Simulator(cfg, kernel, devices) as sim:
-        accs = sim.simulate_batches(0, nb, last)
-    return finalize(cfg, fold(accs, cfg.flags))
+        total = fold(sim.simulate_batches(0, nb, last), cfg.flags) if per_batch else sim.simulate_merged(0, nb, last)
+    return finalize(cfg, total)
 
 
 def main_run(valeurs_path: str, out_dir: str = "", features="", kernel: int = KERNEL_FAST, n_dev: int = 1):
@@ -455,6 +480,17 @@ def main_run(valeurs_path: str, out_dir: str = "", features="", kernel: int = KE
     if rc != OK:
         raise Tp3Error(rc, buf.value.decode())
     return buf.value.decode(), float(secs.value)
+
+
+def acc_from_f64x13(values) -> Acc:
+    """The 13 doubles of tp3_simulate_merged_device (summed over ranks or not) back as an accumulator."""
+    a = Acc()
+    a.selected_events = int(round(values[0]))
+    for k in range(5):
+        a.spm2[k] = values[1 + k]
+        a.vars[k] = values[6 + k]
+    a.sigma, a.variance = values[11], values[12]
+    return a
 
 
 # ------------------------------------------------------------------------------ multi-process

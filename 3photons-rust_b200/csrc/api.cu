@@ -34,10 +34,10 @@ struct DeviceSlot {
     size_t xo_states_cap = 0;
     tp3_acc* d_out = nullptr;
     size_t out_cap = 0;
-    tp3_acc* d_merged = nullptr;
-    cudaStream_t merge_stream = nullptr;   // folds chunk i while chunk i+1 is simulated
-    cudaStream_t alt_stream = nullptr;     // odd chunks: their first CTAs fill the SMs the previous chunk's tail leaves idle
-    cudaEvent_t chunk_done = nullptr, merge_done = nullptr, call_start = nullptr;
+    FoldState* d_fold = nullptr;           // in-kernel ordered fold of the last launch (kernels.cuh)
+    uint32_t* d_unit_done = nullptr;       // per-unit completion marks, compared with `epoch`
+    size_t unit_done_cap = 0;
+    uint32_t epoch = 0;
     unsigned long long* d_hist_counts = nullptr;  // per-event observables: [TP3_HIST_OBSERVABLES][hist_bins]
     double* d_hist_weights = nullptr;
     uint32_t* d_fe_ranf_states = nullptr;  // faster-evgen: [n][57] batch start states from the host scheduler
@@ -68,6 +68,15 @@ struct tp3_ctx {
     std::string err;
     uint64_t launches = 0;
     uint32_t hist_bins = 0;  // per-event observables on (tp3_histograms_enable)
+    // tp3_set_option: test / A-B switches, read once here instead of from the environment on every launch
+    int64_t opt_unit_batches = 0;    // consecutive batches per scheduling unit (0 = by launch size)
+    int64_t opt_grid_warps = 0;      // warps in the grid (0 = what the device holds at once)
+    int64_t opt_f32_scalar = 0;      // f32: one event per lane instead of the packed two-events-per-lane kernel
+    int64_t opt_fe_split = 0;        // faster-evgen: 1 = one thread per batch, 32 = one lane per 313 events, 0 = by launch size
+    int64_t opt_fe_host_scan = 0;    // faster-evgen: batch start states from the host walk (the reference's method; cross-check)
+    int64_t opt_fe_xo_seg_units = 0; // faster-evgen + xoshiro scan: segment length in units of 2048 outputs (0 = by launch size)
+    int64_t opt_fe_timing = 0;       // print the scan phases of every call to stderr
+    int64_t stat_fe_xo_pass_b = 0;   // tp3_get_stat: pass-B repetitions of the last xoshiro scan
     // host copies of the seeding data
     uint32_t ranf_base[kRanfLag];
     std::vector<uint32_t> ranf_table;
@@ -97,8 +106,6 @@ namespace {
         }                                                                                                \
     } while (0)
 
-// bench.py counts these bytes as the host->device payload of a launch (e2e.h2d_bytes_per_step)
-static_assert(sizeof(SimArgs) == 312 && sizeof(PhysParams<double>) == 296, "update the kernel-argument byte count in bench.py");
 
 template <class F> struct ScalarOf { using type = F; };
 template <> struct ScalarOf<f2> { using type = float; };
@@ -128,27 +135,63 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
     return q;
 }
 
+// What a launcher needs to lay out the static schedule of kernels.cuh.
+struct Sched {
+    int sm_count;
+    int64_t unit_batches;  // 0 = auto
+    int64_t grid_warps;    // 0 = auto
+    bool stream_continues; // sequential RANF: a warp's next batch continues the stream, so units of several batches pay
+};
+
+// Fill the schedule fields of `a` for a kernel that runs `warps`-warp CTAs, `ctas_per_sm` of them per SM.
+cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& sc) {
+    if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+    uint64_t W = (uint64_t)sc.sm_count * ctas_per_sm * warps;  // what the device holds at once
+    if (sc.grid_warps > 0) W = ((uint64_t)sc.grid_warps + warps - 1) / warps * warps;
+    if (a.n_batches < W) W = (a.n_batches + warps - 1) / warps * warps;  // one batch per warp, no full round
+    uint64_t unit = 1;
+    if (sc.stream_continues) {
+        unit = a.n_batches / (W * 4);  // at least ~4 rounds, so that the ordered fold overlaps the simulation
+        unit = unit < 1 ? 1 : unit > 8 ? 8 : unit;
+    }
+    if (sc.unit_batches > 0) unit = (uint64_t)sc.unit_batches;
+    a.n_warps = (uint32_t)W;
+    a.unit_batches = (uint32_t)unit;
+    a.full_rounds = (uint32_t)(a.n_batches / (W * unit));
+    return cudaSuccess;
+}
+// Resident CTAs per SM of a kernel (asked once per kernel and dynamic shared memory size).
+template <class K> int ctas_per_sm(K kernel, int threads, size_t dyn) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn) != cudaSuccess) return 0;
+    return n;
+}
+
 template <class F, int RNG, bool SORT, bool LITERAL>
-void launch_sim(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
+cudaError_t launch_sim(SimArgs a, const tp3_params& p, cudaStream_t st, const Sched& sc) {
     constexpr int warps = sim_warps(LITERAL, false);
-    const uint64_t per_cta = (uint64_t)warps * a.batches_per_warp;
-    simulate_kernel<F, RNG, SORT, LITERAL><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), 32 * warps, 0, st>>>(a, phys_params<F>(p));
+    auto kernel = simulate_kernel<F, RNG, SORT, LITERAL>;
+    static const int occ = ctas_per_sm(kernel, 32 * warps, 0);
+    if (cudaError_t e = fill_schedule(a, warps, occ, sc)) return e;
+    kernel<<<a.n_warps / warps, 32 * warps, 0, st>>>(a, phys_params<F>(p));
+    return cudaGetLastError();
 }
 // Fast kernel with the per-event observable epilogue: the CTA's event counts in dynamic shared memory (4 bytes per bin).
 template <class F, int RNG, bool SORT>
-void launch_sim_hist(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
-    const uint64_t per_cta = (uint64_t)kWarps * a.batches_per_warp;
+cudaError_t launch_sim_hist(SimArgs a, const tp3_params& p, cudaStream_t st, const Sched& sc) {
     const size_t dyn = (size_t)TP3_HIST_OBSERVABLES * a.hist_bins * sizeof(uint32_t);
     auto kernel = simulate_kernel<F, RNG, SORT, false, true>;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  // an error shows up at the launch
-    kernel<<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), kThreads, dyn, st>>>(a, phys_params<F>(p));
+    if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) return e;
+    if (cudaError_t e = fill_schedule(a, kWarps, ctas_per_sm(kernel, kThreads, dyn), sc)) return e;
+    kernel<<<a.n_warps / kWarps, kThreads, dyn, st>>>(a, phys_params<F>(p));
+    return cudaGetLastError();
 }
 template <class F, int RNG, bool SORT, bool LITERAL>
 void launch_dump(const SimArgs& a, const tp3_params& p, const DumpArgs& d, cudaStream_t st) {
     dump_kernel<F, RNG, SORT, LITERAL><<<1, kThreads, 0, st>>>(a, phys_params<F>(p), d);
 }
 
-using SimFn = void (*)(const SimArgs&, const tp3_params&, cudaStream_t);
+using SimFn = cudaError_t (*)(SimArgs, const tp3_params&, cudaStream_t, const Sched&);
 using DumpFn = void (*)(const SimArgs&, const tp3_params&, const DumpArgs&, cudaStream_t);
 
 template <class F, int RNG> SimFn pick_sim2(bool sort, bool literal) {
@@ -160,26 +203,35 @@ template <class F, int RNG> DumpFn pick_dump2(bool sort, bool literal) {
     return literal ? launch_dump<F, RNG, false, true> : launch_dump<F, RNG, false, false>;
 }
 // f32 fast kernel, two events per lane in packed FP32 arithmetic (f32x2.cuh)
-template <int RNG> void launch_sim_x2(const SimArgs& a, const tp3_params& p, cudaStream_t st) {
-    const uint64_t per_cta = (uint64_t)x2_warps(RNG) * a.batches_per_warp;
-    simulate_kernel_x2<RNG><<<(unsigned)((a.n_batches + per_cta - 1) / per_cta), 32 * x2_warps(RNG), 0, st>>>(a, phys_params<f2>(p));
+template <int RNG> cudaError_t launch_sim_x2(SimArgs a, const tp3_params& p, cudaStream_t st, const Sched& sc) {
+    constexpr int warps = x2_warps(RNG);
+    auto kernel = simulate_kernel_x2<RNG>;
+    static const int occ = ctas_per_sm(kernel, 32 * warps, 0);
+    if (cudaError_t e = fill_schedule(a, warps, occ, sc)) return e;
+    kernel<<<a.n_warps / warps, 32 * warps, 0, st>>>(a, phys_params<f2>(p));
+    return cudaGetLastError();
 }
 template <class F, int RNG> SimFn pick_sim_hist2(bool sort) { return sort ? launch_sim_hist<F, RNG, true> : launch_sim_hist<F, RNG, false>; }
-SimFn pick_sim(const tp3_params& p, bool hist = false) {
+SimFn pick_sim(const tp3_params& p, bool hist, bool f32_scalar) {
     const bool f32 = p.flags & TP3_F32, xo = p.flags & TP3_STANDARD_RANDOM;
     const bool sort = !(p.flags & TP3_NO_PHOTON_SORTING), lit = p.kernel == TP3_KERNEL_LITERAL;
     if (hist) {
         if (f32) return xo ? pick_sim_hist2<float, RNG_XOSHIRO>(sort) : pick_sim_hist2<float, RNG_RANF>(sort);
         return xo ? pick_sim_hist2<double, RNG_XOSHIRO>(sort) : pick_sim_hist2<double, RNG_RANF>(sort);
     }
-    if (f32 && !lit && !std::getenv("TP3_F32_SCALAR"))  // (the one-event-per-lane f32 kernel stays for A/B runs and tests)
+    if (f32 && !lit && !f32_scalar)  // (the one-event-per-lane f32 kernel stays for A/B runs and tests: tp3_set_option)
         return xo ? launch_sim_x2<RNG_XOSHIRO> : launch_sim_x2<RNG_RANF>;
     if (f32) return xo ? pick_sim2<float, RNG_XOSHIRO>(sort, lit) : pick_sim2<float, RNG_RANF>(sort, lit);
     return xo ? pick_sim2<double, RNG_XOSHIRO>(sort, lit) : pick_sim2<double, RNG_RANF>(sort, lit);
 }
-DumpFn pick_dump(const tp3_params& p) {
+template <int RNG> void launch_dump_x2(const SimArgs& a, const tp3_params& p, const DumpArgs& d, cudaStream_t st) {
+    dump_kernel_x2<RNG><<<1, 32, 0, st>>>(a, phys_params<f2>(p), d);
+}
+DumpFn pick_dump(const tp3_params& p, bool f32_scalar) {
     const bool f32 = p.flags & TP3_F32, xo = p.flags & TP3_STANDARD_RANDOM;
     const bool sort = !(p.flags & TP3_NO_PHOTON_SORTING), lit = p.kernel == TP3_KERNEL_LITERAL;
+    // the shipped f32 kernel is the packed one: its per-event dump goes through the same packed physics (unsorted photons)
+    if (f32 && !lit && !f32_scalar) return xo ? launch_dump_x2<RNG_XOSHIRO> : launch_dump_x2<RNG_RANF>;
     if (f32) return xo ? pick_dump2<float, RNG_XOSHIRO>(sort, lit) : pick_dump2<float, RNG_RANF>(sort, lit);
     return xo ? pick_dump2<double, RNG_XOSHIRO>(sort, lit) : pick_dump2<double, RNG_RANF>(sort, lit);
 }
@@ -319,7 +371,7 @@ int fe_device_states_ranf(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n,
     const bool f32 = c->params.flags & TP3_F32;
     const uint32_t part_len = split == 1 ? (uint32_t)TP3_EVENT_BATCH_SIZE : (uint32_t)kLaneEvents;
     const uint64_t n_bnd = n * split;
-    const bool timing = std::getenv("TP3_FE_TIMING") != nullptr;
+    const bool timing = c->opt_fe_timing != 0;
     auto now = []() { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
@@ -494,10 +546,8 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, u
         // segment fails to coalesce about once in 800 (event lengths are odd, which slows the merging down: measured 3.7 %
         // per 2048 outputs) and pass B would run 2-3 times; 8192 outputs (2e-6) is the better trade.
         if (split > 1) seg_units = 4;
-        if (const char* e = std::getenv("TP3_FE_XO_SEG_UNITS")) {  // test hook: short segments make pass B repeat
-            const int v = std::atoi(e);
-            if (v >= 1 && v <= 64) seg_units = (uint32_t)v;
-        }
+        if (c->opt_fe_xo_seg_units >= 1 && c->opt_fe_xo_seg_units <= 64)  // test hook: short segments make pass B repeat
+            seg_units = (uint32_t)c->opt_fe_xo_seg_units;
         const uint64_t seg_len = (uint64_t)seg_units * kXoSegUnit;
         const uint64_t n_seg = (outputs + seg_len - 1) / seg_len + 1;
         if (n_seg * seg_units >= (1ull << (8 * c->xo_digits))) {
@@ -534,7 +584,8 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, u
             c->err = "faster-evgen xoshiro scan did not settle";
             return TP3_E_CUDA;
         }
-        if (std::getenv("TP3_FE_TIMING"))
+        c->stat_fe_xo_pass_b = passes_b;
+        if (c->opt_fe_timing)
             std::fprintf(stderr, "[tp3 fe xo scan] batches %llu split %u: %llu segments of %llu outputs, pass B x %d\n", (unsigned long long)n, split,
                          (unsigned long long)n_seg, (unsigned long long)seg_len, passes_b);
         std::vector<uint32_t> h_count(n_seg);
@@ -576,6 +627,7 @@ template <class F, int RNG> void launch_fe(const FeArgs& a, const tp3_params& p,
 }
 
 int ensure_out(tp3_ctx* c, DeviceSlot& s, uint64_t n) {
+    if (!s.d_fold) TP3_CUDA(c, cudaMalloc(&s.d_fold, sizeof(FoldState)));
     if (s.out_cap < n) {
         if (s.d_out) TP3_CUDA(c, cudaFree(s.d_out));
         s.d_out = nullptr;
@@ -600,18 +652,6 @@ SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     a.n_batches = n;
     a.last_batch_len = last_len;
     a.jump_seeding = (c->params.flags & TP3_FASTER_THREADING) ? 1u : 0u;
-    // Consecutive batches per warp: the sequential RANF stream continues from one batch into the next, so the
-    // jump-ahead is paid once per warp. Keep at least ~8 warp-tasks per resident warp slot for load balance.
-    a.batches_per_warp = 1;
-    if (!(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING))) {
-        const uint64_t resident_warps = (uint64_t)s.sm_count * 16;
-        uint64_t nb = n / (resident_warps * 8);
-        a.batches_per_warp = (uint32_t)(nb < 1 ? 1 : nb > 8 ? 8 : nb);
-        if (const char* e = std::getenv("TP3_BATCHES_PER_WARP")) {  // test hook
-            const int v = std::atoi(e);
-            if (v >= 1 && v <= 64) a.batches_per_warp = (uint32_t)v;
-        }
-    }
     a.ranf_table = s.d_ranf_table;
     a.xo_batch_states = s.d_xo_states;
     a.xo_lane_polys = s.d_xo_lane_polys;
@@ -622,10 +662,10 @@ SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
 }
 
 // Enqueue seeding (xoshiro) + the fused kernel for [first, first+n) on one device slot.
-int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len, uint64_t slot_off = 0,
-                  uint64_t cap = 0) {
+// `fold`: also left-fold the accumulators in batch order into s.d_fold->running (in the kernel; merge_kernel under faster-evgen).
+int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len, bool fold = false) {
     TP3_CUDA(c, cudaSetDevice(s.dev));
-    int rc = ensure_out(c, s, cap ? cap : n);
+    int rc = ensure_out(c, s, n);
     if (rc) return rc;
     if (n > 0x7fffffffull) {
         c->err = "too many batches in one launch";
@@ -649,20 +689,20 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     const bool seq_faster = faster && !(c->params.flags & TP3_FASTER_THREADING);
     std::vector<uint32_t> fe_ranf;
     std::vector<uint64_t> fe_xo;
-    const bool device_scan = seq_faster && !(c->params.flags & TP3_STANDARD_RANDOM) && !std::getenv("TP3_FE_HOST_SCAN");
+    const bool device_scan = seq_faster && !(c->params.flags & TP3_STANDARD_RANDOM) && !c->opt_fe_host_scan;
     uint32_t fe_split = 1;
     if (device_scan) {
         // One lane per 313 events: fills the device for any run size and keeps a warp's lanes on one batch (measured
         // faster than one thread per batch at every size).  Costs 7.3 KB of start states per batch, so very long
         // ranges fall back to one thread per batch.
         fe_split = n <= (1ull << 20) ? 32 : 1;
-        if (const char* e = std::getenv("TP3_FE_SPLIT")) fe_split = std::atoi(e) == 32 ? 32 : 1;  // test hook
+        if (c->opt_fe_split) fe_split = c->opt_fe_split == 32 ? 32 : 1;  // test hook (tp3_set_option)
         rc = fe_device_states_ranf(c, s, first, n, fe_split);
         if (rc) return rc;
-    } else if (seq_faster && (c->params.flags & TP3_STANDARD_RANDOM) && !std::getenv("TP3_FE_HOST_SCAN")) {
+    } else if (seq_faster && (c->params.flags & TP3_STANDARD_RANDOM) && !c->opt_fe_host_scan) {
         // one thread per batch fills the GPU from ~76 000 batches on; below that a warp shares a batch (32 lane starts each)
         fe_split = n <= 65536 ? 32 : 1;
-        if (const char* e = std::getenv("TP3_FE_SPLIT")) fe_split = std::atoi(e) == 32 ? 32 : 1;  // test hook
+        if (c->opt_fe_split) fe_split = c->opt_fe_split == 32 ? 32 : 1;  // test hook (tp3_set_option)
         rc = fe_device_states_xo(c, s, first, n, fe_split);
         if (rc) return rc;
     } else if (seq_faster) {
@@ -682,9 +722,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // the host vectors die at the end of this call
     }
     SimArgs a = make_args(c, s, first, n, last_len);
-    a.out = s.d_out + slot_off;
-    if (a.xo_batch_states) a.xo_batch_states += 4 * slot_off;
-    uint64_t* xo_states = s.d_xo_states ? s.d_xo_states + 4 * slot_off : nullptr;
+    uint64_t* xo_states = s.d_xo_states;
     if ((c->params.flags & TP3_STANDARD_RANDOM) && !seq_faster) {
         const unsigned blocks = (unsigned)((n + 127) / 128);
         if (c->params.flags & TP3_F32)
@@ -712,14 +750,44 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         const bool f32 = c->params.flags & TP3_F32, xo = c->params.flags & TP3_STANDARD_RANDOM;
         if (f32) { if (xo) launch_fe<float, RNG_XOSHIRO>(f, c->params, s.stream); else launch_fe<float, RNG_RANF>(f, c->params, s.stream); }
         else { if (xo) launch_fe<double, RNG_XOSHIRO>(f, c->params, s.stream); else launch_fe<double, RNG_RANF>(f, c->params, s.stream); }
+        ++c->launches;
+        TP3_CUDA(c, cudaGetLastError());
+        if (fold) {  // strict left fold of the per-batch accumulators by one CTA, after the batch kernel
+            if (c->params.flags & TP3_F32) merge_kernel<float><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, n, &s.d_fold->running, true);
+            else merge_kernel<double><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, n, &s.d_fold->running, true);
+            ++c->launches;
+            TP3_CUDA(c, cudaGetLastError());
+        }
     } else {
         a.hist_bins = c->hist_bins;
         a.hist_counts = s.d_hist_counts;
         a.hist_weights = s.d_hist_weights;
-        pick_sim(c->params, c->hist_bins != 0)(a, c->params, s.stream);
+        const Sched sc{s.sm_count, c->opt_unit_batches, c->opt_grid_warps,
+                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING))};
+        if (fold) {
+            // Completion marks: one word per unit, compared with this launch's epoch (no memset per launch).  The number
+            // of units is at most n + the grid's warps; the grid never exceeds 64 warps per SM.
+            const size_t need = (size_t)n + (size_t)s.sm_count * 64 + 64 + (c->opt_grid_warps > 0 ? (size_t)c->opt_grid_warps : 0);
+            if (s.unit_done_cap < need) {
+                if (s.d_unit_done) TP3_CUDA(c, cudaFree(s.d_unit_done));
+                s.d_unit_done = nullptr;
+                s.unit_done_cap = 0;
+                TP3_CUDA(c, cudaMalloc(&s.d_unit_done, need * sizeof(uint32_t)));
+                s.unit_done_cap = need;
+                s.epoch = 0;
+            }
+            if (s.epoch == 0 || s.epoch == 0xffffffffu) {
+                TP3_CUDA(c, cudaMemsetAsync(s.d_unit_done, 0, s.unit_done_cap * sizeof(uint32_t), s.stream));
+                s.epoch = 0;
+            }
+            a.epoch = ++s.epoch;
+            a.unit_done = s.d_unit_done;
+            a.fold = s.d_fold;
+            TP3_CUDA(c, cudaMemsetAsync(s.d_fold, 0, sizeof(FoldState), s.stream));
+        }
+        TP3_CUDA(c, pick_sim(c->params, c->hist_bins != 0, c->opt_f32_scalar != 0)(a, c->params, s.stream, sc));
+        ++c->launches;
     }
-    ++c->launches;
-    TP3_CUDA(c, cudaGetLastError());
     s.last_first = first;
     s.last_n = n;
     return TP3_OK;
@@ -789,7 +857,6 @@ int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx*
             t.insert(t.end(), c->ranf_base, c->ranf_base + kRanfLag);
             e = up(t.data(), t.size() * 4, (void**)&s.d_ranf_table);
         }
-        if (e == cudaSuccess) e = cudaMalloc(&s.d_merged, sizeof(tp3_acc));
         c->devs.push_back(s);
         if (e != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
     }
@@ -801,6 +868,7 @@ void tp3_destroy(tp3_ctx* c) {
     if (!c) return;
     for (auto& s : c->devs) {
         cudaSetDevice(s.dev);
+        if (s.stream) cudaStreamSynchronize(s.stream);  // nothing of this context is in flight when its buffers go
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_ranf_table);
         cudaFree(s.d_xo_digit_polys);
@@ -809,7 +877,8 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_xo_scan);
         cudaFree(s.d_xo_bnd);
         cudaFree(s.d_out);
-        cudaFree(s.d_merged);
+        cudaFree(s.d_fold);
+        cudaFree(s.d_unit_done);
         cudaFree(s.d_fe_ranf_states);
         cudaFree(s.d_fe_bnd);
         cudaFree(s.d_fe_maps);
@@ -819,11 +888,6 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_fe_seg_events);
         cudaFree(s.d_hist_counts);
         cudaFree(s.d_hist_weights);
-        if (s.merge_stream) cudaStreamDestroy(s.merge_stream);
-        if (s.alt_stream) cudaStreamDestroy(s.alt_stream);
-        if (s.call_start) cudaEventDestroy(s.call_start);
-        if (s.chunk_done) cudaEventDestroy(s.chunk_done);
-        if (s.merge_done) cudaEventDestroy(s.merge_done);
     }
     delete c;
 }
@@ -897,16 +961,17 @@ int tp3_histograms_fetch(tp3_ctx* c, uint64_t* counts, double* weights) {
 int tp3_set_stream(tp3_ctx* c, int slot, void* stream) {
     if (!c || slot < 0 || slot >= (int)c->devs.size()) return TP3_E_INVALID;
     DeviceSlot& s = c->devs[slot];
-    if (s.own_stream && s.stream) {
-        cudaSetDevice(s.dev);
-        cudaStreamDestroy(s.stream);
-    }
+    TP3_CUDA(c, cudaSetDevice(s.dev));
+    if (s.stream) TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // work queued on the old stream finishes before the switch
+    if (s.own_stream && s.stream) TP3_CUDA(c, cudaStreamDestroy(s.stream));
     s.stream = (cudaStream_t)stream;
     s.own_stream = false;
     return TP3_OK;
 }
 
 uint64_t tp3_launch_count(const tp3_ctx* c) { return c ? c->launches : 0; }
+
+size_t tp3_kernel_arg_bytes(void) { return sizeof(SimArgs) + sizeof(PhysParams<double>); }
 
 int tp3_synchronize(tp3_ctx* c) {
     if (!c) return TP3_E_INVALID;
@@ -958,73 +1023,105 @@ int tp3_simulate_batches(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_l
     return tp3_fetch(c, out, n);
 }
 
-int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
-    if (!c || !out || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE) {
-        if (c) c->err = "tp3_simulate_merged: bad range";
-        return TP3_E_INVALID;
-    }
-    // The ordered fold is one serial chain of additions, so it is overlapped with the simulation: every device
-    // range is cut into chunks; while chunk i+1 is being simulated on the main stream, a second stream folds
-    // chunk i into the running accumulator (strict batch order is kept: the folds are serialised on that stream).
-    const bool chunked = !(c->params.flags & TP3_FASTER_EVGEN);
+// One launch per device with the in-kernel ordered fold; leaves every slot's result in s.d_fold (asynchronous).
+static int enqueue_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len) {
     const size_t G = c->devs.size();
-    const bool f32 = c->params.flags & TP3_F32;
     for (size_t g = 0; g < G; ++g) {
         DeviceSlot& s = c->devs[g];
         uint64_t off, cnt;
         split(n, G, g, off, cnt);
         s.last_n = 0;
         if (!cnt) continue;
-        TP3_CUDA(c, cudaSetDevice(s.dev));
-        if (!s.merge_stream) {
-            int prio_lo = 0, prio_hi = 0;  // the single fold CTA should get the first SM slot that frees up
-            TP3_CUDA(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-            TP3_CUDA(c, cudaStreamCreateWithPriority(&s.merge_stream, cudaStreamNonBlocking, prio_hi));
-            TP3_CUDA(c, cudaStreamCreateWithFlags(&s.alt_stream, cudaStreamNonBlocking));
-            TP3_CUDA(c, cudaEventCreateWithFlags(&s.chunk_done, cudaEventDisableTiming));
-            TP3_CUDA(c, cudaEventCreateWithFlags(&s.merge_done, cudaEventDisableTiming));
-            TP3_CUDA(c, cudaEventCreateWithFlags(&s.call_start, cudaEventDisableTiming));
-        }
         const uint32_t range_last = (off + cnt == n) ? last_len : TP3_EVENT_BATCH_SIZE;
-        const uint64_t n_chunks = (chunked && cnt >= 65536) ? 8 : 1;
-        TP3_CUDA(c, cudaStreamWaitEvent(s.merge_stream, s.merge_done, 0));  // previous call's fold (if any) is over
-        // Chunks alternate between two streams: a kernel's last wave leaves most SMs idle, the next chunk's first CTAs
-        // take them (8 chunks back to back on one stream cost 3.5 % more than one launch).
-        cudaStream_t const main_stream = s.stream;
-        if (n_chunks > 1) {
-            TP3_CUDA(c, cudaEventRecord(s.call_start, main_stream));
-            TP3_CUDA(c, cudaStreamWaitEvent(s.alt_stream, s.call_start, 0));  // ordered after earlier work of the context
-        }
-        for (uint64_t k = 0; k < n_chunks; ++k) {
-            const uint64_t lo = cnt * k / n_chunks, hi = cnt * (k + 1) / n_chunks;
-            cudaStream_t const st = (k & 1) ? s.alt_stream : main_stream;
-            s.stream = st;
-            int rc = enqueue_range(c, s, first + off + lo, hi - lo, hi == cnt ? range_last : TP3_EVENT_BATCH_SIZE, lo, cnt);
-            s.stream = main_stream;
-            if (rc) return rc;
-            TP3_CUDA(c, cudaEventRecord(s.chunk_done, st));
-            TP3_CUDA(c, cudaStreamWaitEvent(s.merge_stream, s.chunk_done, 0));
-            if (f32) merge_kernel<float><<<1, kMergeThreads, 0, s.merge_stream>>>(s.d_out + lo, hi - lo, s.d_merged, k == 0);
-            else merge_kernel<double><<<1, kMergeThreads, 0, s.merge_stream>>>(s.d_out + lo, hi - lo, s.d_merged, k == 0);
-            ++c->launches;
-            TP3_CUDA(c, cudaGetLastError());
-        }
-        TP3_CUDA(c, cudaEventRecord(s.merge_done, s.merge_stream));
-        TP3_CUDA(c, cudaStreamWaitEvent(s.stream, s.merge_done, 0));  // the main stream owns the result
-        s.last_first = first + off;
-        s.last_n = cnt;
+        int rc = enqueue_range(c, s, first + off, cnt, range_last, /*fold=*/true);
+        if (rc) return rc;
     }
-    std::vector<tp3_acc> parts;
-    for (auto& s : c->devs) {
+    return TP3_OK;
+}
+
+int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
+    if (!c || !out || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE) {
+        if (c) c->err = "tp3_simulate_merged: bad range";
+        return TP3_E_INVALID;
+    }
+    int rc = enqueue_merged(c, first, n, last_len);
+    if (rc) return rc;
+    const bool in_kernel = !(c->params.flags & TP3_FASTER_EVGEN);
+    std::vector<FoldState> parts(c->devs.size());
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        DeviceSlot& s = c->devs[g];
         if (!s.last_n) continue;
-        tp3_acc h;
         TP3_CUDA(c, cudaSetDevice(s.dev));
-        TP3_CUDA(c, cudaMemcpyAsync(&h, s.d_merged, sizeof h, cudaMemcpyDeviceToHost, s.stream));
-        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
-        parts.push_back(h);
+        TP3_CUDA(c, cudaMemcpyAsync(&parts[g], s.d_fold, sizeof(FoldState), cudaMemcpyDeviceToHost, s.stream));
     }
-    *out = parts[0];
-    for (size_t i = 1; i < parts.size(); ++i) tp3_merge(out, &parts[i], c->params.flags);
+    bool have = false;
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        DeviceSlot& s = c->devs[g];
+        if (!s.last_n) continue;
+        TP3_CUDA(c, cudaSetDevice(s.dev));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        if (in_kernel && (parts[g].lock != 0 || parts[g].next_unit == 0)) {  // every unit was folded and the lock released
+            c->err = "ordered fold did not complete";
+            return TP3_E_CUDA;
+        }
+        // Device partials are merged in device (= batch) order: with several devices the result is a fold of per-device
+        // folds, reproducible for a fixed device count (the reference's FastAccumulator, multi_threading.rs:130-190, is
+        // order-insensitive in the same way); the per-batch path (tp3_simulate_batches + tp3_fold_batches) does not
+        // depend on the device count.
+        if (!have) *out = parts[g].running;
+        else tp3_merge(out, &parts[g].running, c->params.flags);
+        have = true;
+    }
+    return TP3_OK;
+}
+
+// 13 doubles for one ncclReduce(sum): the event count is exact as a double below 2^53.
+__global__ void export_merged_kernel(const FoldState* fs, double* out13) {
+    const int i = threadIdx.x;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&fs->running);
+    if (i == 0) out13[0] = (double)src[0];
+    else if (i < 13) out13[i] = __longlong_as_double((long long)src[i]);
+}
+
+int tp3_simulate_merged_device(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, double* d_out13) {
+    if (!c || !d_out13 || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE || c->devs.size() != 1) {
+        if (c) c->err = "tp3_simulate_merged_device: bad range, or a context with several devices";
+        return TP3_E_INVALID;
+    }
+    int rc = enqueue_merged(c, first, n, last_len);
+    if (rc) return rc;
+    DeviceSlot& s = c->devs[0];
+    export_merged_kernel<<<1, 32, 0, s.stream>>>(s.d_fold, d_out13);
+    ++c->launches;
+    TP3_CUDA(c, cudaGetLastError());
+    return TP3_OK;
+}
+
+int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return TP3_E_INVALID;
+    const std::string k(name);
+    if (k == "unit_batches" && value >= 0 && value <= 4096) c->opt_unit_batches = value;
+    else if (k == "grid_warps" && value >= 0 && value <= (1 << 20)) c->opt_grid_warps = value;
+    else if (k == "f32_scalar") c->opt_f32_scalar = value != 0;
+    else if (k == "fe_split" && (value == 0 || value == 1 || value == 32)) c->opt_fe_split = value;
+    else if (k == "fe_host_scan") c->opt_fe_host_scan = value != 0;
+    else if (k == "fe_xo_seg_units" && value >= 0 && value <= 64) c->opt_fe_xo_seg_units = value;
+    else if (k == "fe_timing") c->opt_fe_timing = value != 0;
+    else {
+        c->err = "tp3_set_option: unknown option or value out of range: " + k;
+        return TP3_E_INVALID;
+    }
+    return TP3_OK;
+}
+
+int tp3_get_stat(tp3_ctx* c, const char* name, int64_t* value) {
+    if (!c || !name || !value) return TP3_E_INVALID;
+    const std::string k(name);
+    if (k == "fe_xo_pass_b") *value = c->stat_fe_xo_pass_b;
+    else {
+        c->err = "tp3_get_stat: unknown statistic: " + k;
+        return TP3_E_INVALID;
+    }
     return TP3_OK;
 }
 
@@ -1055,15 +1152,18 @@ static int run_dump(tp3_ctx* c, uint64_t batch, uint32_t n_events, uint64_t* wor
     DumpArgs d;
     std::memset(&d, 0, sizeof d);
     d.n_events = n_events;
-    if (words) TP3_CUDA(c, cudaMalloc(&d.words, (size_t)n_events * 12 * 8));
+    cudaError_t e = cudaSuccess;  // the buffers allocated so far are freed below whatever fails
+    if (words) e = cudaMalloc(&d.words, (size_t)n_events * 12 * 8);
     if (momenta) {
-        TP3_CUDA(c, cudaMalloc(&d.momenta, (size_t)n_events * 12 * 8));
-        TP3_CUDA(c, cudaMalloc(&d.kept, (size_t)n_events * 4));
-        TP3_CUDA(c, cudaMalloc(&d.m2, (size_t)n_events * 5 * 8));
+        if (e == cudaSuccess) e = cudaMalloc(&d.momenta, (size_t)n_events * 12 * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&d.kept, (size_t)n_events * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d.m2, (size_t)n_events * 5 * 8);
     }
-    pick_dump(c->params)(a, c->params, d, s.stream);
-    ++c->launches;
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        pick_dump(c->params, c->opt_f32_scalar != 0)(a, c->params, d, s.stream);
+        ++c->launches;
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
     if (e == cudaSuccess && words) e = cudaMemcpy(words, d.words, (size_t)n_events * 12 * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && momenta) {

@@ -8,6 +8,20 @@
 // on full warps, then folds its 13 sums with shuffles and writes one 104-byte accumulator.  There is no CTA-level
 // barrier after the prologue, so warps never wait for each other.  What bounds it (the vector register file) and what
 // follows from that is in DESIGN.md section 4d.
+//
+// Scheduling (multi_threading.rs:46-70 hands out batches to workers; here the hand-out is static): the grid is exactly
+// the number of warps the device holds at once (W), and the launch's batches are cut into UNITS of consecutive batches,
+// in batch order: `full_rounds` rounds of W units of `unit_batches` batches each (unit r W + w belongs to warp w), then
+// one last round in which the remaining batches are split evenly over the W warps (sizes differ by at most one batch).
+// Every warp therefore does the same work to within ONE batch whatever the launch size (no wave quantisation), the
+// sequential RANF stream is re-positioned once per unit, and units complete roughly in batch order, which is what the
+// ordered fold below needs.
+//
+// Ordered fold (ResultsAccumulator::merge in batch order, sequential.rs:24-36 / multi_threading.rs:107-126) inside the
+// kernel: a warp that finishes a unit publishes it and then TRIES to take the fold lock; the holder adds every unit
+// that is complete, in unit (= batch) order, to the running accumulator.  Nobody waits: a warp that finds the lock taken
+// goes on simulating, and the holder re-checks after releasing, so a unit published meanwhile is never left behind.
+// The sum is the strict left fold over the batches whichever warps did the adding.
 #pragma once
 
 #include <cstdint>
@@ -63,7 +77,13 @@ struct SimArgs {
     uint64_t n_batches;        // batches in this launch
     uint32_t last_batch_len;   // events in the last batch of the launch
     uint32_t jump_seeding;     // TP3_FASTER_THREADING: batch b starts after b rng.jump()s
-    uint32_t batches_per_warp; // consecutive batches handled by one warp (the RANF stream simply continues)
+    // static schedule (see the head of this file)
+    uint32_t n_warps;          // W: warps in the grid
+    uint32_t unit_batches;     // consecutive batches per unit in the full rounds (the RANF stream simply continues inside a unit)
+    uint32_t full_rounds;      // rounds of W full units; the rest is split evenly in one more round
+    uint32_t epoch;            // value that marks a unit of THIS launch as done in unit_done
+    uint32_t* unit_done;       // [(full_rounds + 1) * W], or null: no in-kernel fold
+    struct FoldState* fold;    // running accumulator of the ordered fold, or null
     const uint32_t* ranf_table;        // [kRanfDigits][256][55]
     const uint64_t* xo_batch_states;   // [n_batches][4] from the seeding kernel
     const uint64_t* xo_lane_polys;     // [32][4] jump polynomial of each lane's offset in the batch
@@ -74,6 +94,14 @@ struct SimArgs {
     uint32_t hist_bins;
     unsigned long long* hist_counts;   // [TP3_HIST_OBSERVABLES][hist_bins]
     double* hist_weights;              // [kHistReplicas][TP3_HIST_OBSERVABLES][hist_bins]
+};
+
+// Ordered fold of a launch (one per device slot, reset by the host before the launch).
+struct FoldState {
+    uint32_t lock;                 // 0 free, 1 held
+    uint32_t pad;
+    unsigned long long next_unit;  // first unit that has not been added yet
+    tp3_acc running;               // fold of the batches of units [0, next_unit)
 };
 
 struct DumpArgs {
@@ -333,6 +361,94 @@ __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
     return (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
 }
 
+// Batches [lo, hi) of the launch that make up unit u.
+__device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint64_t n_batches, uint64_t u,
+                                           uint64_t& lo, uint64_t& hi) {
+    const uint64_t W = n_warps, full = (uint64_t)full_rounds * W;
+    if (u < full) {
+        lo = u * unit_batches;
+        hi = lo + unit_batches;
+    } else {
+        const uint64_t base = full * unit_batches, rem = n_batches - base, w = u - full;
+        lo = base + rem * w / W;
+        hi = base + rem * (w + 1) / W;
+    }
+}
+__device__ __forceinline__ void unit_range(const SimArgs& a, uint64_t u, uint64_t& lo, uint64_t& hi) {
+    unit_range(a.n_warps, a.full_rounds, a.unit_batches, a.n_batches, u, lo, hi);
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_sc() { asm volatile("fence.sc.gpu;" ::: "memory"); }
+
+// Publish unit u (its accumulators are in a.out) and fold whatever is ready.  Called by all lanes of the warp.
+// F is the run's Float: under f32 the merge adds in f32 (resacc.rs:133-139 on f32 fields), like tp3_merge.
+// (The schedule is passed by value: a reference to the kernel's parameter block would force a local-memory copy of it.)
+template <class F>
+__device__ __noinline__ void fold_publish(FoldState* fs, uint32_t* unit_done, const tp3_acc* out, uint32_t n_warps, uint32_t full_rounds,
+                                          uint32_t unit_batches, uint32_t epoch, uint64_t n_batches, uint64_t u, int lane) {
+    const uint64_t n_units = ((uint64_t)full_rounds + 1) * n_warps;
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();  // this unit's accumulators (written by lane 0) before the flag
+        *reinterpret_cast<volatile uint32_t*>(unit_done + u) = epoch;
+    }
+    for (;;) {
+        uint32_t got = 0;
+        if (lane == 0) {
+            fence_sc();  // flag store (or lock release below) before the lock read: the other side does the mirror image
+            got = atomicCAS(&fs->lock, 0u, 1u) == 0u;
+            if (got) __threadfence();
+        }
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (!got) return;  // the holder re-checks after it releases
+        uint64_t nu = *reinterpret_cast<volatile unsigned long long*>(&fs->next_unit);
+        // lane k < 12 carries field k (spm2[5], vars[5], sigma, variance), lane 12 the event count
+        const unsigned long long* run = reinterpret_cast<const unsigned long long*>(&fs->running);
+        F acc = 0;
+        uint64_t cnt = 0;
+        if (nu > 0) {
+            if (lane < 12) acc = (F)__longlong_as_double((long long)__ldcg(run + 1 + lane));
+            else if (lane == 12) cnt = __ldcg(run);
+        }
+        while (nu < n_units && ld_acquire_u32(unit_done + nu) == epoch) {
+            uint64_t lo, hi;
+            unit_range(n_warps, full_rounds, unit_batches, n_batches, nu, lo, hi);
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(out + lo);
+            for (uint64_t b = lo; b < hi; b += 8) {  // loads first, then the dependent chain of additions
+                unsigned long long v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = (b + j < hi && lane < 13) ? __ldcg(src + (b - lo + j) * 13 + (lane < 12 ? 1 + lane : 0)) : 0ull;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (b + j < hi) {
+                        if (lane < 12) acc += (F)__longlong_as_double((long long)v[j]);
+                        else cnt += v[j];
+                    }
+                }
+            }
+            ++nu;
+        }
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&fs->running);
+        if (lane < 12) __stcg(dst + 1 + lane, (unsigned long long)__double_as_longlong((double)acc));
+        else if (lane == 12) __stcg(dst, (unsigned long long)cnt);
+        __syncwarp();
+        bool again = false;
+        if (lane == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(&fs->next_unit) = nu;
+            __threadfence();
+            atomicExch(&fs->lock, 0u);
+            fence_sc();
+            again = nu < n_units && ld_acquire_u32(unit_done + nu) == epoch;  // published while we held the lock?
+        }
+        if (!__shfl_sync(0xffffffffu, (uint32_t)again, 0)) return;
+    }
+}
+
 template <class F, int RNG, bool SORT, bool LITERAL, bool HIST = false>
 __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LITERAL, HIST)) simulate_kernel(const SimArgs a, const PhysParams<F> P) {
     constexpr int kWarps = sim_warps(LITERAL, HIST), kThreads = 32 * kWarps;  // this kernel's CTA shape
@@ -357,12 +473,14 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
     constexpr bool kSort = SORT && LITERAL;
 
     WarpRng<F, RNG> rng;
-    const uint64_t slot0 = ((uint64_t)blockIdx.x * kWarps + warp) * a.batches_per_warp;
-  for (uint32_t bi = 0; bi < a.batches_per_warp; ++bi) {
-    const uint64_t slot = slot0 + bi;
-    if (slot >= a.n_batches) break;
+    const uint64_t wid = (uint64_t)blockIdx.x * kWarps + warp;
+  for (uint32_t round = 0; round <= a.full_rounds; ++round) {
+    const uint64_t unit = (uint64_t)round * a.n_warps + wid;
+    uint64_t unit_lo, unit_hi;
+    unit_range(a, unit, unit_lo, unit_hi);
+  for (uint64_t slot = unit_lo; slot < unit_hi; ++slot) {
     const int n_ev = batch_len(a, slot);
-    if (bi == 0 || !rng.next_batch(a, n_ev, lane)) rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
+    if (slot == unit_lo || !rng.next_batch(a, n_ev, lane)) rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
 
 #if TP3_ACC_SMEM
     SmemLaneAcc<F> acc{sm.acc[warp], lane, 0};
@@ -470,6 +588,8 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
     }
     __syncwarp();
   }
+    if (a.fold) fold_publish<F>(a.fold, a.unit_done, a.out, a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+  }
     if (HIST) {  // CTA histograms -> device histograms
         __syncthreads();
         for (int i = threadIdx.x; i < hist_n; i += kThreads) {
@@ -496,12 +616,14 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
     const FastMath fm{nullptr, nullptr};  // the f32 elementary functions are SFU instructions, no tables
 
     WarpRng<F, RNG> rng;
-    const uint64_t slot0 = ((uint64_t)blockIdx.x * kWarps + warp) * a.batches_per_warp;
-    for (uint32_t bi = 0; bi < a.batches_per_warp; ++bi) {
-        const uint64_t slot = slot0 + bi;
-        if (slot >= a.n_batches) break;
+    const uint64_t wid = (uint64_t)blockIdx.x * kWarps + warp;
+  for (uint32_t round = 0; round <= a.full_rounds; ++round) {
+    const uint64_t unit = (uint64_t)round * a.n_warps + wid;
+    uint64_t unit_lo, unit_hi;
+    unit_range(a, unit, unit_lo, unit_hi);
+    for (uint64_t slot = unit_lo; slot < unit_hi; ++slot) {
         const int n_ev = batch_len(a, slot);
-        if (bi == 0 || !rng.next_batch(a, n_ev, lane)) rng.init(a, &smw[warp], a.first_batch + slot, slot, n_ev, lane);
+        if (slot == unit_lo || !rng.next_batch(a, n_ev, lane)) rng.init(a, &smw[warp], a.first_batch + slot, slot, n_ev, lane);
 
         f2 spm2[5], vars[5], sigma(0.0f), variance(0.0f);
 #pragma unroll
@@ -634,6 +756,8 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
         }
         __syncwarp();
     }
+    if (a.fold) fold_publish<float>(a.fold, a.unit_done, a.out, a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+  }
 }
 
 // Parity hook: same streams, same event -> lane mapping, per-event outputs instead of sums.
@@ -682,6 +806,62 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
             for (int c = 0; c < 4; ++c) d.momenta[((size_t)e * 3 + q) * 4 + c] = (double)p[q][c];
         d.kept[e] = k;
         for (int c = 0; c < 5; ++c) d.m2[(size_t)e * 5 + c] = (double)m[c];
+    }
+}
+
+// Parity hook for the shipped f32 kernel: the per-event outputs of simulate_kernel_x2's PACKED physics (two events per
+// lane through gen_event<f2>, keep_event<f2>, me_fast<f2>), same streams and the same pairing of warp iterations.
+template <int RNG>
+__global__ void __launch_bounds__(32) dump_kernel_x2(const SimArgs a, const PhysParams<f2> P, const DumpArgs d) {
+    using F = float;
+    using Word = typename RawWord<F, RNG>::type;
+    __shared__ WarpSmem<F, kQueue2, 3> smw;
+    const int lane = threadIdx.x & 31;
+    const FastMath fm{nullptr, nullptr};
+    WarpRng<F, RNG> rng;
+    rng.init(a, &smw, a.first_batch, 0, batch_len(a, 0), lane);
+    const int n_it = rng.iterations();
+    for (int it = 0; it < n_it; it += 2) {
+        Word w0[12], w1[12];
+        rng.draws(it, lane, w0);
+        const bool have_b = it + 1 < n_it;
+        if (have_b) {
+            rng.begin_next(lane);
+            rng.template tick<1>(lane); rng.template tick<2>(lane); rng.template tick<3>(lane); rng.template tick<4>(lane);
+            rng.template tick<5>(lane); rng.template tick<6>(lane); rng.template tick<7>(lane);
+            rng.draws(it + 1, lane, w1);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) w1[j] = w0[j];
+        }
+        if (it + 2 < n_it) {
+            rng.begin_next(lane);
+            rng.template tick<1>(lane); rng.template tick<2>(lane); rng.template tick<3>(lane); rng.template tick<4>(lane);
+            rng.template tick<5>(lane); rng.template tick<6>(lane); rng.template tick<7>(lane);
+        }
+        f2 u[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) u[j] = f2(WarpRng<F, RNG>::uniform(w0[j], (j & 3) == 1, P.fc), WarpRng<F, RNG>::uniform(w1[j], (j & 3) == 1, P.fc));
+        f2 p[3][4];
+        NoTick no_tick;
+        gen_event<f2, false, false>(u, P.e_total, fm, p, no_tick);
+        const m2 ok = keep_event<f2, false, false>(p, P);
+        f2 m[5];
+        me_fast<f2>(p, P, m);
+        const int ev[2] = {rng.event_of(it, lane), have_b ? rng.event_of(it + 1, lane) : -1};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int e = ev[h];
+            if (e < 0 || e >= (int)d.n_events) continue;
+            if (d.words)
+                for (int j = 0; j < 12; ++j) d.words[(size_t)e * 12 + j] = (uint64_t)(h ? w1[j] : w0[j]);
+            if (!d.momenta) continue;
+            const bool k = h ? ok.y : ok.x;
+            for (int q = 0; q < 3; ++q)
+                for (int c = 0; c < 4; ++c) d.momenta[((size_t)e * 3 + q) * 4 + c] = (double)(h ? p[q][c].hi() : p[q][c].lo());
+            d.kept[e] = k;
+            for (int c = 0; c < 5; ++c) d.m2[(size_t)e * 5 + c] = k ? (double)(h ? m[c].hi() : m[c].lo()) : 0.0;
+        }
     }
 }
 

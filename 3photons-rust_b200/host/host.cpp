@@ -11,6 +11,7 @@
 // All arithmetic is done in the run's Float (f32 under TP3_F32) and carried across the C ABI
 // as exactly-widened doubles.
 #include <charconv>
+#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -408,25 +409,40 @@ size_t emit(const std::string& s, char* buf, size_t cap) {
     return s.size();
 }
 
-bool parse_bool_item(std::string s, bool& ok) {  // config.rs:187-195
-    for (auto& ch : s) ch = (char)std::tolower((unsigned char)ch);
+bool parse_bool_item(const std::string& s, bool& ok) {  // config.rs:187-195
+    // lower-cased only for the FORTRAN forms; anything else goes to Rust's bool parser, which takes exactly "true" / "false"
+    std::string low = s;
+    for (auto& ch : low) ch = (char)std::tolower((unsigned char)ch);
     ok = true;
-    if (s == ".true." || s == "true") return true;
-    if (s == ".false." || s == "false") return false;
+    if (low == ".true.") return true;
+    if (low == ".false.") return false;
+    if (s == "true") return true;
+    if (s == "false") return false;
     ok = false;
     return false;
 }
 
 template <class T> bool parse_num(const std::string& s, T& out) {
     // Rust's FromStr rejects trailing garbage and leading whitespace; accepts "0.e0", "91.187e0", "+1"
-    if (s.empty()) return false;
+    if (s.empty() || std::isspace((unsigned char)s[0])) return false;
     char* end = nullptr;
-    if constexpr (std::is_same<T, float>::value) out = std::strtof(s.c_str(), &end);
-    else if constexpr (std::is_same<T, double>::value) out = std::strtod(s.c_str(), &end);
-    else if constexpr (std::is_same<T, uint64_t>::value) {
+    errno = 0;
+    if constexpr (std::is_floating_point<T>::value) {
+        // what strtod takes and Rust's f64::from_str does not: hexadecimal floats and nan(...) payloads
+        for (char ch : s)
+            if (ch == 'x' || ch == 'X' || ch == '(') return false;
+        if constexpr (std::is_same<T, float>::value) out = std::strtof(s.c_str(), &end);
+        else out = std::strtod(s.c_str(), &end);
+        // (out-of-range decimals parse to inf / 0 in Rust as well: ERANGE is not an error here)
+    } else if constexpr (std::is_same<T, uint64_t>::value) {
         if (s[0] == '-') return false;
         out = std::strtoull(s.c_str(), &end, 10);
-    } else out = (T)std::strtol(s.c_str(), &end, 10);
+        if (errno == ERANGE) return false;  // Rust: "number too large to fit in target type"
+    } else {
+        const long v = std::strtol(s.c_str(), &end, 10);
+        if (errno == ERANGE || v < INT32_MIN || v > INT32_MAX) return false;
+        out = (T)v;
+    }
     return end && *end == 0;
 }
 
@@ -507,6 +523,13 @@ int tp3_merge(tp3_acc* into, const tp3_acc* other, uint32_t flags) {
     return TP3_OK;
 }
 
+int tp3_fold_batches(const tp3_acc* per_batch, uint64_t n, uint32_t flags, tp3_acc* out) {
+    if (!per_batch || !out || n == 0) return TP3_E_INVALID;
+    *out = per_batch[0];  // the fold starts FROM the first batch (sequential.rs:24-26)
+    for (uint64_t b = 1; b < n; ++b) tp3_merge(out, &per_batch[b], flags);
+    return TP3_OK;
+}
+
 int tp3_finalize(const tp3_config* cfg, uint32_t flags, const tp3_acc* merged, tp3_final* out) {
     if (!cfg || !merged || !out) return TP3_E_INVALID;
     if (flags & TP3_F32) finalize_t<float>(*cfg, *merged, *out);
@@ -554,15 +577,14 @@ int tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint3
     // left fold in batch order (sequential.rs:24-36)
     const uint64_t nb = (cfg.num_events + TP3_EVENT_BATCH_SIZE - 1) / TP3_EVENT_BATCH_SIZE;
     const uint32_t last = (uint32_t)(cfg.num_events - (nb - 1) * TP3_EVENT_BATCH_SIZE);
-    std::vector<tp3_acc> per_batch(nb);
-    rc = tp3_simulate_batches(ctx, 0, nb, last, per_batch.data());
+    // (tp3_simulate_merged: the same left fold, done on the device while the batches are simulated)
+    tp3_acc total;
+    rc = tp3_simulate_merged(ctx, 0, nb, last, &total);
     if (rc) {
         emit(tp3_last_error(ctx), stdout_buf, stdout_cap);
         tp3_destroy(ctx);
         return rc;
     }
-    tp3_acc total = per_batch[0];
-    for (uint64_t b = 1; b < nb; ++b) tp3_merge(&total, &per_batch[b], flags);
     tp3_final fin;
     tp3_finalize(&cfg, flags, &total, &fin);
     // ... and stops it before output (main.rs:138)
@@ -608,12 +630,17 @@ int tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint3
     {  // output.rs:148-173
         std::ofstream f(dir + "pil.mc", std::ios::app);
         if (!f) return TP3_E_IO;
-        auto col = [&](int i) { return fin.spm2[0][i] + fin.spm2[1][i]; };
-        const double r1 = col(0), r2 = col(1) * cfg.beta_plus * cfg.beta_plus, r3 = col(2) * cfg.beta_minus * cfg.beta_minus,
-                     r4 = col(3) * cfg.beta_plus;
         f << stamp << "\n";
-        f << disp(cfg.e_total) << " " << disp(r1 / 4) << " " << disp(r2 / 4) << " " << disp(r3 / 4) << " " << disp(r4 / 4) << " "
-          << disp((r1 + r2 + r3 + r4) / 4) << " " << disp(fin.sigma) << "\n";
+        auto line = [&](auto zero) {  // in the run's Float, like every other number the reference prints
+            using F = decltype(zero);
+            auto col = [&](int i) { return (F)((F)fin.spm2[0][i] + (F)fin.spm2[1][i]); };
+            const F bp = (F)cfg.beta_plus, bm = (F)cfg.beta_minus;
+            const F r1 = col(0), r2 = col(1) * (bp * bp), r3 = col(2) * (bm * bm), r4 = col(3) * bp;
+            f << disp(cfg.e_total) << " " << disp(r1 / (F)4) << " " << disp(r2 / (F)4) << " " << disp(r3 / (F)4) << " " << disp(r4 / (F)4)
+              << " " << disp((r1 + r2 + r3 + r4) / (F)4) << " " << disp(fin.sigma) << "\n";
+        };
+        if (f32) line(0.0f);
+        else line(0.0);
     }
     return TP3_OK;
 }

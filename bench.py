@@ -6,22 +6,28 @@
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's CPU path (oracle restatement)
 
-Workload (BASELINE.json configs[4], the configuration the metric is quoted on): the default
-`valeurs` with num_events = 10^10 per GPU, i.e. 10^6 batches of 10 000 events (scheduling/mod.rs:21),
-default features (f64, RANF, sorted photons).  The run's batch range is sharded contiguously over the
-ranks with no data-path collective (weak scaling by default: N GPUs simulate N x 10^10 events;
---scaling strong splits 10^10 events over the ranks); the rank results are gathered and folded on
-rank 0 for the end-to-end number.
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): ONE run of the default
+`valeurs` with num_events = 10^10, i.e. 10^6 batches of 10 000 events (scheduling/mod.rs:21), default
+features (f64, RANF, sorted photons), its batch range sharded contiguously over the N ranks with no
+data-path collective (multi_threading.rs:25,46-70): strong scaling, the default.  `--scaling weak` gives
+every GPU 10^10 events instead (N x 10^10 in total) and is reported as a sub-record of the same line.
 
-A "step" is one pass of the fused kernel over this rank's batch range.
+A "step" is one pass of the fused kernel (with its in-kernel ordered fold) over this rank's batch range.
   value : whole-job events/s, device time (CUDA events on the launching stream, max over ranks),
-          everything the kernel reads (jump table, parameters) already resident in HBM.
-  e2e   : same metric through the C ABI call with HOST buffers (tp3_simulate_batches: launch +
-          device->host copy of the per-batch accumulators), plus gather + ordered fold + finalize.
-  roofline: the path is FP64-pipe bound (no tensor cores, ~0.01 B/event of HBM traffic), so the
-          roofline is achieved algorithmic FP64 TFLOP/s (833 flop per generated event, SURVEY.md
-          §8d) over the DFMA peak measured live on this GPU by tp3_peak_probe (MEASURED_PEAKS.json
-          carries no FP64 figure).
+          everything the kernel reads (jump table, parameters) already resident in HBM; the merged
+          accumulator stays in HBM.
+  e2e   : the same metric through the call INTEGRATION.md tells a maintainer to bind: tp3_simulate_merged
+          into a HOST accumulator (N = 1), or tp3_simulate_merged_device + ONE ncclReduce(sum) of the 13
+          doubles to rank 0 + a 104-byte device->host copy (N > 1), then finalize() on the host.
+  e2e_per_batch : the per-batch form of the boundary (tp3_simulate_batches into a host array of one
+          accumulator per batch + the host left fold tp3_fold_batches + finalize).
+  roofline: the path is FP64-pipe bound (no tensor cores, ~0.01 B/event of HBM traffic).  `achieved` /
+          `frac` follow SURVEY.md section 8d: algorithmic FP64 TFLOP/s (833 flop per generated event as
+          the reference writes them) over the DFMA peak measured live on this GPU by tp3_peak_probe
+          (MEASURED_PEAKS.json carries no FP64 figure).  Because the fast kernel EXECUTES fewer flops
+          than the reference writes, `executed_tflops` / `frac_executed` (SASS-counted FP64 flops per
+          event from the committed ncu capture) and `pipe_active` (ncu FP64-pipe active fraction) are
+          given next to it.
 """
 import argparse
 import ctypes
@@ -46,11 +52,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--events", type=float, default=1e10, help="events per step PER GPU (weak) or in total (strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--events", type=float, default=1e10, help="events per step in total (strong) or PER GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--no-weak-subrecord", action="store_true", help="N > 1, strong: skip the extra weak-scaling measurement")
     ap.add_argument("--features", default="", help="cargo-style feature list, e.g. f32,standard-random")
     ap.add_argument("--kernel", default="fast", choices=["fast", "literal"])
-    ap.add_argument("--cpu-sample-events", type=float, default=5e7)
+    ap.add_argument("--cpu-sample-events", type=float, default=2e8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -67,10 +74,33 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+ORACLE_NATIVE_FLAGS = ["-O3", "-march=native", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-pthread"]
+_oracle_build = None
+
+
+def native_oracle():
+    """The CPU baseline is rebuilt ON THIS BOX with -O3 -march=native (-ffp-contract=off stays: the
+    Rust reference never fuses a*b+c).  Falls back to the portable prebuilt library if there is no compiler."""
+    global _oracle_build
+    if _oracle_build is None:
+        import oracle_lib  # CPU baseline leg: the only place bench.py executes oracle/
+        out = os.path.join(ROOT, "oracle", "_build", "liboracle_native.so")
+        cmd = ["g++"] + ORACLE_NATIVE_FLAGS + ["-shared", "-o", out, os.path.join(ROOT, "oracle", "oracle_main.cpp")]
+        try:
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run(cmd, check=True, capture_output=True, timeout=300)
+            oracle_lib.use_library(out)
+            _oracle_build = "g++ " + " ".join(ORACLE_NATIVE_FLAGS) + " (built on this box)"
+        except (OSError, subprocess.SubprocessError) as e:
+            _oracle_build = f"prebuilt -O2 library (native rebuild failed: {type(e).__name__})"
+    return _oracle_build
+
+
 def cpu_reference_rate(n_events, threads):
     """events/s of the CPU oracle run with the reference's `multi-threading` semantics (one task
     per batch, scheduler thread pre-advances the RNG, ordered merge) on `threads` host threads."""
     import oracle_lib  # CPU baseline leg: the only place bench.py executes oracle/
+    native_oracle()
     run = oracle_lib.run(valeurs_text(), REFERENCE_FEATURES, threads=threads, num_events=int(n_events),
                          want_batches=False, want_text=False)
     return n_events / run.seconds, run.seconds
@@ -115,12 +145,23 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": power}
 
 
+def config_dict(args, world, n_events, nb):
+    """`config` of the JSON line: the same dictionary for both arms (the reference arm times a bounded sample of it)."""
+    strong = args.scaling == "strong"
+    workload = (f"default valeurs, ONE run of num_events={n_events:.3g} ({nb} batches of 10000; BASELINE configs[4], the shape of "
+                f"configs[1]) sharded over {world} GPU(s) by contiguous batch ranges") if strong else (
+                f"default valeurs, num_events={n_events:.3g} = {args.events:.3g} per GPU ({nb} batches of 10000), contiguous batch ranges per GPU")
+    return {"workload": workload, "features": args.features or "default (f64, RANF, photon sorting)", "kernel": args.kernel,
+            "l2": "not applicable: no input tensors; the kernel reads a 281 KB jump table and writes 104 B per batch"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path, all host threads."""
     if rank != 0:
         return
     threads = host_threads()
     sample = args.cpu_sample_events
+    n_total = int(args.events) * (args.gpus if args.scaling == "weak" else 1)
     for _ in range(args.warmup):
         cpu_reference_rate(min(sample, 2e6), threads)
     t = 0.0
@@ -130,17 +171,23 @@ def run_reference(args, rank):
     rate = sample * args.steps / t
     unit = "events/s"
     desc = (f"{sample:.3g} events of the default valeurs per step (bounded sample of the 1e10-event workload), "
-            f"C++ restatement of the reference's `multi-threading` build (oracle/), {threads} threads")
+            f"C++ restatement of the reference's `multi-threading` build (oracle/), {threads} threads, {native_oracle()}")
     print(json.dumps({
         "impl": "reference", "metric": "events/sec", "value": rate, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "default valeurs shape, 1e10 events (configs[4]); CPU arm times a bounded sample",
-                   "features": REFERENCE_FEATURES},
+        "config": config_dict(args, args.gpus, n_total, (n_total + 9999) // 10000),
+        "reference_build": f"cargo features `{REFERENCE_FEATURES}` (same numbers as the default features: the reference's golden is shared)",
         "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+# FP64 work the shipped fast f64 kernel EXECUTES per generated event (SASS-counted from the committed ncu capture:
+# DFMA = 2 flops, DMUL / DADD = 1), and the ncu FP64-pipe active fraction of the bench's own launch.
+EXECUTED = {"source": "profiles/r01_final2_fast_f64_ranf.txt, profiles/r01_bench_kernel_1e10_events.txt",
+            "dfma": 161.0, "dmul": 108.0, "dadd": 54.0, "pipe_active": 0.693}
 
 
 def main():
@@ -162,21 +209,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    # weak scaling (default): every GPU gets the 1e10-event workload, i.e. the run has N x 1e10 events and
-    # is sharded by contiguous batch ranges; strong: the 1e10 events are split over the N GPUs.
-    n_events = int(args.events) * (world if args.scaling == "weak" else 1)
-    cfg = pkg.Configuration.parse(valeurs_text(), args.features).with_num_events(n_events)
     kernel = pkg.KERNEL_FAST if args.kernel == "fast" else pkg.KERNEL_LITERAL
-    nb, last = pkg.batch_layout(n_events)
-    lo, cnt = pkg.shard_range(nb, world, rank)
-    my_last = last if lo + cnt == nb else pkg.EVENT_BATCH_SIZE
-    my_events = (cnt - 1) * pkg.EVENT_BATCH_SIZE + my_last if cnt else 0
-
-    sim = pkg.Simulator(cfg, kernel, devices=[local_rank])
     stream = torch.cuda.current_stream()
-    sim.set_stream(stream.cuda_stream)
-    peak_tflops = sim.peak_probe(1 if "f32" in args.features else 0)
+    warmup = max(args.warmup, 3)
 
     def barrier():
         torch.cuda.synchronize()
@@ -184,112 +219,161 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def over_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def measure(scaling, steps, with_e2e):
+        """One configuration: strong = ONE run of args.events events sharded over the ranks (configs[4] as written),
+        weak = args.events per GPU."""
+        n_events = int(args.events) * (world if scaling == "weak" else 1)
+        cfg = pkg.Configuration.parse(valeurs_text(), args.features).with_num_events(n_events)
+        nb, last = pkg.batch_layout(n_events)
+        lo, cnt = pkg.shard_range(nb, world, rank)  # multi_threading.rs:25,46-70: contiguous batch ranges
+        my_last = last if lo + cnt == nb else pkg.EVENT_BATCH_SIZE
+        sim = pkg.Simulator(cfg, kernel, devices=[local_rank])
+        sim.set_stream(stream.cuda_stream)
+        out13 = torch.zeros(13, dtype=torch.float64, device="cuda")
+        res = {"n_events": n_events, "nb": nb, "cfg": cfg, "sim": sim}
 
-    # ---- device-resident timing ("value") --------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        sim.simulate_batches_device(lo, cnt, my_last)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = sim.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        sim.simulate_batches_device(lo, cnt, my_last)
-    ev1.record(stream)
-    barrier()
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = int(sum_over_ranks(sim.launch_count - launches0))
-    clocks = sampler.stop()
-    value = n_events * args.steps / (dev_ms * 1e-3)
+        def step_device():
+            sim.simulate_merged_device(lo, cnt, my_last, out13.data_ptr())
 
-    # ---- end to end through the C ABI with host buffers ("e2e") -----------------------------
-    # What a caller of the reference's run_simulation gets: the merged accumulator of the whole run,
-    # finalized. Per rank: tp3_simulate_merged = launch + on-device ordered fold + D2H of one 104-byte
-    # accumulator into host memory; the rank partials are gathered (gloo-sized payload, sent over NCCL)
-    # and folded in rank order on rank 0, then finalize() runs on the host.
-    acc_bytes = ctypes.sizeof(pkg.Acc)
+        # ---- device-resident timing ("value") ----
+        for _ in range(warmup):
+            step_device()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = sim.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            step_device()
+        ev1.record(stream)
+        barrier()
+        res["dev_ms"] = over_ranks(ev0.elapsed_time(ev1), dist.ReduceOp.MAX)
+        res["launches"] = int(over_ranks(sim.launch_count - launches0, dist.ReduceOp.SUM))
+        res["clocks"] = sampler.stop()
+        res["value"] = n_events * steps / (res["dev_ms"] * 1e-3)
+        if not with_e2e:
+            return res
 
-    def e2e_step():
-        mine = sim.simulate_merged(lo, cnt, my_last)
-        if world > 1:
+        # ---- end to end through the C ABI ("e2e"): what a caller of the reference's run_simulation gets — the merged
+        # accumulator of the whole run on the HOST, finalized.
+        def e2e_step():
+            if world == 1:
+                return pkg.finalize(cfg, sim.simulate_merged(lo, cnt, my_last))
+            step_device()
+            dist.reduce(out13, dst=0, op=dist.ReduceOp.SUM)  # the run's one inter-GPU exchange: 13 doubles
+            if rank != 0:
+                torch.cuda.synchronize()
+                return None
+            return pkg.finalize(cfg, pkg.acc_from_f64x13(out13.cpu().tolist()))  # 104-byte device->host copy
+
+        for _ in range(2):
+            fin = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fin = e2e_step()
+        barrier()
+        e2e_s = over_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX)
+        res["e2e"] = n_events * steps / e2e_s
+        res["fin"] = fin
+
+        # ---- the per-batch form of the boundary: one accumulator per batch into a host array + host left fold ----
+        host = (pkg.Acc * cnt)()
+
+        def per_batch_step():
+            sim._check(pkg.lib().tp3_simulate_batches(sim._h, lo, cnt, my_last, host))
+            mine = pkg.fold(host, cfg.flags)
+            if world == 1:
+                return pkg.finalize(cfg, mine)
             t = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).cuda()
-            parts = [torch.empty(acc_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-            dist.gather(t, parts, dst=0)
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
             if rank != 0:
                 return None
             accs = [pkg.Acc.from_buffer_copy(p.cpu().numpy().tobytes()) for p in parts]
-            total = pkg.fold(accs, cfg.flags)
-        else:
-            total = mine
-        return pkg.finalize(cfg, total)
+            return pkg.finalize(cfg, pkg.fold(accs, cfg.flags))
 
-    fin = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fin = e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = n_events * args.steps / e2e_s
+        per_batch_step()
+        barrier()
+        n_pb = max(1, min(steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_pb):
+            fin_pb = per_batch_step()
+        barrier()
+        res["e2e_per_batch"] = n_events * n_pb / over_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX)
+        res["fin_pb"] = fin_pb
+        res["d2h_per_batch"] = nb * ctypes.sizeof(pkg.Acc)
+        return res
 
-    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    main_res = measure(args.scaling, args.steps, True)
+    sim = main_res["sim"]
+    peak_tflops = sim.peak_probe(1 if "f32" in args.features else 0)
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak_subrecord:
+        w = measure("weak", max(2, min(args.steps, 5)), False)
+        weak = {"value": w["value"], "unit": "events/s", "events_per_gpu": int(args.events), "ms_per_step": w["dev_ms"] / max(2, min(args.steps, 5))}
+        w["sim"].close()
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
+        cpu_reference_rate(2e6, threads)
         rate, secs = cpu_reference_rate(args.cpu_sample_events, threads)
         cpu = {"value": rate, "unit": "events/s", "cores": threads, "kind": "port",
                "sample": f"{args.cpu_sample_events:.3g} events of the default valeurs ({secs:.2f} s), C++ restatement of "
-                         f"the reference's `multi-threading` build, {threads} threads"}
+                         f"the reference's `multi-threading` build, {threads} threads, {native_oracle()}"}
 
     if rank == 0:
+        n_events, nb, cfg, value, dev_ms = main_res["n_events"], main_res["nb"], main_res["cfg"], main_res["value"], main_res["dev_ms"]
         achieved = value / world * FLOP_PER_EVENT / 1e12  # per GPU, to compare with a per-GPU peak
         f32 = "f32" in args.features
+        default_f64 = not args.features and args.kernel == "fast"
+        acc_bytes = ctypes.sizeof(pkg.Acc)
+        exec_flop = 2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]
         # bytes per launch, from the committed ncu capture of exactly this launch shape (default features, 1e6 batches)
-        ncu_traffic = 58799360 if (not args.features and args.kernel == "fast" and nb // world == 1000000) else None
+        ncu_traffic = 58799360 if (default_f64 and nb // world == 1000000) else None
+        fin, fin_pb = main_res["fin"], main_res["fin_pb"]
         line = {
             "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if f32 else "f64", "data": "synthetic",
-            "config": {"workload": f"default valeurs, num_events={n_events:.3g} ({nb} batches of 10000; BASELINE configs[4] = 1e10 events "
-                                   f"{'per GPU' if args.scaling == 'weak' else 'in total'}, the shape of configs[1]); contiguous batch ranges per GPU",
-                       "features": args.features or "default (f64, RANF, photon sorting)", "kernel": args.kernel,
-                       "l2": "not applicable: no input tensors; the kernel reads a 281 KB jump table and writes 104 B per batch"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": world * 8 * (312 + 296),
-                    "d2h_bytes_per_step": world * acc_bytes,
-                    "note": "tp3_simulate_merged into a host tp3_acc + finalize(); the only host->device payload is the kernel "
-                            "argument block (SimArgs 312 B + PhysParams 296 B, sizes pinned by a static_assert in api.cu) of the 8 chunk launches per GPU"},
-            "gpu_launches": launches,
+            "config": config_dict(args, world, n_events, nb),
+            "clocks": main_res["clocks"],
+            "e2e": {"value": main_res["e2e"], "unit": "events/s", "h2d_bytes_per_step": world * int(pkg.lib().tp3_kernel_arg_bytes()),
+                    "d2h_bytes_per_step": acc_bytes,
+                    "note": "tp3_simulate_merged into a host tp3_acc + finalize() (N = 1); tp3_simulate_merged_device + one ncclReduce(sum) of 13 "
+                            "doubles + 104-byte D2H on rank 0 + finalize() (N > 1). The only host->device payload is the kernel argument block."},
+            "e2e_per_batch": {"value": main_res["e2e_per_batch"], "unit": "events/s", "d2h_bytes_per_step": main_res["d2h_per_batch"],
+                              "note": "tp3_simulate_batches into a host array (one 104-byte accumulator per batch) + tp3_fold_batches on the host + finalize()"},
+            "gpu_launches": main_res["launches"],
             "roofline": {"bound": "fp64" if not f32 else "fp32", "achieved": achieved, "peak": peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": ncu_traffic,
+                         "frac_note": "SURVEY.md section 8d convention: 833 flop per generated event AS THE REFERENCE WRITES THEM over the measured DFMA peak; "
+                                      "the fast kernel executes fewer (see executed_*), so this is reference-equivalent throughput, not pipe utilisation",
+                         "executed_flop_per_event": exec_flop if default_f64 else None,
+                         "executed_tflops": value / world * exec_flop / 1e12 if default_f64 else None,
+                         "frac_executed": value / world * exec_flop / 1e12 / peak_tflops if default_f64 else None,
+                         "pipe_active": EXECUTED["pipe_active"] if default_f64 else None,
+                         "executed_source": EXECUTED["source"] if default_f64 else None,
                          "traffic_note": None if ncu_traffic is None else
-                                         "DRAM bytes of one launch of the default f64 kernel over 1e6 batches, ncu --set full "
-                                         "(profiles/r01_bench_kernel_1e10_events.txt): 0.27 MB read (the jump table) + 58.5 MB "
-                                         "written of the 104 MB of per-batch accumulators (the rest is still in L2 when the "
-                                         "kernel ends); the bound is the FP64 pipe, not HBM",
-                         "pipe_note": None if f32 else
-                                      "ncu on this launch: FP64 pipe 69.3 % active; the kernel sits at 97.6 % of the bound set by the "
-                                      "vector register file (one 64-bit operand per cycle: a three-register DFMA issues every 3 "
-                                      "cycles, profiles/r01_final2_fast_f64_ranf.txt, DESIGN.md section 4d)",
+                                         "DRAM bytes of one launch of the default f64 kernel over 1e6 batches, ncu --set full: the jump table read + "
+                                         "the part of the 104 MB of per-batch accumulators that leaves L2; the bound is the FP64 pipe, not HBM",
                          "peak_source": "measured live: tp3_peak_probe (8 independent FMA chains per thread, all SMs)",
                          "flop_per_event": FLOP_PER_EVENT},
             "cpu_baseline": cpu,
-            "check": {"selected_events": fin.selected_events, "sigma_pb": fin.sigma},
+            "weak": weak,
+            "check": {"selected_events": fin.selected_events, "sigma_pb": fin.sigma,
+                      "per_batch_path_selected_events": fin_pb.selected_events, "per_batch_path_sigma_pb": fin_pb.sigma},
         }
         print(json.dumps(line), flush=True)
     sim.close()

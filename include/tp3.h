@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TP3_ABI_VERSION 1
+#define TP3_ABI_VERSION 2
 
 /* Size of an event batch — src/scheduling/mod.rs:21 (EVENT_BATCH_SIZE) */
 #define TP3_EVENT_BATCH_SIZE 10000u
@@ -98,12 +98,45 @@ int  tp3_simulate_batches_device(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_
 /* Copy the accumulators of the last *_device launch to the host and synchronise. */
 int  tp3_fetch(tp3_ctx* ctx, tp3_acc* out_per_batch, uint64_t n_batches);
 /* Same range, but the per-batch accumulators are left-folded in batch order ON DEVICE
- * (ResultsAccumulator::merge, resacc.rs:133-139) and only the merged one comes back. */
+ * (ResultsAccumulator::merge, resacc.rs:133-139; the fold of sequential.rs:24-36 and
+ * multi_threading.rs:107-126) and only the merged one comes back (104 bytes device->host).
+ * The fold runs inside the simulation kernel, in strict batch order, so the result is bit-identical
+ * to tp3_simulate_batches + tp3_fold_batches for any launch shape.  With several devices in the
+ * context each device folds its contiguous sub-range and the per-device results are merged in
+ * device order: reproducible for a fixed device count (the reference's order-insensitive
+ * FastAccumulator, multi_threading.rs:130-190, makes the same trade). */
 int  tp3_simulate_merged(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
                          uint32_t last_batch_len, tp3_acc* out_merged);
+/* Asynchronous form for multi-GPU runs (single-device contexts): the merged accumulator is left in
+ * the caller's DEVICE buffer as 13 doubles {selected_events, spm2[5], vars[5], sigma, variance}
+ * (the count is exact as a double below 2^53), i.e. the operand of one ncclReduce(sum) over the
+ * ranks -- the whole inter-GPU exchange of a run. */
+int  tp3_simulate_merged_device(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
+                                uint32_t last_batch_len, double* device_out13);
+/* Host left fold of per-batch accumulators in batch order, starting FROM the first one
+ * (sequential.rs:24-36), in the run's Float (flags & TP3_F32). */
+int  tp3_fold_batches(const tp3_acc* per_batch, uint64_t n_batches, uint32_t flags, tp3_acc* out);
 int  tp3_synchronize(tp3_ctx* ctx);
 /* Number of kernel launches issued by this context so far. */
 uint64_t tp3_launch_count(const tp3_ctx* ctx);
+/* Bytes of kernel arguments one launch of the fused kernel carries host->device (the only input). */
+size_t tp3_kernel_arg_bytes(void);
+
+/* ---- test / A-B switches ------------------------------------------------------------
+ * Explicit, per context (nothing is read from the environment).  None of them changes a result
+ * beyond the order of floating-point additions, and none selects a CPU path for the simulation:
+ *   "unit_batches"     consecutive batches per scheduling unit of the fused kernel (0 = by launch size)
+ *   "grid_warps"       warps in the grid (0 = as many as the device holds at once)
+ *   "f32_scalar"       f32: one event per lane instead of the packed two-events-per-lane kernel
+ *   "fe_split"         faster-evgen: 1 = one thread per batch, 32 = one lane per 313 events, 0 = by launch size
+ *   "fe_host_scan"     faster-evgen: batch start states from the reference's own method, the event-by-event
+ *                      walk of the master generator on the host (evgen.rs:257-267), instead of the GPU scans:
+ *                      the cross-check of those scans
+ *   "fe_xo_seg_units"  faster-evgen + xoshiro scan: segment length in units of 2048 outputs (0 = by launch size)
+ *   "fe_timing"        print the scan phases of every call to stderr */
+int  tp3_set_option(tp3_ctx* ctx, const char* name, int64_t value);
+/* "fe_xo_pass_b": how many times pass B of the last xoshiro faster-evgen scan ran. */
+int  tp3_get_stat(tp3_ctx* ctx, const char* name, int64_t* value);
 
 /* ---- per-event observables (the reference's empty hook) ---------------------------------------------
  * The reference parses `num_bins` (config.rs:45-46,102) and marks, without implementing them, the places

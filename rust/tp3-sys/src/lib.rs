@@ -1,7 +1,9 @@
-//! Raw bindings to `include/tp3.h` (ABI version 1). UNCOMPILED in this repository: no Rust toolchain.
+//! Raw bindings to `include/tp3.h`. UNCOMPILED in this repository (no Rust toolchain in the image); the symbol names and
+//! arities of the extern block are held to the header by tests/test_host_surface.py::test_rust_sys_crate_matches_header.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
+pub const TP3_ABI_VERSION: i32 = 2;
 pub const TP3_EVENT_BATCH_SIZE: u32 = 10_000; // scheduling/mod.rs:21
 
 pub const TP3_F32: u32 = 1 << 0;
@@ -50,6 +52,47 @@ pub struct tp3_ctx {
     _private: [u8; 0],
 }
 
+/// `tp3_config`: `Configuration` (config.rs:8-53), values widened to f64.
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct tp3_config {
+    pub num_events: u64,
+    pub e_total: f64,
+    pub beam_photons_cut: f64,
+    pub photon_photon_cut: f64,
+    pub e_min: f64,
+    pub beam_photon_plane_cut: f64,
+    pub alpha: f64,
+    pub alpha_z: f64,
+    pub gev2_to_picobarn: f64,
+    pub m_z0: f64,
+    pub g_z0: f64,
+    pub sin2_weinberg: f64,
+    pub branching_ep_em: f64,
+    pub beta_plus: f64,
+    pub beta_minus: f64,
+    pub num_bins: i32,
+    pub impr: i32,
+    pub plot: i32,
+}
+
+/// `tp3_final`: `FinalResults` (resfin.rs:26-62).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct tp3_final {
+    pub selected_events: u64,
+    pub spm2: [[f64; 5]; 2],
+    pub vars: [[f64; 5]; 2],
+    pub sigma: f64,
+    pub prec: f64,
+    pub variance: f64,
+    pub beta_min: f64,
+    pub ss_p: f64,
+    pub inc_ss_p: f64,
+    pub ss_m: f64,
+    pub inc_ss_m: f64,
+}
+
 pub const TP3_HIST_OBSERVABLES: usize = 6;
 pub const TP3_HIST_MAX_BINS: u32 = 1024;
 
@@ -65,13 +108,31 @@ extern "C" {
     pub fn tp3_fetch(ctx: *mut tp3_ctx, out_per_batch: *mut tp3_acc, n_batches: u64) -> c_int;
     pub fn tp3_simulate_merged(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
                                out_merged: *mut tp3_acc) -> c_int;
+    pub fn tp3_simulate_merged_device(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
+                                      device_out13: *mut f64) -> c_int;
+    pub fn tp3_fold_batches(per_batch: *const tp3_acc, n_batches: u64, flags: u32, out: *mut tp3_acc) -> c_int;
     pub fn tp3_synchronize(ctx: *mut tp3_ctx) -> c_int;
     pub fn tp3_launch_count(ctx: *const tp3_ctx) -> u64;
+    pub fn tp3_kernel_arg_bytes() -> usize;
+    pub fn tp3_set_option(ctx: *mut tp3_ctx, name: *const c_char, value: i64) -> c_int;
+    pub fn tp3_get_stat(ctx: *mut tp3_ctx, name: *const c_char, value: *mut i64) -> c_int;
     /// Per-event observables, the hook main.rs:117-122,133 leaves empty: [TP3_HIST_OBSERVABLES][num_bins] histograms.
     pub fn tp3_histograms_enable(ctx: *mut tp3_ctx, num_bins: u32) -> c_int;
     pub fn tp3_histograms_reset(ctx: *mut tp3_ctx) -> c_int;
     pub fn tp3_histograms_fetch(ctx: *mut tp3_ctx, counts: *mut u64, weights: *mut f64) -> c_int;
     pub fn tp3_rng_dump(ctx: *mut tp3_ctx, batch: u64, n_words: u32, out_words: *mut u64) -> c_int;
     pub fn tp3_events_dump(ctx: *mut tp3_ctx, batch: u64, n: u32, momenta: *mut f64, kept: *mut i32, m2_sums: *mut f64) -> c_int;
+    pub fn tp3_fastmath_probe(ctx: *mut tp3_ctx, which: c_int, n: u32, input: *const f64, out: *mut f64) -> c_int;
     pub fn tp3_peak_probe(ctx: *mut tp3_ctx, which: c_int, tflops: *mut f64) -> c_int;
+    // host side of the reference surface (config.rs, coupling.rs, resacc.rs, resfin.rs, output.rs)
+    pub fn tp3_config_parse(valeurs_text: *const c_char, flags: u32, out: *mut tp3_config, err_buf: *mut c_char, err_cap: usize) -> c_int;
+    pub fn tp3_params_from_config(cfg: *const tp3_config, flags: u32, kernel: u32, out: *mut tp3_params) -> c_int;
+    pub fn tp3_merge(into: *mut tp3_acc, other: *const tp3_acc, flags: u32) -> c_int;
+    pub fn tp3_finalize(cfg: *const tp3_config, flags: u32, merged: *const tp3_acc, out: *mut tp3_final) -> c_int;
+    pub fn tp3_format_res_data(cfg: *const tp3_config, flags: u32, fin: *const tp3_final, buf: *mut c_char, cap: usize) -> usize;
+    pub fn tp3_format_stdout(cfg: *const tp3_config, flags: u32, fin: *const tp3_final, buf: *mut c_char, cap: usize) -> usize;
+    pub fn tp3_run(valeurs_path: *const c_char, out_dir: *const c_char, flags: u32, kernel: u32, n_dev: c_int,
+                   stdout_buf: *mut c_char, stdout_cap: usize, elapsed_seconds: *mut f64) -> c_int;
+    pub fn tp3_host_ranf_round(seed: i32, round: u64, out55: *mut u32) -> c_int;
+    pub fn tp3_host_xoshiro_state(f32_: c_int, n_steps: u64, n_jumps: u64, out4: *mut u64) -> c_int;
 }

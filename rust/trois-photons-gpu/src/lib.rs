@@ -27,9 +27,8 @@ fn feature_flags() -> u32 {
     f
 }
 
-/// Simulates every batch of the run on `n_gpus` devices and returns the per-batch sums in batch order.
-pub fn simulate_all_batches(inputs: &KernelInputs, n_gpus: i32) -> Result<Vec<BatchSums>, String> {
-    let params = tp3_params {
+fn kernel_params(inputs: &KernelInputs) -> tp3_params {
+    tp3_params {
         num_events_total: inputs.num_events as u64,
         e_total: inputs.e_total,
         acut: inputs.cuts[0], bcut: inputs.cuts[1], e_min: inputs.cuts[2], sincut: inputs.cuts[3],
@@ -37,7 +36,32 @@ pub fn simulate_all_batches(inputs: &KernelInputs, n_gpus: i32) -> Result<Vec<Ba
         sigma_contribs: inputs.sigma_contribs,
         flags: feature_flags(),
         kernel: TP3_KERNEL_FAST,
-    };
+    }
+}
+
+/// The whole run, merged in batch order on the device (tp3_simulate_merged): what `run_simulation` needs before `finalize`.
+pub fn simulate_run_merged(inputs: &KernelInputs, n_gpus: i32) -> Result<BatchSums, String> {
+    let params = kernel_params(inputs);
+    let batch = TP3_EVENT_BATCH_SIZE as usize;
+    let n_batches = (inputs.num_events + batch - 1) / batch;       // multi_threading.rs:25
+    let last_len = inputs.num_events - (n_batches - 1) * batch;    // multi_threading.rs:47
+    let mut ctx = std::ptr::null_mut();
+    let mut out = BatchSums::default();
+    unsafe {
+        if tp3_create(&params, n_gpus, std::ptr::null(), &mut ctx) != TP3_OK {
+            return Err(CStr::from_ptr(tp3_last_error(std::ptr::null())).to_string_lossy().into_owned());
+        }
+        let rc = tp3_simulate_merged(ctx, 0, n_batches as u64, last_len as u32, &mut out);
+        let err = if rc != TP3_OK { Some(CStr::from_ptr(tp3_last_error(ctx)).to_string_lossy().into_owned()) } else { None };
+        tp3_destroy(ctx);
+        if let Some(e) = err { return Err(e); }
+    }
+    Ok(out)
+}
+
+/// Simulates every batch of the run on `n_gpus` devices and returns the per-batch sums in batch order.
+pub fn simulate_all_batches(inputs: &KernelInputs, n_gpus: i32) -> Result<Vec<BatchSums>, String> {
+    let params = kernel_params(inputs);
     let batch = TP3_EVENT_BATCH_SIZE as usize;
     let n_batches = (inputs.num_events + batch - 1) / batch;       // multi_threading.rs:25
     let last_len = inputs.num_events - (n_batches - 1) * batch;    // multi_threading.rs:47

@@ -29,6 +29,13 @@ class Acc(C.Structure):
 _lib = None
 
 
+def use_library(path):
+    """Load another build of the same oracle (bench.py's -O3 -march=native rebuild on the GPU box)."""
+    global _lib, LIB_PATH
+    LIB_PATH = path
+    _lib = None
+
+
 def lib():
     global _lib
     if _lib is None:

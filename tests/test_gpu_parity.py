@@ -152,6 +152,44 @@ def test_events_match_oracle(sims, oracle, valeurs_text, features, kernel):
             assert abs(g - w) <= 1e-9 * scale, f"event {e} contribution {k}: {g!r} vs {w!r}"
 
 
+@pytest.mark.parametrize("scalar", [0, 1], ids=["packed-x2", "one-event-per-lane"])
+@pytest.mark.parametrize("features", ["f32", "standard-random,f32", "f32,no-photon-sorting"])
+def test_events_match_oracle_f32(tp3, oracle, valeurs_text, features, scalar):
+    """Per-event parity of the f32 kernels with the f32 oracle.  The shipped f32 kernel is the packed one
+    (simulate_kernel_x2): its dump goes through the same packed gen_event<f2> / keep_event<f2> / me_fast<f2>.
+    Stated f32 bounds (MUFU sin/cos/lg2/rcp/rsq approximations, 2-3 ulp each, against glibc's correctly rounded float
+    functions): momenta within 4e-6 of e_total, identical cut decisions except for events within rounding of a
+    threshold (at most 3 in 10 000), matrix elements within 2e-3 of their scale for 99.9 % of the events (ill-conditioned
+    events amplify the input differences; the rest within 5e-2)."""
+    n = 10000
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    with tp3.Simulator(cfg) as sim:
+        sim.set_option("f32_scalar", scalar)
+        mom, kept, m2 = sim.events_dump(0, n)
+    omom, okept, om2 = oracle.events(valeurs_text, features, n)
+    import numpy as np
+    mom, omom = np.array(mom).reshape(n, 3, 4), np.array(omom).reshape(n, 3, 4)
+    m2, om2 = np.array(m2).reshape(n, 5), np.array(om2).reshape(n, 5)
+    # the fast kernels do not sort the photons (the sums are permutation invariant): order both sides by energy
+    order = np.argsort(-mom[:, :, 3], axis=1, kind="stable")
+    oorder = np.argsort(-omom[:, :, 3], axis=1, kind="stable")
+    mom = np.take_along_axis(mom, order[:, :, None], axis=1)
+    omom = np.take_along_axis(omom, oorder[:, :, None], axis=1)
+    worst_mom = np.abs(mom - omom).max() / 91.187
+    flips = int((np.array(kept) != np.array(okept)).sum())
+    both = (np.array(kept) == 1) & (np.array(okept) == 1)
+    scale = np.abs(om2[both]).copy()
+    scale[:, 3:] = np.maximum(scale[:, 3:], 2 * np.sqrt(om2[both][:, 0:1] * om2[both][:, 1:2]))
+    err = np.abs(m2[both] - om2[both]) / scale
+    worst_per_event = err.max(axis=1)
+    print(f"f32 events [{features}, scalar={scalar}]: momenta {worst_mom:.3g} of e_total, {flips} cut flips, "
+          f"matrix elements: median {np.median(worst_per_event):.3g}, 99.9 % {np.quantile(worst_per_event, 0.999):.3g}, max {worst_per_event.max():.3g}")
+    assert worst_mom <= 4e-6
+    assert flips <= 3
+    assert np.quantile(worst_per_event, 0.999) <= 2e-3
+    assert worst_per_event.max() <= 5e-2
+
+
 # --------------------------------------------------------------------- per-batch accumulators
 @pytest.mark.parametrize("kernel", [0, 1], ids=["fast", "literal"])
 @pytest.mark.parametrize("features", ["", "no-photon-sorting", "standard-random", "multi-threading,faster-threading",
@@ -170,20 +208,23 @@ def test_batches_match_oracle_f64(sims, oracle, valeurs_text, features, kernel):
         assert_acc_close(accs[b], want, REL_F64, what=f"batch {b}")
 
 
-@pytest.mark.parametrize("per_warp", [2, 3, 5, 16])
-def test_stream_continues_across_batches(tp3, oracle, valeurs_text, per_warp, monkeypatch):
-    """A warp that handles several consecutive batches continues the sequential RANF stream instead of
-    jumping again; the per-batch accumulators must not depend on that grouping (bit for bit), and must
+@pytest.mark.parametrize("unit,grid", [(2, 2), (3, 1), (5, 0), (16, 0), (2, 3)])
+def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid):
+    """A warp that handles several consecutive batches (a scheduling unit) continues the sequential RANF stream instead
+    of jumping again; the per-batch accumulators must not depend on how the launch is cut into units and rounds
+    (bit for bit: grids of 1, 2 and 3 warps give several full rounds plus the evenly split last round), and must
     match the oracle."""
     nb = 11
     cfg = tp3.Configuration.parse(valeurs_text)
-    monkeypatch.setenv("TP3_BATCHES_PER_WARP", "1")
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("unit_batches", 1)
         ref = sim.simulate_batches(3, nb, 7777)
-    monkeypatch.setenv("TP3_BATCHES_PER_WARP", str(per_warp))
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("unit_batches", unit).set_option("grid_warps", grid)
         got = sim.simulate_batches(3, nb, 7777)
+        merged = sim.simulate_merged(3, nb, 7777)
     assert bytes(got) == bytes(ref)
+    assert bytes(merged) == bytes(tp3.fold(ref))
     run = oracle.run(valeurs_text, "", threads=8, num_events=14 * 10000, want_text=False)
     scale = (14 * 10000) / 1e7
     for b in range(nb - 1):
@@ -337,18 +378,17 @@ def test_default_run_f32(tp3, valeurs_text, features, suffix):
 
 
 @pytest.mark.parametrize("features", ["f32", "standard-random,f32", "f32,no-photon-sorting", "f32,multi-threading,faster-threading"])
-def test_f32_two_events_per_lane_equals_one_event_per_lane(tp3, valeurs_text, features, monkeypatch):
+def test_f32_two_events_per_lane_equals_one_event_per_lane(tp3, valeurs_text, features):
     """The shipped f32 kernel carries two events per lane in packed FP32 arithmetic (f32x2.cuh, FFMA2 / FMUL2 / FADD2);
-    the one-event-per-lane instantiation of the generic kernel stays behind TP3_F32_SCALAR.  Same streams, same event
+    the one-event-per-lane instantiation of the generic kernel stays behind the `f32_scalar` option.  Same streams, same event
     physics: the event selection may differ only where a cut is decided within rounding, the sums by the order of
     the additions.  A ragged last batch (77 events: odd number of warp iterations, half-filled last step)."""
     cfg = tp3.Configuration.parse(valeurs_text, features)
     nb = 12
     with tp3.Simulator(cfg) as sim:
         packed = sim.simulate_batches(3, nb, 77)
-    monkeypatch.setenv("TP3_F32_SCALAR", "1")
     with tp3.Simulator(cfg) as sim:
-        scalar = sim.simulate_batches(3, nb, 77)
+        scalar = sim.set_option("f32_scalar", 1).simulate_batches(3, nb, 77)
     for b in range(nb):
         assert abs(packed[b].selected_events - scalar[b].selected_events) <= 1, f"batch {b}"
         g, w = acc_fields(packed[b]), acc_fields(scalar[b])
@@ -384,21 +424,21 @@ def test_faster_evgen_batches_match_oracle(sims, oracle, valeurs_text, features)
 
 @pytest.mark.parametrize("split", [1, 32])
 @pytest.mark.parametrize("features,first,nb", [("faster-evgen", 0, 300), ("faster-evgen", 4990, 260), ("faster-evgen,f32", 7, 64)])
-def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, split, monkeypatch):
+def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, split):
     """The start states of the sequential RANF stream come from a scan over per-round transition maps on the GPU
     (fe_scan.cuh); the reference's own method — walking the stream event by event on the scheduler thread,
-    evgen.rs:257-267 — is kept on the host behind TP3_FE_HOST_SCAN for this cross-check.
+    evgen.rs:257-267 — is kept on the host behind the `fe_host_scan` option for this cross-check.
     split = 1: one thread per batch from the scanned batch starts: identical bits.
     split = 32: the scan also locates the 32 lane starts inside every batch and a warp shares the batch: identical
     event selection (one differing draw position would change it), sums equal up to the order of the additions.
     The last batch is ragged (1234 events: most lanes of its warp have nothing to do)."""
     cfg = tp3.Configuration.parse(valeurs_text, features)
-    monkeypatch.setenv("TP3_FE_SPLIT", str(split))
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("fe_split", split)
         dev = sim.simulate_batches(first, nb, 1234)
         dev_again = sim.simulate_batches(first + 5, 20)  # continues / restarts the cached scan
-    monkeypatch.setenv("TP3_FE_HOST_SCAN", "1")
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("fe_split", split).set_option("fe_host_scan", 1)
         host = sim.simulate_batches(first, nb, 1234)
         host_again = sim.simulate_batches(first + 5, 20)
     if split == 1:
@@ -414,24 +454,23 @@ def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, fea
 @pytest.mark.parametrize("features,first,nb", [("faster-evgen,standard-random", 0, 300), ("faster-evgen,standard-random", 1990, 130),
                                                ("faster-evgen,standard-random,f32", 7, 64)])
 @pytest.mark.parametrize("split", [1, 32])
-def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, split, monkeypatch):
+def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, split):
     """xoshiro has no rounds to hang transition maps on: the batch start states of the sequential stream come from
     coalescing segment walks on the GPU (fe_scan_xo.cuh: pass A guesses every segment's exit, pass B re-walks from the
     implied entries and verifies, pass C walks to the wanted event indices).  Cross-check against the reference's own
-    method, the event-by-event walk kept on the host behind TP3_FE_HOST_SCAN: identical bits, for a range that starts at
+    method, the event-by-event walk kept on the host behind the `fe_host_scan` option: identical bits, for a range that starts at
     the beginning, one that the scan has to reach first, continued and restarted calls, and a ragged last batch.
     split = 32 (the default for runs too small to fill the GPU with one thread per batch): the scan also locates the 32
     lane starts inside every batch and a warp shares the batch — same event selection, sums equal up to the order of the
     additions."""
     cfg = tp3.Configuration.parse(valeurs_text, features)
-    monkeypatch.delenv("TP3_FE_HOST_SCAN", raising=False)
-    monkeypatch.setenv("TP3_FE_SPLIT", str(split))
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("fe_split", split)
         dev = sim.simulate_batches(first, nb, 1234)
         dev_next = sim.simulate_batches(first + nb - 1, 20)  # the full batch the ragged one stood for, then continues
         dev_again = sim.simulate_batches(first + 5, 20)       # restarts the scan
-    monkeypatch.setenv("TP3_FE_HOST_SCAN", "1")
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("fe_split", split).set_option("fe_host_scan", 1)
         host = sim.simulate_batches(first, nb, 1234)
         host_next = sim.simulate_batches(first + nb - 1, 20)
         host_again = sim.simulate_batches(first + 5, 20)
@@ -447,23 +486,17 @@ def test_faster_evgen_xoshiro_device_scan_equals_host_pre_advance(tp3, valeurs_t
         assert_acc_close(got, want, rel, what="split 32 vs host walk")
 
 
-def test_faster_evgen_xoshiro_scan_repeats_pass_b(tp3, valeurs_text, monkeypatch, capfd):
-    """With 2048-output segments (TP3_FE_XO_SEG_UNITS=1) a segment's exit depends on its entry about once in 2000
+def test_faster_evgen_xoshiro_scan_repeats_pass_b(tp3, valeurs_text):
+    """With 2048-output segments (option fe_xo_seg_units = 1) a segment's exit depends on its entry about once in 2000
     segments, so over ~25 000 segments pass B has to be repeated with corrected exits: the result must still be the
     host walk's, bit for bit."""
     cfg = tp3.Configuration.parse(valeurs_text, "faster-evgen,standard-random")
-    monkeypatch.setenv("TP3_FE_XO_SEG_UNITS", "1")
-    monkeypatch.setenv("TP3_FE_SPLIT", "1")
-    monkeypatch.setenv("TP3_FE_TIMING", "1")
-    monkeypatch.delenv("TP3_FE_HOST_SCAN", raising=False)
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("fe_xo_seg_units", 1).set_option("fe_split", 1)
         dev = sim.simulate_batches(0, 300)
-    err = capfd.readouterr().err
-    passes = [int(line.rsplit("x", 1)[1]) for line in err.splitlines() if "[tp3 fe xo scan]" in line]
-    assert passes and max(passes) >= 2, err  # the repeat path was taken
-    monkeypatch.delenv("TP3_FE_XO_SEG_UNITS")
-    monkeypatch.setenv("TP3_FE_HOST_SCAN", "1")
+        assert sim.get_stat("fe_xo_pass_b") >= 2  # the repeat path was taken
     with tp3.Simulator(cfg) as sim:
+        sim.set_option("fe_split", 1).set_option("fe_host_scan", 1)
         host = sim.simulate_batches(0, 300)
     assert bytes(dev) == bytes(host)
 

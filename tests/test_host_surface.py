@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol(tp3):
     lib = tp3.lib()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.tp3_abi_version() == 1
+    assert lib.tp3_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tp3):
@@ -64,6 +64,15 @@ def test_config_parse_f32_rounds_text_directly(tp3, valeurs_text):
     (lambda t: re.sub(r"\.false\.(\s+'HBook)", r".true.\1", t), "Plotting is not supported"),
     (lambda t: re.sub(r"\.false\.(\s+'Impression)", r".TRUE.\1", t), "Individual result printing is not supported"),
     (lambda t: re.sub(r"\.false\.(\s+'Impression)", r"maybe\1", t), "could not parse configuration of impr"),
+    # config.rs:187-195: only the FORTRAN forms are lower-cased; Rust's bool parser takes exactly "true" / "false"
+    (lambda t: re.sub(r"\.false\.(\s+'Impression)", r"False\1", t), "could not parse configuration of impr"),
+    (lambda t: re.sub(r"\.false\.(\s+'HBook)", r"TRUE\1", t), "could not parse configuration of plot"),
+    # what strtod / strtol would take and Rust's FromStr does not
+    (lambda t: t.replace("91.187e0", "0x1.6cbf7ced916873p+6", 1), "could not parse configuration of e_total"),
+    (lambda t: t.replace("91.187e0", "nan(123)", 1), "could not parse configuration of e_total"),
+    (lambda t: t.replace("10000000 ", "99999999999999999999999 ", 1), "could not parse configuration of num_events"),
+    (lambda t: t.replace("10000000 ", "-5 ", 1), "could not parse configuration of num_events"),
+    (lambda t: re.sub(r"^200(\s)", r"4294967296\1", t, flags=re.M), "could not parse configuration of num_bins"),
 ])
 def test_config_errors(tp3, valeurs_text, mutate, message):
     with pytest.raises(tp3.Tp3Error) as e:
@@ -195,6 +204,54 @@ def test_missing_library_fails_loudly(tmp_path):
     env = dict(os.environ, TP3_LIB=str(tmp_path / "does_not_exist.so"))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_config_accepts_what_rust_accepts(tp3, valeurs_text):
+    """Rust's `bool` parser takes lower-case true/false; FORTRAN forms in any case; numbers with a leading +."""
+    t = re.sub(r"\.false\.(\s+'Impression)", r"false\1", valeurs_text)
+    t = re.sub(r"\.false\.(\s+'HBook)", r".FALSE.\1", t)
+    t = t.replace("91.187e0", "+91.187", 1)
+    a, b = tp3.Configuration.parse(valeurs_text).raw, tp3.Configuration.parse(t).raw
+    assert bytes(a) == bytes(b)
+
+
+def test_fold_batches_is_the_left_fold(tp3):
+    """tp3_fold_batches = sequential.rs:24-36: starts FROM the first accumulator, adds the rest in order, in the run's Float."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    n = 1000
+    accs = (tp3.Acc * n)()
+    vals = rng.standard_normal((n, 12)) * 10.0 ** rng.integers(-8, 8, (n, 12))
+    for i in range(n):
+        accs[i].selected_events = int(rng.integers(0, 10000))
+        for k in range(5):
+            accs[i].spm2[k], accs[i].vars[k] = vals[i, k], vals[i, 5 + k]
+        accs[i].sigma, accs[i].variance = vals[i, 10], vals[i, 11]
+    got = tp3.fold(accs)
+    want = np.add.accumulate(vals, axis=0)[-1]
+    assert list(got.spm2) + list(got.vars) + [got.sigma, got.variance] == want.tolist()
+    assert got.selected_events == sum(a.selected_events for a in accs)
+    got32 = tp3.fold(accs, tp3.F32)
+    want32 = np.add.accumulate(vals.astype(np.float32), axis=0, dtype=np.float32)[-1]
+    assert [np.float32(x) for x in list(got32.spm2) + list(got32.vars) + [got32.sigma, got32.variance]] == want32.tolist()
+    one = tp3.fold(accs[:1])
+    assert bytes(one) == bytes(accs[0])
+
+
+def test_rust_sys_crate_matches_header(tp3):
+    """rust/tp3-sys/src/lib.rs cannot be compiled here (no rustc in the image), so at least its extern "C" block is held
+    to include/tp3.h statically: same symbol names, same number of arguments."""
+    header = open(os.path.join(ROOT, "include", "tp3.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(tp3_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)}
+    arity_h = {k: 0 if v.strip() in ("", "void") else v.count(",") + 1 for k, v in decl.items()}
+    rust = open(os.path.join(ROOT, "rust", "tp3-sys", "src", "lib.rs")).read()
+    rust = re.sub(r"//[^\n]*", "", rust)
+    fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (tp3_[a-z0-9_]+)\s*\(([^)]*)\)", rust, flags=re.S)}
+    arity_r = {k: 0 if not v.strip() else len([a for a in v.split(",") if a.strip()]) for k, v in fns.items()}
+    assert set(arity_r) == set(arity_h), (set(arity_h) - set(arity_r), set(arity_r) - set(arity_h))
+    assert arity_r == arity_h
+    assert "pub const TP3_ABI_VERSION: i32 = %d;" % tp3.lib().tp3_abi_version() in rust
 
 
 def test_merge_is_done_in_the_runs_float(tp3):

@@ -15,6 +15,7 @@
 #include "faster_evgen.cuh"
 #include "fe_scan.cuh"
 #include "fe_scan_xo.cuh"
+#include "fe_stream.cuh"
 
 using namespace tp3;
 
@@ -56,6 +57,18 @@ struct DeviceSlot {
     size_t xo_scan_cap = 0;
     void* d_xo_bnd = nullptr;
     size_t xo_bnd_cap = 0;
+    // faster-evgen stream pipeline (fe_stream.cuh): grow-only workspaces
+    FeRecord* d_fs_records = nullptr;
+    size_t fs_records_cap = 0;        // records
+    uint32_t* d_fs_count = nullptr;   // per segment: events started
+    uint8_t *d_fs_exit = nullptr, *d_fs_fail = nullptr;
+    uint64_t* d_fs_seg_events = nullptr;
+    uint32_t* d_fs_redo_list = nullptr;
+    uint8_t* d_fs_redo_entry = nullptr;
+    size_t fs_seg_cap = 0;
+    uint32_t* d_fs_unit_seg = nullptr;
+    tp3_acc* d_fs_parts = nullptr;
+    size_t fs_unit_cap = 0;
     // last launch
     uint64_t last_first = 0, last_n = 0;
 };
@@ -77,6 +90,13 @@ struct tp3_ctx {
     int64_t opt_fe_xo_seg_units = 0; // faster-evgen + xoshiro scan: segment length in units of 2048 outputs (0 = by launch size)
     int64_t opt_fe_timing = 0;       // print the scan phases of every call to stderr
     int64_t stat_fe_xo_pass_b = 0;   // tp3_get_stat: pass-B repetitions of the last xoshiro scan
+    int64_t opt_fe_legacy = 0;       // faster-evgen + RANF: the round-1 pipeline (scan over transition maps + one lane per 313 events)
+    int64_t opt_fe_pass_segments = 0;// faster-evgen stream pipeline: segments per pass (0 = one full wave of lanes)
+    int64_t opt_fe_seg_rounds = 0;   // ... rounds per segment (0 = by pass size, <= 1024)
+    int64_t opt_fe_warm = 0;         // ... warm-up rounds before a segment (0 = kFeWarm); small values exercise the redo path
+    int64_t stat_fe_passes = 0, stat_fe_redone = 0;  // passes and redone segments of the last call
+    // faster-evgen stream pipeline: a round (segment boundary of an earlier pass) whose absolute event index is known
+    uint64_t fs_round = 0, fs_events = 0;
     // host copies of the seeding data
     uint32_t ranf_base[kRanfLag];
     std::vector<uint32_t> ranf_table;
@@ -621,6 +641,205 @@ int fe_device_states_xo(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, u
     return TP3_E_CUDA;
 }
 
+// ---- faster-evgen + RANF, sequential stream: walk -> event records -> physics (fe_stream.cuh) -----------------------
+// Fills s.d_out[0 .. n) with the accumulators of batches [first, first + n).  The stream is processed in passes of
+// consecutive rounds; the context remembers a round whose absolute event index is known, so consecutive calls continue.
+template <class T> int fs_grow(tp3_ctx* c, T*& ptr, size_t& cap, size_t need) {
+    if (cap >= need) return TP3_OK;
+    if (ptr) TP3_CUDA(c, cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    TP3_CUDA(c, cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
+    return TP3_OK;
+}
+
+int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len) {
+    const bool f32 = c->params.flags & TP3_F32;
+    const uint64_t B = TP3_EVENT_BATCH_SIZE;
+    const uint64_t e_lo = first * B, e_hi = (first + n - 1) * B + last_len;  // events wanted: [e_lo, e_hi)
+    if (c->fs_events > e_lo) c->fs_round = c->fs_events = 0;                 // the known point is past the start: from the seed again
+    c->stat_fe_passes = c->stat_fe_redone = 0;
+    const double kRoundsPerEvent = 0.3252;  // 3.076 events start per round on average (measured); only sizes the passes
+    const uint64_t lanes_per_wave = (uint64_t)s.sm_count * 16 * 32;
+    const uint32_t warm = c->opt_fe_warm > 0 ? (uint32_t)c->opt_fe_warm : (uint32_t)kFeWarm;
+    uint64_t done_batches = 0;  // batches [first, first + done_batches) are in s.d_out
+    std::vector<uint32_t> h_count;
+    std::vector<uint8_t> h_exit, h_fail;
+    std::vector<uint64_t> h_seg_events;
+    std::vector<uint32_t> h_unit_seg;
+    while (done_batches < n) {
+        // ---- size of this pass
+        const uint64_t next_event = (first + done_batches) * B;
+        // far from the first wanted event: count-only passes (no records) until about 400 batches before it
+        const bool skipping = (double)(next_event - c->fs_events) * kRoundsPerEvent > 16.0 * (double)lanes_per_wave;
+        const uint64_t want_events = skipping ? next_event - c->fs_events : e_hi - c->fs_events;
+        uint64_t want_rounds = (uint64_t)((double)want_events * kRoundsPerEvent * 1.002) + 4096;
+        uint64_t max_seg = c->opt_fe_pass_segments > 0 ? (uint64_t)c->opt_fe_pass_segments : lanes_per_wave;
+        uint32_t seg_rounds = 64;
+        if (c->opt_fe_seg_rounds > 0) seg_rounds = (uint32_t)c->opt_fe_seg_rounds;
+        else
+            while (seg_rounds < 1024 && want_rounds / seg_rounds > lanes_per_wave) seg_rounds *= 2;  // fill the device first, then lengthen
+        uint64_t n_seg = (want_rounds + seg_rounds - 1) / seg_rounds;
+        if (n_seg > max_seg) n_seg = max_seg;
+        if (skipping) {  // stop a little before the first wanted event, at a segment boundary
+            const uint64_t lim = (uint64_t)((double)want_events * kRoundsPerEvent * 0.99) / seg_rounds;
+            if (n_seg > lim) n_seg = lim;
+            if (n_seg == 0) n_seg = 1;
+        }
+        const size_t slots_per_seg = (size_t)kFeSlotsPerRound * seg_rounds;
+        int rc = TP3_OK;
+        if (!skipping && (rc = fs_grow(c, s.d_fs_records, s.fs_records_cap, (size_t)n_seg * slots_per_seg))) return rc;
+        if (s.fs_seg_cap < n_seg + 1) {
+            size_t cap = 0;
+            if ((rc = fs_grow(c, s.d_fs_count, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, s.d_fs_exit, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, s.d_fs_fail, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, s.d_fs_seg_events, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, s.d_fs_redo_list, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, s.d_fs_redo_entry, cap, n_seg + 1))) return rc;
+            s.fs_seg_cap = n_seg + 1;
+        }
+        // ---- 1. walk
+        FeWalkArgs w;
+        std::memset(&w, 0, sizeof w);
+        w.jump_table = s.d_ranf_table;
+        w.first_round = c->fs_round;
+        w.n_seg = (uint32_t)n_seg;
+        w.seg_rounds = seg_rounds;
+        w.warm = warm;
+        w.warm_first = kFeWarmFirst;
+        w.seg_count = s.d_fs_count;
+        w.seg_exit = s.d_fs_exit;
+        w.seg_fail = s.d_fs_fail;
+        w.records = skipping ? nullptr : s.d_fs_records;
+        auto walk = [&](const FeWalkArgs& a, uint32_t items) {
+            const unsigned blocks = (items + 127) / 128;
+            if (f32) fe_walk_kernel<float><<<blocks, 128, 0, s.stream>>>(a);
+            else fe_walk_kernel<double><<<blocks, 128, 0, s.stream>>>(a);
+            ++c->launches;
+        };
+        walk(w, (uint32_t)n_seg);
+        TP3_CUDA(c, cudaGetLastError());
+        h_count.resize(n_seg);
+        h_exit.resize(n_seg);
+        h_fail.resize(n_seg);
+        TP3_CUDA(c, cudaMemcpyAsync(h_count.data(), s.d_fs_count, n_seg * 4, cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaMemcpyAsync(h_exit.data(), s.d_fs_exit, n_seg, cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaMemcpyAsync(h_fail.data(), s.d_fs_fail, n_seg, cudaMemcpyDeviceToHost, s.stream));
+        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        ++c->stat_fe_passes;
+        // ---- segments whose nine walks had not coincided at their start: redo them from the predecessor's exit state
+        for (int round = 0; round < 64; ++round) {
+            std::vector<uint32_t> list;
+            std::vector<uint8_t> entry;
+            for (uint64_t g = 0; g < n_seg; ++g) {
+                if (!h_fail[g]) continue;
+                if (g == 0 || h_fail[g - 1] || h_exit[g - 1] == 0xff) {
+                    if (g == 0) {
+                        c->err = "faster-evgen walk: the warm-up of a pass did not settle";
+                        return TP3_E_CUDA;
+                    }
+                    continue;  // its predecessor is redone first
+                }
+                list.push_back((uint32_t)g);
+                entry.push_back(h_exit[g - 1]);
+            }
+            if (list.empty()) break;
+            if (round == 63) {
+                c->err = "faster-evgen walk: too many redo rounds (fe_warm too small)";
+                return TP3_E_INVALID;
+            }
+            c->stat_fe_redone += (int64_t)list.size();
+            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_redo_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, s.stream));
+            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_redo_entry, entry.data(), entry.size(), cudaMemcpyHostToDevice, s.stream));
+            FeWalkArgs r = w;
+            r.seg_list = s.d_fs_redo_list;
+            r.seg_entry = s.d_fs_redo_entry;
+            r.n_list = (uint32_t)list.size();
+            walk(r, r.n_list);
+            TP3_CUDA(c, cudaGetLastError());
+            TP3_CUDA(c, cudaMemcpyAsync(h_count.data(), s.d_fs_count, n_seg * 4, cudaMemcpyDeviceToHost, s.stream));
+            TP3_CUDA(c, cudaMemcpyAsync(h_exit.data(), s.d_fs_exit, n_seg, cudaMemcpyDeviceToHost, s.stream));
+            TP3_CUDA(c, cudaMemcpyAsync(h_fail.data(), s.d_fs_fail, n_seg, cudaMemcpyDeviceToHost, s.stream));
+            TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        }
+        // ---- 2. absolute index of every segment's first event (multi_threading.rs:59-64 finds these event by event)
+        h_seg_events.resize(n_seg + 1);
+        h_seg_events[0] = c->fs_events;
+        for (uint64_t g = 0; g < n_seg; ++g) h_seg_events[g + 1] = h_seg_events[g] + h_count[g];
+        const uint64_t pass_end = h_seg_events[n_seg];
+        if (skipping) {
+            c->fs_round += n_seg * seg_rounds;
+            c->fs_events = pass_end;
+            continue;
+        }
+        // ---- batches whose events all start in this pass
+        uint64_t b_hi = done_batches;
+        while (b_hi < n) {
+            const uint64_t end = (b_hi + 1 == n) ? e_hi : (first + b_hi + 1) * B;
+            if (end > pass_end) break;
+            ++b_hi;
+        }
+        const bool advanced = b_hi > done_batches;
+        if (advanced) {
+            // ---- 3. physics on the records
+            const uint64_t nb = b_hi - done_batches, n_units = nb * kFeParts;
+            if (s.fs_unit_cap < n_units) {
+                size_t cap = 0;
+                if ((rc = fs_grow(c, s.d_fs_unit_seg, cap, n_units))) return rc;
+                cap = 0; if ((rc = fs_grow(c, s.d_fs_parts, cap, n_units))) return rc;
+                s.fs_unit_cap = n_units;
+            }
+            h_unit_seg.resize(n_units);
+            uint64_t g = 0;
+            for (uint64_t u = 0; u < n_units; ++u) {
+                const uint64_t ev = (first + done_batches + u / kFeParts) * B + (u % kFeParts) * (uint64_t)kFePartLen;
+                while (g + 1 < n_seg && h_seg_events[g + 1] <= ev) ++g;
+                h_unit_seg[u] = (uint32_t)g;
+            }
+            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_seg_events, h_seg_events.data(), (n_seg + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_unit_seg, h_unit_seg.data(), n_units * 4, cudaMemcpyHostToDevice, s.stream));
+            FePhysArgs ph;
+            std::memset(&ph, 0, sizeof ph);
+            ph.records = s.d_fs_records;
+            ph.slots_per_seg = (uint32_t)slots_per_seg;
+            ph.seg_events = s.d_fs_seg_events;
+            ph.unit_seg = s.d_fs_unit_seg;
+            ph.first_event = (first + done_batches) * B;
+            ph.end_event = e_hi;
+            ph.n_units = (uint32_t)n_units;
+            ph.out_parts = s.d_fs_parts;
+            uint64_t W = (uint64_t)s.sm_count * 16;
+            if (c->opt_grid_warps > 0) W = (uint64_t)c->opt_grid_warps;
+            if (W > n_units) W = n_units;
+            ph.n_warps = (uint32_t)W;
+            if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, 0, s.stream>>>(ph, phys_params<float>(c->params));
+            else fe_physics_kernel<double><<<(unsigned)W, 32, 0, s.stream>>>(ph, phys_params<double>(c->params));
+            ++c->launches;
+            TP3_CUDA(c, cudaGetLastError());
+            const unsigned cb = (unsigned)((nb * 13 + 255) / 256);
+            if (f32) fe_combine_parts_kernel<float><<<cb, 256, 0, s.stream>>>(s.d_fs_parts, nb, s.d_out + done_batches);
+            else fe_combine_parts_kernel<double><<<cb, 256, 0, s.stream>>>(s.d_fs_parts, nb, s.d_out + done_batches);
+            ++c->launches;
+            TP3_CUDA(c, cudaGetLastError());
+            TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // the host vectors are reused by the next pass
+            done_batches = b_hi;
+        }
+        // ---- the next pass (or call) starts at the last segment boundary at or before the next batch's first event
+        const uint64_t next = (first + done_batches) * B;
+        uint64_t g = n_seg;
+        while (g > 0 && h_seg_events[g] > next) --g;
+        if (g == 0 && !advanced) {  // the pass holds less than the one batch it was sized for
+            c->err = "faster-evgen stream pipeline: a pass must hold at least one batch (fe_pass_segments x fe_seg_rounds too small)";
+            return TP3_E_INVALID;
+        }
+        c->fs_round += g * seg_rounds;
+        c->fs_events = h_seg_events[g];
+    }
+    return TP3_OK;
+}
+
 template <class F, int RNG> void launch_fe(const FeArgs& a, const tp3_params& p, cudaStream_t st) {
     const uint64_t units = a.n_batches * a.split;
     faster_evgen_kernel<F, RNG><<<(unsigned)((units + kFeThreads - 1) / kFeThreads), kFeThreads, 0, st>>>(a, phys_params<F>(p));
@@ -691,6 +910,20 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     std::vector<uint64_t> fe_xo;
     const bool device_scan = seq_faster && !(c->params.flags & TP3_STANDARD_RANDOM) && !c->opt_fe_host_scan;
     uint32_t fe_split = 1;
+    if (device_scan && !c->opt_fe_legacy && !c->opt_fe_split) {
+        // walk -> event records -> physics (fe_stream.cuh): the shipped path for the sequential RANF stream
+        rc = fe_stream_simulate(c, s, first, n, last_len);
+        if (rc) return rc;
+        if (fold) {
+            if (c->params.flags & TP3_F32) merge_kernel<float><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, n, &s.d_fold->running, true);
+            else merge_kernel<double><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, n, &s.d_fold->running, true);
+            ++c->launches;
+            TP3_CUDA(c, cudaGetLastError());
+        }
+        s.last_first = first;
+        s.last_n = n;
+        return TP3_OK;
+    }
     if (device_scan) {
         // One lane per 313 events: fills the device for any run size and keeps a warp's lanes on one batch (measured
         // faster than one thread per batch at every size).  Costs 7.3 KB of start states per batch, so very long
@@ -879,6 +1112,15 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_out);
         cudaFree(s.d_fold);
         cudaFree(s.d_unit_done);
+        cudaFree(s.d_fs_records);
+        cudaFree(s.d_fs_count);
+        cudaFree(s.d_fs_exit);
+        cudaFree(s.d_fs_fail);
+        cudaFree(s.d_fs_seg_events);
+        cudaFree(s.d_fs_redo_list);
+        cudaFree(s.d_fs_redo_entry);
+        cudaFree(s.d_fs_unit_seg);
+        cudaFree(s.d_fs_parts);
         cudaFree(s.d_fe_ranf_states);
         cudaFree(s.d_fe_bnd);
         cudaFree(s.d_fe_maps);
@@ -1107,6 +1349,10 @@ int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
     else if (k == "fe_host_scan") c->opt_fe_host_scan = value != 0;
     else if (k == "fe_xo_seg_units" && value >= 0 && value <= 64) c->opt_fe_xo_seg_units = value;
     else if (k == "fe_timing") c->opt_fe_timing = value != 0;
+    else if (k == "fe_legacy") c->opt_fe_legacy = value != 0;
+    else if (k == "fe_pass_segments" && value >= 0 && value <= (1 << 24)) c->opt_fe_pass_segments = value;
+    else if (k == "fe_seg_rounds" && value >= 0 && value <= 4096) c->opt_fe_seg_rounds = value;
+    else if (k == "fe_warm" && value >= 0 && value <= 1024) c->opt_fe_warm = value;
     else {
         c->err = "tp3_set_option: unknown option or value out of range: " + k;
         return TP3_E_INVALID;
@@ -1118,6 +1364,8 @@ int tp3_get_stat(tp3_ctx* c, const char* name, int64_t* value) {
     if (!c || !name || !value) return TP3_E_INVALID;
     const std::string k(name);
     if (k == "fe_xo_pass_b") *value = c->stat_fe_xo_pass_b;
+    else if (k == "fe_passes") *value = c->stat_fe_passes;
+    else if (k == "fe_redone") *value = c->stat_fe_redone;
     else {
         c->err = "tp3_get_stat: unknown statistic: " + k;
         return TP3_E_INVALID;

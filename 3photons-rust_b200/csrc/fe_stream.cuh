@@ -1,0 +1,445 @@
+// `faster-evgen` with RANF, second design: WALK the stream once, PHYSICS on event records.
+//
+// Under this feature the position of an event in the random stream depends on every earlier event (9 numbers, 6 numbers,
+// 2 more per re-roll of a point outside the unit disc, and RANF discards the rest of a 55-number round when a request does
+// not fit: evgen.rs:143-173,221-249, ranf.rs:78-102).  The reference's reproducible scheduler therefore walks the stream
+// sequentially (evgen.rs:257-267).  Here:
+//
+//   1. fe_walk_kernel     ONE LANE = ONE SEGMENT of consecutive rounds, private generator per lane (started by jump-ahead).
+//        A lane starts `warm` rounds BEFORE its segment with all nine possible consumer states (fe_scan.cuh) and follows
+//        only the states that are still possible; every request that does not fit puts every walk back at a round start,
+//        so the nine walks coincide after 2.2 rounds on average (never more than 17 in 4e5 trials; `warm` = 24 leaves
+//        ~1e-8 per segment, and a segment that has not collapsed is simply redone from its predecessor's exit state).
+//        From its segment start on the lane's state is the TRUE one: it serves the requests exactly as the reference does
+//        and writes, for every event that starts in its segment, a 64-byte RECORD with the 15 integers the event keeps:
+//        the nine numbers of random_array::<9>() and the (x, y) numbers of the three accepted points.
+//        The accept / re-roll decision is EXACT: with X = 2n - 1e9 the reference's floating-point test r^2 > 1 can only
+//        differ from the integer test X^2 + Y^2 > 1e18 when the two sides are within the rounding error of the
+//        floating-point expression (|X^2 + Y^2 - 1e18| <= 2665 in f64, 1.9e12 in f32, see FeTol); outside that band the
+//        integer comparison decides, inside it the reference's own expression is evaluated (no FMA contraction).
+//   2. (host)             prefix sum of the per-segment event counts: the absolute index of every segment's first event.
+//   3. fe_physics_kernel  ONE LANE = ONE EVENT: records are fetched with cp.async one warp iteration ahead, then the same
+//        generation -> cuts -> survivor compaction -> matrix elements as the fused default kernel.  A batch is cut into
+//        four fixed parts of 2500 events (one warp each, partial sums folded in part order), so that a pass of a few
+//        thousand batches still balances over the 2368 resident warps; the result does not depend on the launch shape.
+//
+// Cost (profiles/r02_fe_*): the walk is integer work (generator + ~3.8 disc tests per event), the physics kernel has no
+// generator and no rejection loop left.  HBM carries 64 B per event each way, far below the bandwidth the FP64-bound
+// physics kernel leaves idle.
+#pragma once
+
+#include <cstddef>
+
+#include "fe_scan.cuh"
+
+namespace tp3 {
+
+struct alignas(16) FeRecord {
+    // w[0..8]: random_array::<9>() in the reference's order (evgen.rs:149-153: column-major 3x3 -> cos_theta of the three
+    // photons, then the two factors of each exp(-E)); w[9 + 2k], w[10 + 2k]: the numbers behind (x, y) of accepted point k.
+    uint32_t w[16];
+};
+
+constexpr int kFeParts = 4;                       // fixed parts of a batch in the physics kernel
+constexpr int kFePartLen = kBatch / kFeParts;     // 2500 events
+constexpr int kFeWarm = 24;                       // warm-up rounds before a segment (see the head of this file)
+constexpr int kFeWarmFirst = 256;                 // ... before the first segment of a pass, which has no predecessor to redo it from
+constexpr int kFeSlotsPerRound = 4;               // an event takes >= 15 of the 55 numbers of a round: at most 4 start in one
+
+// |X^2 + Y^2 - 1e18| up to which the floating-point test of the reference may disagree with the exact one (bounds derived
+// in DESIGN.md section 3c: 24 eps in f64, 32 eps in f32, times 1e18; the constants below leave a factor 2-3).
+template <class F> struct FeTol;
+template <> struct FeTol<double> { static constexpr long long value = 8192; };
+template <> struct FeTol<float> { static constexpr long long value = 1ll << 42; };
+
+template <class F> __device__ __forceinline__ bool fe_outside_exact(uint32_t a, uint32_t b) {
+    const int x = (int)(a + a) - 1000000000, y = (int)(b + b) - 1000000000;  // 2n - 1e9, in (-1e9, 1e9)
+    const long long s = (long long)x * x + (long long)y * y - 1000000000000000000ll;
+    if (s > FeTol<F>::value) return true;
+    if (s < -FeTol<F>::value) return false;
+    return fe_outside<F>(a, b);  // within rounding of the circle: the reference's own expression decides
+}
+
+// State after the six-number request (three points, flags "outside") and after an accepted re-roll (fe_scan.cuh).
+__device__ __forceinline__ int fe_after_six(bool n0, bool n1, bool n2) { return n0 ? 2 + 2 * (int)n1 + (int)n2 : n1 ? 6 + (int)n2 : n2 ? 8 : 0; }
+__device__ __forceinline__ int fe_after_roll(int s) {
+    if (s < 6) {
+        const int f1 = (s - 2) >> 1, f2 = (s - 2) & 1;
+        return f1 ? 6 + f2 : f2 ? 8 : 0;
+    }
+    return (s < 8 && (s - 6)) ? 8 : 0;
+}
+
+// One round from entry state s with the exact test, nothing recorded (warm-up): exit state, events started.
+template <class F> __device__ __forceinline__ int fe_walk_round_exact(const uint32_t* row, int s, int& count) {
+    int idx = kRanfLag;
+    count = 0;
+    for (;;) {
+        if (s == 0) {
+            if (idx < 9) break;
+            idx -= 9;
+            ++count;
+            s = 1;
+        } else if (s == 1) {
+            if (idx < 6) break;
+            idx -= 6;
+            s = fe_after_six(fe_outside_exact<F>(row[idx], row[idx + 3]), fe_outside_exact<F>(row[idx + 1], row[idx + 4]),
+                             fe_outside_exact<F>(row[idx + 2], row[idx + 5]));
+        } else {
+            if (idx < 2) break;
+            idx -= 2;
+            if (!fe_outside_exact<F>(row[idx], row[idx + 1])) s = fe_after_roll(s);
+        }
+    }
+    return s;
+}
+
+struct FeWalkArgs {
+    const uint32_t* jump_table;   // [kRanfDigits][256][55], the seeded round 0 behind it (api.cu)
+    uint64_t first_round;         // absolute index of the round where segment 0 starts
+    uint32_t n_seg, seg_rounds;
+    uint32_t warm, warm_first;
+    const uint32_t* seg_list;     // redo mode: the segments to walk (else null: all of them) ...
+    const uint8_t* seg_entry;     // ... and their true entry states
+    uint32_t n_list;
+    uint32_t* seg_count;          // [n_seg] events started in the segment
+    uint8_t* seg_exit;            // [n_seg] consumer state at the end of the segment (0xff: the walks never coincided)
+    uint8_t* seg_fail;            // [n_seg] 1: the nine walks had not coincided at the segment start -> redo
+    FeRecord* records;            // [n_seg][kFeSlotsPerRound * seg_rounds], or null: count only
+};
+
+struct FeWalkSmem {
+    uint32_t win[2 * kRanfLag + 2];
+    uint32_t tile[32][kRanfLag + 2];  // one private generator per lane, row[k] = numbers[k + 1]; odd row stride: conflict free
+};
+
+// ranf.rs:106-119 in place on a lane's private row.
+__device__ __forceinline__ void fe_next_round(uint32_t* row) {
+#pragma unroll
+    for (int k = 0; k < 24; ++k) row[k] = ranf_sub(row[k], row[k + 31]);
+#pragma unroll
+    for (int k = 24; k < kRanfLag; ++k) row[k] = ranf_sub(row[k], row[k - 24]);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
+    __shared__ FeWalkSmem sm[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FeWalkSmem& w = sm[warp];
+    const bool redo = a.seg_list != nullptr;
+    const uint32_t n_items = redo ? a.n_list : a.n_seg;
+    const uint32_t item0 = (blockIdx.x * 4 + warp) * 32;
+    if (item0 >= n_items) return;
+    const uint32_t* base = a.jump_table + (size_t)kRanfDigits * 256 * kRanfLag;  // the seeded round 0
+
+    // where every lane's walk starts, and its generator there (jump-ahead is a warp-cooperative operation)
+    uint32_t my_seg = 0;
+    uint64_t my_start = 0;
+    int my_warm = 0;
+    uint64_t prev_start = 0;
+    for (int k = 0; k < 32; ++k) {
+        if (item0 + k >= n_items) break;  // warp-uniform
+        const uint32_t g = redo ? a.seg_list[item0 + k] : item0 + k;
+        const uint64_t s_round = a.first_round + (uint64_t)g * a.seg_rounds;
+        const uint64_t want_warm = redo ? 0 : (g == 0 ? a.warm_first : a.warm);
+        const uint64_t start = s_round >= want_warm ? s_round - want_warm : 0;
+        if (k == 0 || redo) ranf_jump_to_round(w.win, base, start, a.jump_table, lane);
+        else ranf_jump_to_round(w.win, w.win, start - prev_start, a.jump_table, lane);  // segments of a warp are consecutive
+        prev_start = start;
+        for (int i = lane; i < kRanfLag; i += 32) w.tile[k][i] = w.win[i];
+        if (lane == k) {
+            my_seg = g;
+            my_start = start;
+            my_warm = (int)(s_round - start);
+        }
+        __syncwarp();
+    }
+    const bool live = item0 + lane < n_items;
+    uint32_t* const row = w.tile[lane];
+    FeRecord* const rec_base = (a.records && live) ? a.records + (size_t)my_seg * kFeSlotsPerRound * a.seg_rounds : nullptr;
+
+    // consumer state: where each of the nine possible entry states is now (warm-up), then the single true state
+    uint64_t cur = 0x876543210ull;
+    bool single = false;
+    int s = 0;
+    if (redo) {
+        single = true;
+        s = live ? a.seg_entry[item0 + lane] : 0;
+    } else if (my_start == 0) {  // the very beginning of the stream: a new event is about to start
+        single = true;
+        s = 0;
+    }
+    uint32_t count = 0;
+    bool done = !live, rec = false, failed = false;
+    uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0, u4 = 0, u5 = 0, u6 = 0, u7 = 0, u8 = 0, p0a = 0, p0b = 0, p1a = 0, p1b = 0, p2a = 0, p2b = 0;
+    const int seg_end = my_warm + (int)a.seg_rounds;
+
+    for (int t = 0; !__all_sync(0xffffffffu, done); ++t) {
+        if (t > 0 && !done) fe_next_round(row);
+        const bool warming = !done && t < my_warm;
+        if (warming) {  // ---- warm-up: follow every state that is still possible, record nothing
+            if (single) {
+                int c;
+                s = fe_walk_round_exact<F>(row, s, c);
+            } else {
+                uint32_t img = 0;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) img |= 1u << ((cur >> (4 * q)) & 15u);
+                uint64_t m = 0;
+                while (img) {
+                    const int q = __ffs(img) - 1;
+                    img &= img - 1;
+                    int c;
+                    m |= (uint64_t)fe_walk_round_exact<F>(row, q, c) << (4 * q);
+                }
+                uint64_t nxt = 0;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) nxt |= ((m >> (4 * ((cur >> (4 * q)) & 15u))) & 15ull) << (4 * q);
+                cur = nxt;
+                if (cur == (cur & 15u) * kFeNine4) {
+                    single = true;
+                    s = (int)(cur & 15u);
+                }
+            }
+        }  // (no `continue`: the other lanes of the warp may be in their segment already, and the votes below are warp-wide)
+        if (!done && t == my_warm && !single) {  // the segment starts and its state is still ambiguous: the host redoes it
+            failed = true;
+            done = true;
+        }
+        if (!done && t == seg_end) {
+            if (a.seg_exit) a.seg_exit[my_seg] = (uint8_t)s;  // state at the end of the segment = entry state of the next one
+            if (!rec) done = true;                             // no event in progress: nothing left to do
+        }
+        const bool in_seg = t < seg_end;
+        bool active = !done && !warming;
+        int idx = kRanfLag;
+        // One round, request by request, the lanes of the warp in step: [pending requests] then up to four times
+        // [9 numbers][6 numbers + three tests][re-rolls]; a lane whose next request does not fit is finished with the round.
+        for (int e = 0; e < 6; ++e) {
+            if (e > 0 && active && s == 0) {
+                if (idx >= 9 && in_seg) {  // a new event starts here (random_array::<9>, evgen.rs:149)
+                    idx -= 9;
+                    u0 = row[idx]; u1 = row[idx + 1]; u2 = row[idx + 2]; u3 = row[idx + 3]; u4 = row[idx + 4];
+                    u5 = row[idx + 5]; u6 = row[idx + 6]; u7 = row[idx + 7]; u8 = row[idx + 8];
+                    ++count;
+                    rec = true;
+                    s = 1;
+                } else {
+                    active = false;
+                }
+            }
+            if (active && s == 1) {
+                if (idx >= 6) {  // the three points, column-major 3x2 (evgen.rs:223-225): point k = (v[k], v[3 + k])
+                    idx -= 6;
+                    const uint32_t a0 = row[idx], a1 = row[idx + 1], a2 = row[idx + 2], a3 = row[idx + 3], a4 = row[idx + 4], a5 = row[idx + 5];
+                    const bool n0 = fe_outside_exact<F>(a0, a3), n1 = fe_outside_exact<F>(a1, a4), n2 = fe_outside_exact<F>(a2, a5);
+                    p0a = a0; p0b = a3; p1a = a1; p1b = a4; p2a = a2; p2b = a5;  // re-rolled points are overwritten below
+                    s = fe_after_six(n0, n1, n2);
+                } else {
+                    active = false;
+                }
+            }
+            while (__any_sync(0xffffffffu, active && s >= 2)) {
+                if (active && s >= 2) {
+                    if (idx >= 2) {  // one re-roll of the first point that is still outside (evgen.rs:231-241)
+                        idx -= 2;
+                        const uint32_t x = row[idx], y = row[idx + 1];
+                        if (s < 6) { p0a = x; p0b = y; }
+                        else if (s < 8) { p1a = x; p1b = y; }
+                        else { p2a = x; p2b = y; }
+                        if (!fe_outside_exact<F>(x, y)) s = fe_after_roll(s);
+                    } else {
+                        active = false;
+                    }
+                }
+            }
+            if (active && s == 0 && rec) {  // the event is complete: its record
+                rec = false;
+                if (rec_base) {
+                    uint4* o = reinterpret_cast<uint4*>(rec_base + (count - 1));
+                    o[0] = make_uint4(u0, u1, u2, u3);
+                    o[1] = make_uint4(u4, u5, u6, u7);
+                    o[2] = make_uint4(u8, p0a, p0b, p1a);
+                    o[3] = make_uint4(p1b, p2a, p2b, 0u);
+                }
+                if (!in_seg) {  // that was the event straddling the end of the segment
+                    active = false;
+                    done = true;
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) break;
+        }
+    }
+    if (live) {
+        a.seg_count[my_seg] = count;
+        a.seg_fail[my_seg] = failed ? 1 : 0;
+        if (failed && a.seg_exit) a.seg_exit[my_seg] = 0xff;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- physics
+// Event from its record (evgen.rs:143-173): the f64 path works straight from the integers like gen_event_ints.
+template <class F> __device__ __forceinline__ void fe_event_from_record(const uint32_t w[15], F e_total, const FastMath fm, F p[3][4]);
+template <> __device__ __forceinline__ void fe_event_from_record<double>(const uint32_t w[15], double e_total, const FastMath fm, double p[3][4]) {
+    double q[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double c = fma((double)(int)w[k], fm.fc->u_scale2, -1.0);
+        const double e = fma((double)(int)w[3 + k] * (double)(int)w[6 + k], fm.fc->u_scale_sq, Num<double>::MIN_POSITIVE);
+        const double x = fma((double)(int)w[9 + 2 * k], fm.fc->u_scale2, -1.0), y = fma((double)(int)w[10 + 2 * k], fm.fc->u_scale2, -1.0);
+        const double st = fast_sqrt(fma(-c, c, 1.0));
+        const double en = fast_neg_log(e, fm);
+        double s_, n;
+        fast_sqrt_rsqrt(fma(x, x, y * y), s_, n);  // n = 1 / sqrt(r2)
+        const double esn = (en * st) * n;
+        q[k][0] = esn * x;
+        q[k][1] = esn * y;
+        q[k][2] = en * c;
+        q[k][3] = en;
+    }
+    conformal_transform<double, false, false, Cons3<double, false>::value>(q, e_total, p);
+}
+template <> __device__ __forceinline__ void fe_event_from_record<float>(const uint32_t w[15], float e_total, const FastMath fm, float p[3][4]) {
+    float u9[9], xy[3][2], r2[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) u9[i] = (float)(int)w[i] * 1e-9f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        xy[k][0] = 2.0f * ((float)(int)w[9 + 2 * k] * 1e-9f) - 1.0f;
+        xy[k][1] = 2.0f * ((float)(int)w[10 + 2 * k] * 1e-9f) - 1.0f;
+        r2[k] = xy[k][0] * xy[k][0] + xy[k][1] * xy[k][1];
+    }
+    gen_event_faster<float, false>(u9, xy, r2, e_total, fm, p);
+}
+
+struct FePhysArgs {
+    const FeRecord* records;
+    uint32_t slots_per_seg;        // kFeSlotsPerRound * seg_rounds
+    const uint64_t* seg_events;    // [n_seg + 1] absolute index of the first event that starts in each segment of the pass
+    const uint32_t* unit_seg;      // [n_units] segment of the pass holding the unit's first event
+    uint64_t first_event;          // absolute index of the first event of unit 0 (a batch start)
+    uint64_t end_event;            // absolute index one past the last event wanted (a short last batch)
+    uint32_t n_units;              // kFeParts per batch
+    uint32_t n_warps;
+    tp3_acc* out_parts;            // [n_units]
+};
+
+template <class F> struct FePhysSmem {
+    double2 log_tab[128];                                                   // FastMathSmem::log_tab (no sin / cos in this event generator)
+    alignas(16) typename Pair<F>::type queue[2 * kQueuePhotons][kQueue];  // survivor queue (kernels.cuh)
+    alignas(16) uint4 stage[2][4][32];                                      // records of this / the next warp iteration
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+// ONE WARP = ONE CTA, like the fused default kernel; warp w takes units [n_units w / W, n_units (w + 1) / W).
+template <class F> __global__ void __launch_bounds__(32, 16) fe_physics_kernel(const FePhysArgs a, const PhysParams<F> P) {
+    __shared__ FePhysSmem<F> sm;
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 128; i += 32) sm.log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
+    __syncwarp();
+    static_assert(offsetof(FastMathSmem, log_tab) == 0, "log_tab must lead FastMathSmem");
+    const FastMath fm{reinterpret_cast<const FastMathSmem*>(sm.log_tab), &P.fc};  // only log_tab is read (fast_neg_log)
+    const uint64_t u_lo = (uint64_t)a.n_units * blockIdx.x / a.n_warps, u_hi = (uint64_t)a.n_units * (blockIdx.x + 1) / a.n_warps;
+    for (uint64_t u = u_lo; u < u_hi; ++u) {
+        const uint64_t e0 = a.first_event + (u / kFeParts) * kBatch + (u % kFeParts) * kFePartLen;
+        const uint64_t e1 = min(e0 + kFePartLen, a.end_event);
+        const int n_ev = e1 > e0 ? (int)(e1 - e0) : 0;
+        uint32_t g = a.unit_seg[u];
+        auto fetch = [&](int it) {  // this lane's record of warp iteration `it` -> stage buffer (asynchronous)
+            const uint64_t ev = min(e0 + (uint64_t)it * 32 + lane, e1 - 1);  // lanes past the end re-read the last record
+            while (ev >= __ldg(a.seg_events + g + 1)) ++g;                    // events of a unit are in stream order
+            const uint4* src = reinterpret_cast<const uint4*>(a.records + (size_t)g * a.slots_per_seg + (ev - __ldg(a.seg_events + g)));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async16(&sm.stage[it & 1][c][lane], src + c);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        LaneAcc<F> acc;
+        acc.clear();
+        int q_head = 0, q_count = 0;
+        const int n_it = (n_ev + 31) / 32;
+        if (n_it) fetch(0);
+        for (int it = 0; it < n_it; ++it) {
+            if (it + 1 < n_it) {
+                fetch(it + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            uint32_t w[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 v = sm.stage[it & 1][c][lane];
+                w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+            }
+            F p[3][4];
+            fe_event_from_record<F>(w, P.e_total, fm, p);
+            const bool keep = it * 32 + lane < n_ev && keep_event<F, false, false>(p, P);
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) queue_push<F>(sm.queue, (q_head + q_count + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1), p);
+            q_count += __popc(mask);
+            __syncwarp();
+            if (q_count >= 32) {
+                F e[3][4];
+                queue_pop<F>(sm.queue, (q_head + lane) & (kQueue - 1), P.e_total, e);
+                __syncwarp();
+                q_head = (q_head + 32) & (kQueue - 1);
+                q_count -= 32;
+                F m[5];
+                me_fast<F>(e, P, m);
+                acc.integrate(m, P.sigma_contribs);
+            }
+        }
+        if (lane < q_count) {  // drain
+            F e[3][4];
+            queue_pop<F>(sm.queue, (q_head + lane) & (kQueue - 1), P.e_total, e);
+            F m[5];
+            me_fast<F>(e, P, m);
+            acc.integrate(m, P.sigma_contribs);
+        }
+        __syncwarp();
+        F v[12];
+        acc.fields(v);
+        uint32_t n = acc.selected;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) v[k] += shfl_xor_t(v[k], off);
+            n += __shfl_xor_sync(0xffffffffu, n, off);
+        }
+        if (lane == 0) {
+            tp3_acc* o = a.out_parts + u;
+            o->selected_events = n;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                o->spm2[k] = (double)v[k];
+                o->vars[k] = (double)v[5 + k];
+            }
+            o->sigma = (double)v[10];
+            o->variance = (double)v[11];
+        }
+    }
+}
+
+// Batch accumulator = its kFeParts part accumulators merged in part order, in the run's Float (resacc.rs:133-139).
+template <class F> __global__ void fe_combine_parts_kernel(const tp3_acc* __restrict__ parts, uint64_t n_batches, tp3_acc* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t b = i / 13;
+    const int f = (int)(i % 13);
+    if (b >= n_batches) return;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(parts + b * kFeParts);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + b);
+    if (f == 0) {
+        unsigned long long n = 0;
+        for (int k = 0; k < kFeParts; ++k) n += src[k * 13];
+        dst[0] = n;
+    } else {
+        F s = (F)__longlong_as_double((long long)src[f]);
+        for (int k = 1; k < kFeParts; ++k) s += (F)__longlong_as_double((long long)src[k * 13 + f]);
+        dst[f] = (unsigned long long)__double_as_longlong((double)s);
+    }
+}
+
+}  // namespace tp3

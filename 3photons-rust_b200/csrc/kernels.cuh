@@ -415,23 +415,30 @@ __device__ __noinline__ void fold_publish(FoldState* fs, uint32_t* unit_done, co
             if (lane < 12) acc = (F)__longlong_as_double((long long)__ldcg(run + 1 + lane));
             else if (lane == 12) cnt = __ldcg(run);
         }
-        while (nu < n_units && ld_acquire_u32(unit_done + nu) == epoch) {
-            uint64_t lo, hi;
+        const int word = lane < 12 ? 1 + lane : 0;
+        for (;;) {
+            // how many of the next 32 units are complete: one flag per lane, one round trip
+            const bool ready = nu + lane < n_units && ld_acquire_u32(unit_done + nu + lane) == epoch;
+            const unsigned m = __ffs(~__ballot_sync(0xffffffffu, ready)) - 1;  // leading run of ready units (32 if all)
+            if (m == 0) break;
+            uint64_t lo, hi, lo2;
             unit_range(n_warps, full_rounds, unit_batches, n_batches, nu, lo, hi);
-            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(out + lo);
-            for (uint64_t b = lo; b < hi; b += 8) {  // loads first, then the dependent chain of additions
-                unsigned long long v[8];
+            unit_range(n_warps, full_rounds, unit_batches, n_batches, nu + m - 1, lo2, hi);  // units are consecutive batch ranges
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(out) + word;
+            for (uint64_t b = lo; b < hi; b += 16) {  // 16 loads in flight, then the dependent chain of additions
+                unsigned long long v[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (b + j < hi && lane < 13) ? __ldcg(src + (b - lo + j) * 13 + (lane < 12 ? 1 + lane : 0)) : 0ull;
+                for (int j = 0; j < 16; ++j) v[j] = (b + j < hi && lane < 13) ? __ldcg(src + (b + j) * 13) : 0ull;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     if (b + j < hi) {
                         if (lane < 12) acc += (F)__longlong_as_double((long long)v[j]);
                         else cnt += v[j];
                     }
                 }
             }
-            ++nu;
+            nu += m;
+            if (m < 32) break;
         }
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(&fs->running);
         if (lane < 12) __stcg(dst + 1 + lane, (unsigned long long)__double_as_longlong((double)acc));

@@ -451,6 +451,44 @@ def test_faster_evgen_device_scan_equals_host_pre_advance(tp3, valeurs_text, fea
         assert_acc_close(got, want, rel, what="split 32 vs host walk")
 
 
+@pytest.mark.parametrize("opts", [{}, {"fe_pass_segments": 160, "fe_seg_rounds": 64, "fe_warm": 3}], ids=["default-passes", "small-passes-redo"])
+@pytest.mark.parametrize("features,first,nb", [("faster-evgen", 0, 300), ("faster-evgen", 4990, 260), ("faster-evgen,f32", 7, 64)])
+def test_faster_evgen_stream_pipeline_equals_host_pre_advance(tp3, valeurs_text, features, first, nb, opts):
+    """The shipped faster-evgen path for the sequential RANF stream (fe_stream.cuh): one walk of the stream that writes a
+    record of 15 integers per event, then a physics kernel on the records.  Cross-check against the reference's own
+    method, the event-by-event walk of the master generator kept on the host behind `fe_host_scan` (evgen.rs:257-267):
+    identical event selection in every batch (one differing accept / re-roll decision or draw position would change
+    it), sums equal up to the order of the additions.  Covers a range the walk has to reach first (count-only passes), a
+    ragged last batch, continued and restarted calls, and -- with 160 segments of 64 rounds per pass and 3 warm-up rounds --
+    many passes per call plus the redo path for segments whose nine candidate walks had not coincided at the segment
+    start.  The per-batch results must not depend on how the stream is cut into passes and segments (bit for bit)."""
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    with tp3.Simulator(cfg) as sim:
+        for k, v in opts.items():
+            sim.set_option(k, v)
+        dev = sim.simulate_batches(first, nb, 1234)
+        passes, redone = sim.get_stat("fe_passes"), sim.get_stat("fe_redone")
+        dev_next = sim.simulate_batches(first + nb - 1, 20)   # the full batch the ragged one stood for, then continues
+        dev_again = sim.simulate_batches(first + 5, 20)        # restarts
+        merged = sim.simulate_merged(first, nb, 1234)
+    with tp3.Simulator(cfg) as sim:
+        sim.set_option("fe_host_scan", 1).set_option("fe_split", 1)
+        host = sim.simulate_batches(first, nb, 1234)
+        host_next = sim.simulate_batches(first + nb - 1, 20)
+        host_again = sim.simulate_batches(first + 5, 20)
+    assert sum(a.selected_events for a in dev) > 0
+    rel = 2e-12 if "f32" not in features else 5e-5
+    for got, want in list(zip(dev, host)) + list(zip(dev_next, host_next)) + list(zip(dev_again, host_again)):
+        assert got.selected_events == want.selected_events
+        assert_acc_close(got, want, rel, what="stream pipeline vs host walk")
+    assert bytes(merged) == bytes(tp3.fold(dev, cfg.flags))
+    if opts:
+        assert passes > 10 and redone > 0, (passes, redone)
+        with tp3.Simulator(cfg) as sim:
+            plain = sim.simulate_batches(first, nb, 1234)
+        assert bytes(plain) == bytes(dev)
+
+
 @pytest.mark.parametrize("features,first,nb", [("faster-evgen,standard-random", 0, 300), ("faster-evgen,standard-random", 1990, 130),
                                                ("faster-evgen,standard-random,f32", 7, 64)])
 @pytest.mark.parametrize("split", [1, 32])

@@ -187,6 +187,7 @@ def lib() -> C.CDLL:
         "tp3_format_res_data": (C.c_size_t, [P(Config), u32, P(Final), C.c_char_p, C.c_size_t]),
         "tp3_format_stdout": (C.c_size_t, [P(Config), u32, P(Final), C.c_char_p, C.c_size_t]),
         "tp3_run": (C.c_int, [C.c_char_p, C.c_char_p, u32, u32, C.c_int, C.c_char_p, C.c_size_t, P(dbl)]),
+        "tp3_run_stages": (C.c_int, [C.c_char_p, C.c_char_p, u32, u32, C.c_int, C.c_char_p, C.c_size_t, P(dbl), P(dbl)]),
         "tp3_host_ranf_round": (C.c_int, [i32, u64, P(u32)]),
         "tp3_host_xoshiro_state": (C.c_int, [C.c_int, u64, u64, P(u64)]),
     }
@@ -204,7 +205,7 @@ ABI_SYMBOLS = [
     "tp3_rng_dump", "tp3_events_dump", "tp3_peak_probe", "tp3_fastmath_probe", "tp3_config_parse", "tp3_params_from_config", "tp3_merge",
     "tp3_finalize", "tp3_format_res_data", "tp3_format_stdout", "tp3_run", "tp3_host_ranf_round",
     "tp3_host_xoshiro_state", "tp3_histograms_enable", "tp3_histograms_reset", "tp3_histograms_fetch",
-    "tp3_simulate_merged_device", "tp3_fold_batches", "tp3_set_option", "tp3_get_stat", "tp3_kernel_arg_bytes",
+    "tp3_simulate_merged_device", "tp3_fold_batches", "tp3_set_option", "tp3_get_stat", "tp3_kernel_arg_bytes", "tp3_run_stages",
 ]
 
 
@@ -491,6 +492,44 @@ def acc_from_f64x13(values) -> Acc:
         a.vars[k] = values[6 + k]
     a.sigma, a.variance = values[11], values[12]
     return a
+
+
+def acc_to_f64x13(a: Acc) -> List[float]:
+    """An accumulator as the 13 doubles of tp3_simulate_merged_device: {count, spm2[5], vars[5], sigma, variance}."""
+    return [float(a.selected_events)] + list(a.spm2) + list(a.vars) + [a.sigma, a.variance]
+
+
+def run_simulation_reduced(cfg: Configuration, merged13, world_size: int, rank: int, dist=None):
+    """scheduling::run_simulation over `world_size` processes with the ORDER-INSENSITIVE merge of the reference's
+    faster-threading mode (FastAccumulator, multi_threading.rs:130-190): rank r simulates its contiguous batch range
+    (shard_range; multi_threading.rs:25,46-70) and folds it in batch order; `merged13(first, n, last_len)` returns that
+    fold as a torch tensor of 13 float64 (on the GPU: Simulator.simulate_merged_device into a CUDA tensor); ONE
+    reduce(sum) to rank 0 is the run's only exchange; rank 0 finalizes (None elsewhere).  Reproducible for a fixed
+    world size; selected_events is exact for any."""
+    nb, last = batch_layout(cfg.num_events)
+    lo, cnt = shard_range(nb, world_size, rank)
+    my_last = last if lo + cnt == nb else EVENT_BATCH_SIZE
+    t = merged13(lo, cnt, my_last)
+    if world_size > 1:
+        dist.reduce(t, dst=0)
+        if rank != 0:
+            return None
+    return finalize(cfg, acc_from_f64x13(t.cpu().tolist()))
+
+
+RUN_STAGES = ("read + parse valeurs", "context creation", "simulation", "finalize", "format + write outputs", "context destruction")
+
+
+def main_run_stages(valeurs_path: str, out_dir: str = "", features="", kernel: int = KERNEL_FAST, n_dev: int = 1):
+    """tp3_run_stages: (stdout text, reference-style elapsed seconds, {stage name: seconds})."""
+    buf = C.create_string_buffer(1 << 16)
+    secs = C.c_double()
+    stages = (C.c_double * len(RUN_STAGES))()
+    rc = lib().tp3_run_stages(valeurs_path.encode(), out_dir.encode(), feature_mask(features), kernel, n_dev, buf, len(buf),
+                              C.byref(secs), stages)
+    if rc != OK:
+        raise Tp3Error(rc, buf.value.decode())
+    return buf.value.decode(), float(secs.value), dict(zip(RUN_STAGES, stages))
 
 
 # ------------------------------------------------------------------------------ multi-process

@@ -84,6 +84,7 @@ struct tp3_ctx {
     // tp3_set_option: test / A-B switches, read once here instead of from the environment on every launch
     int64_t opt_unit_batches = 0;    // consecutive batches per scheduling unit (0 = by launch size)
     int64_t opt_grid_warps = 0;      // warps in the grid (0 = what the device holds at once)
+    int64_t opt_sched_dynamic = 1;   // 1 (default): one unit per warp, dispatched by the hardware in unit order; 0: static balanced schedule (kernels.cuh)
     int64_t opt_f32_scalar = 0;      // f32: one event per lane instead of the packed two-events-per-lane kernel
     int64_t opt_fe_split = 0;        // faster-evgen: 1 = one thread per batch, 32 = one lane per 313 events, 0 = by launch size
     int64_t opt_fe_host_scan = 0;    // faster-evgen: batch start states from the host walk (the reference's method; cross-check)
@@ -161,6 +162,7 @@ struct Sched {
     int64_t unit_batches;  // 0 = auto
     int64_t grid_warps;    // 0 = auto
     bool stream_continues; // sequential RANF: a warp's next batch continues the stream, so units of several batches pay
+    int64_t dynamic;       // 1: one unit per warp, dispatched by the hardware (kernels.cuh)
 };
 
 // Fill the schedule fields of `a` for a kernel that runs `warps`-warp CTAs, `ctas_per_sm` of them per SM.
@@ -168,6 +170,19 @@ cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& s
     if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
     uint64_t W = (uint64_t)sc.sm_count * ctas_per_sm * warps;  // what the device holds at once
     if (sc.grid_warps > 0) W = ((uint64_t)sc.grid_warps + warps - 1) / warps * warps;
+    if (sc.dynamic) {
+        // Units in batch order, one warp each: big units of `unit` batches, then single batches for the last ~4 waves.
+        uint64_t unit = sc.stream_continues ? 8 : 1;
+        if (sc.unit_batches > 0) unit = (uint64_t)sc.unit_batches;
+        const uint64_t singles = std::min<uint64_t>(a.n_batches, 4 * W);
+        const uint64_t big = unit > 1 ? (a.n_batches - singles) / unit : 0;
+        const uint64_t units = big + (a.n_batches - big * unit);
+        a.dynamic = 1;
+        a.unit_batches = (uint32_t)unit;
+        a.full_rounds = (uint32_t)big;
+        a.n_warps = (uint32_t)((units + warps - 1) / warps * warps);
+        return cudaSuccess;
+    }
     if (a.n_batches < W) W = (a.n_batches + warps - 1) / warps * warps;  // one batch per warp, no full round
     uint64_t unit = 1;
     if (sc.stream_continues) {
@@ -996,7 +1011,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         a.hist_counts = s.d_hist_counts;
         a.hist_weights = s.d_hist_weights;
         const Sched sc{s.sm_count, c->opt_unit_batches, c->opt_grid_warps,
-                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING))};
+                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic};
         if (fold) {
             // Completion marks: one word per unit, compared with this launch's epoch (no memset per launch).  The number
             // of units is at most n + the grid's warps; the grid never exceeds 64 warps per SM.
@@ -1344,6 +1359,7 @@ int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
     const std::string k(name);
     if (k == "unit_batches" && value >= 0 && value <= 4096) c->opt_unit_batches = value;
     else if (k == "grid_warps" && value >= 0 && value <= (1 << 20)) c->opt_grid_warps = value;
+    else if (k == "sched_dynamic") c->opt_sched_dynamic = value != 0;
     else if (k == "f32_scalar") c->opt_f32_scalar = value != 0;
     else if (k == "fe_split" && (value == 0 || value == 1 || value == 32)) c->opt_fe_split = value;
     else if (k == "fe_host_scan") c->opt_fe_host_scan = value != 0;

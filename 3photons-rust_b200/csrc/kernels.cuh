@@ -9,13 +9,16 @@
 // barrier after the prologue, so warps never wait for each other.  What bounds it (the vector register file) and what
 // follows from that is in DESIGN.md section 4d.
 //
-// Scheduling (multi_threading.rs:46-70 hands out batches to workers; here the hand-out is static): the grid is exactly
-// the number of warps the device holds at once (W), and the launch's batches are cut into UNITS of consecutive batches,
-// in batch order: `full_rounds` rounds of W units of `unit_batches` batches each (unit r W + w belongs to warp w), then
-// one last round in which the remaining batches are split evenly over the W warps (sizes differ by at most one batch).
-// Every warp therefore does the same work to within ONE batch whatever the launch size (no wave quantisation), the
-// sequential RANF stream is re-positioned once per unit, and units complete roughly in batch order, which is what the
-// ordered fold below needs.
+// Scheduling (multi_threading.rs:46-70 hands out batches to its workers one by one).  The launch's batches are cut into UNITS
+// of consecutive batches, in batch order; the sequential RANF stream is re-positioned once per unit and simply continues
+// inside it.  Two schedules (profiles/r02_schedule_ab.txt):
+//   * dynamic (shipped): one warp per unit, dispatched by the hardware in unit order.  Units of 8 batches first, then
+//     single batches for the last ~4 waves, so that the device drains within one batch time whatever the launch size
+//     (round 1 used 1-8 equal batches per CTA: 8.8 waves and a 3 % tail at 125 000 batches per GPU).
+//   * static: exactly as many warps as the device holds, each walking the same number of units (+- one batch).  No tail
+//     at all, but 11 % SLOWER: warps that start together stay in step, so their integer phases (stream generation)
+//     and FP64 phases collide instead of overlapping; warps that start at staggered times do not.
+// Units complete roughly in batch order either way, which is what the ordered fold below needs.
 //
 // Ordered fold (ResultsAccumulator::merge in batch order, sequential.rs:24-36 / multi_threading.rs:107-126) inside the
 // kernel: a warp that finishes a unit publishes it and then TRIES to take the fold lock; the holder adds every unit
@@ -81,6 +84,8 @@ struct SimArgs {
     uint32_t n_warps;          // W: warps in the grid
     uint32_t unit_batches;     // consecutive batches per unit in the full rounds (the RANF stream simply continues inside a unit)
     uint32_t full_rounds;      // rounds of W full units; the rest is split evenly in one more round
+    uint32_t dynamic;          // 1: one unit per warp, n_warps units dispatched by the hardware in unit order: `full_rounds` units of
+                               //    unit_batches batches first, then single batches (the last waves are short, so the tail is < 1 batch)
     uint32_t epoch;            // value that marks a unit of THIS launch as done in unit_done
     uint32_t* unit_done;       // [(full_rounds + 1) * W], or null: no in-kernel fold
     struct FoldState* fold;    // running accumulator of the ordered fold, or null
@@ -362,8 +367,16 @@ __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
 }
 
 // Batches [lo, hi) of the launch that make up unit u.
+// (dynamic schedule: n_warps has its top bit set, `full_rounds` is the number of big units, the rest are single batches)
+constexpr uint32_t kSchedDynamic = 0x80000000u;
 __device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint64_t n_batches, uint64_t u,
                                            uint64_t& lo, uint64_t& hi) {
+    if (n_warps & kSchedDynamic) {
+        const uint64_t big = full_rounds;
+        lo = u < big ? u * unit_batches : big * unit_batches + (u - big);
+        hi = u < big ? lo + unit_batches : lo + 1;
+        return;
+    }
     const uint64_t W = n_warps, full = (uint64_t)full_rounds * W;
     if (u < full) {
         lo = u * unit_batches;
@@ -375,7 +388,12 @@ __device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_round
     }
 }
 __device__ __forceinline__ void unit_range(const SimArgs& a, uint64_t u, uint64_t& lo, uint64_t& hi) {
-    unit_range(a.n_warps, a.full_rounds, a.unit_batches, a.n_batches, u, lo, hi);
+    unit_range(a.dynamic ? (a.n_warps | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.n_batches, u, lo, hi);
+}
+// Number of units of a launch.
+__device__ __forceinline__ uint64_t unit_count(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint64_t n_batches) {
+    if (n_warps & kSchedDynamic) return (uint64_t)full_rounds + (n_batches - (uint64_t)full_rounds * unit_batches);
+    return ((uint64_t)full_rounds + 1) * n_warps;
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -391,7 +409,7 @@ __device__ __forceinline__ void fence_sc() { asm volatile("fence.sc.gpu;" ::: "m
 template <class F>
 __device__ __noinline__ void fold_publish(FoldState* fs, uint32_t* unit_done, const tp3_acc* out, uint32_t n_warps, uint32_t full_rounds,
                                           uint32_t unit_batches, uint32_t epoch, uint64_t n_batches, uint64_t u, int lane) {
-    const uint64_t n_units = ((uint64_t)full_rounds + 1) * n_warps;
+    const uint64_t n_units = unit_count(n_warps, full_rounds, unit_batches, n_batches);
     __syncwarp();
     if (lane == 0) {
         __threadfence();  // this unit's accumulators (written by lane 0) before the flag
@@ -419,7 +437,8 @@ __device__ __noinline__ void fold_publish(FoldState* fs, uint32_t* unit_done, co
         for (;;) {
             // how many of the next 32 units are complete: one flag per lane, one round trip
             const bool ready = nu + lane < n_units && ld_acquire_u32(unit_done + nu + lane) == epoch;
-            const unsigned m = __ffs(~__ballot_sync(0xffffffffu, ready)) - 1;  // leading run of ready units (32 if all)
+            const unsigned not_ready = ~__ballot_sync(0xffffffffu, ready);
+            const unsigned m = not_ready ? (unsigned)__ffs(not_ready) - 1u : 32u;  // leading run of ready units
             if (m == 0) break;
             uint64_t lo, hi, lo2;
             unit_range(n_warps, full_rounds, unit_batches, n_batches, nu, lo, hi);
@@ -481,10 +500,12 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
 
     WarpRng<F, RNG> rng;
     const uint64_t wid = (uint64_t)blockIdx.x * kWarps + warp;
-  for (uint32_t round = 0; round <= a.full_rounds; ++round) {
+  const uint32_t last_round = a.dynamic ? 0u : a.full_rounds;  // dynamic schedule: this warp's one unit is unit `wid`
+  for (uint32_t round = 0; round <= last_round; ++round) {
     const uint64_t unit = (uint64_t)round * a.n_warps + wid;
     uint64_t unit_lo, unit_hi;
     unit_range(a, unit, unit_lo, unit_hi);
+    if (unit_lo >= a.n_batches) break;  // (warps past the last unit of a dynamic grid rounded up to whole CTAs)
   for (uint64_t slot = unit_lo; slot < unit_hi; ++slot) {
     const int n_ev = batch_len(a, slot);
     if (slot == unit_lo || !rng.next_batch(a, n_ev, lane)) rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
@@ -595,7 +616,7 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
     }
     __syncwarp();
   }
-    if (a.fold) fold_publish<F>(a.fold, a.unit_done, a.out, a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+    if (a.fold) fold_publish<F>(a.fold, a.unit_done, a.out, a.dynamic ? (a.n_warps | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
   }
     if (HIST) {  // CTA histograms -> device histograms
         __syncthreads();
@@ -624,10 +645,12 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
 
     WarpRng<F, RNG> rng;
     const uint64_t wid = (uint64_t)blockIdx.x * kWarps + warp;
-  for (uint32_t round = 0; round <= a.full_rounds; ++round) {
+  const uint32_t last_round = a.dynamic ? 0u : a.full_rounds;  // dynamic schedule: this warp's one unit is unit `wid`
+  for (uint32_t round = 0; round <= last_round; ++round) {
     const uint64_t unit = (uint64_t)round * a.n_warps + wid;
     uint64_t unit_lo, unit_hi;
     unit_range(a, unit, unit_lo, unit_hi);
+    if (unit_lo >= a.n_batches) break;  // (warps past the last unit of a dynamic grid rounded up to whole CTAs)
     for (uint64_t slot = unit_lo; slot < unit_hi; ++slot) {
         const int n_ev = batch_len(a, slot);
         if (slot == unit_lo || !rng.next_batch(a, n_ev, lane)) rng.init(a, &smw[warp], a.first_batch + slot, slot, n_ev, lane);
@@ -763,7 +786,7 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
         }
         __syncwarp();
     }
-    if (a.fold) fold_publish<float>(a.fold, a.unit_done, a.out, a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+    if (a.fold) fold_publish<float>(a.fold, a.unit_done, a.out, a.dynamic ? (a.n_warps | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
   }
 }
 

@@ -549,6 +549,16 @@ size_t tp3_format_stdout(const tp3_config* cfg, uint32_t flags, const tp3_final*
 
 int tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint32_t kernel, int n_dev, char* stdout_buf,
             size_t stdout_cap, double* elapsed) {
+    return tp3_run_stages(valeurs_path, out_dir, flags, kernel, n_dev, stdout_buf, stdout_cap, elapsed, nullptr);
+}
+
+int tp3_run_stages(const char* valeurs_path, const char* out_dir, uint32_t flags, uint32_t kernel, int n_dev, char* stdout_buf,
+                   size_t stdout_cap, double* elapsed, double* stages) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+    };
+    if (stages) std::fill(stages, stages + TP3_RUN_STAGES, 0.0);
     std::ifstream in(valeurs_path ? valeurs_path : "valeurs");
     if (!in) {
         emit("failed to load the configuration", stdout_buf, stdout_cap);
@@ -563,6 +573,7 @@ int tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint3
         emit(std::string("failed to load the configuration: ") + err, stdout_buf, stdout_cap);
         return rc;
     }
+    if (stages) stages[0] = since(t_begin);
     // The reference starts its clock after configuration I/O (main.rs:83-85) ...
     const auto t0 = std::chrono::steady_clock::now();
     tp3_params params;
@@ -573,6 +584,8 @@ int tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint3
         emit(tp3_last_error(nullptr), stdout_buf, stdout_cap);
         return rc;
     }
+    if (stages) stages[1] = since(t0);
+    const auto t_sim = std::chrono::steady_clock::now();
     // scheduling: ceil(N / 10000) batches, the last one possibly short (multi_threading.rs:25,47);
     // left fold in batch order (sequential.rs:24-36)
     const uint64_t nb = (cfg.num_events + TP3_EVENT_BATCH_SIZE - 1) / TP3_EVENT_BATCH_SIZE;
@@ -585,11 +598,16 @@ int tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint3
         tp3_destroy(ctx);
         return rc;
     }
+    if (stages) stages[2] = since(t_sim);
+    const auto t_fin = std::chrono::steady_clock::now();
     tp3_final fin;
     tp3_finalize(&cfg, flags, &total, &fin);
     // ... and stops it before output (main.rs:138)
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (stages) stages[3] = since(t_fin);
+    const auto t_out = std::chrono::steady_clock::now();
     tp3_destroy(ctx);
+    if (stages) stages[5] = since(t_out);
     if (elapsed) *elapsed = secs;
 
     std::string so(tp3_format_stdout(&cfg, flags, &fin, nullptr, 0) + 1, '\0');

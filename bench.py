@@ -265,15 +265,18 @@ def main():
 
         # ---- end to end through the C ABI ("e2e"): what a caller of the reference's run_simulation gets — the merged
         # accumulator of the whole run on the HOST, finalized.
+        def merged13(first, n_b, last_len):
+            sim.simulate_merged_device(first, n_b, last_len, out13.data_ptr())
+            return out13
+
         def e2e_step():
             if world == 1:
                 return pkg.finalize(cfg, sim.simulate_merged(lo, cnt, my_last))
-            step_device()
-            dist.reduce(out13, dst=0, op=dist.ReduceOp.SUM)  # the run's one inter-GPU exchange: 13 doubles
+            # tp3_simulate_merged_device + the run's one inter-GPU exchange (ncclReduce of 13 doubles) + 104-byte D2H + finalize
+            fin_ = pkg.run_simulation_reduced(cfg, merged13, world, rank, dist)
             if rank != 0:
                 torch.cuda.synchronize()
-                return None
-            return pkg.finalize(cfg, pkg.acc_from_f64x13(out13.cpu().tolist()))  # 104-byte device->host copy
+            return fin_
 
         for _ in range(2):
             fin = e2e_step()

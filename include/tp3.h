@@ -215,6 +215,13 @@ size_t tp3_format_stdout(const tp3_config* cfg, uint32_t flags, const tp3_final*
  * res.times and appends pil.mc in out_dir, returns the stdout text in stdout_buf. */
 int  tp3_run(const char* valeurs_path, const char* out_dir, uint32_t flags, uint32_t kernel, int n_dev,
              char* stdout_buf, size_t stdout_cap, double* elapsed_seconds);
+/* The same, with the wall time of its stages in stages[TP3_RUN_STAGES] (seconds): 0 read + parse `valeurs`,
+ * 1 context creation (device tables, streams), 2 simulation (launch to merged accumulator on the host),
+ * 3 finalize, 4 formatting + writing res.data / res.times / pil.mc, 5 context destruction.  The reference's own
+ * timed region (main.rs:83-85,138) is stages 1 + 2 + 3 = *elapsed_seconds. */
+#define TP3_RUN_STAGES 6
+int  tp3_run_stages(const char* valeurs_path, const char* out_dir, uint32_t flags, uint32_t kernel, int n_dev,
+                    char* stdout_buf, size_t stdout_cap, double* elapsed_seconds, double* stages);
 
 /* Host mirror of the device RANF jump-ahead (no GPU needed): state of the generator's
  * 55-word round `round` (0 = after seeding + warm-up), numbers[1..55] -> out[0..54]. */

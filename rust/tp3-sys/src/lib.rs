@@ -133,6 +133,8 @@ extern "C" {
     pub fn tp3_format_stdout(cfg: *const tp3_config, flags: u32, fin: *const tp3_final, buf: *mut c_char, cap: usize) -> usize;
     pub fn tp3_run(valeurs_path: *const c_char, out_dir: *const c_char, flags: u32, kernel: u32, n_dev: c_int,
                    stdout_buf: *mut c_char, stdout_cap: usize, elapsed_seconds: *mut f64) -> c_int;
+    pub fn tp3_run_stages(valeurs_path: *const c_char, out_dir: *const c_char, flags: u32, kernel: u32, n_dev: c_int,
+                          stdout_buf: *mut c_char, stdout_cap: usize, elapsed_seconds: *mut f64, stages: *mut f64) -> c_int;
     pub fn tp3_host_ranf_round(seed: i32, round: u64, out55: *mut u32) -> c_int;
     pub fn tp3_host_xoshiro_state(f32_: c_int, n_steps: u64, n_jumps: u64, out4: *mut u64) -> c_int;
 }

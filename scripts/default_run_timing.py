@@ -1,16 +1,27 @@
-"""Wall time of the whole default run (10^7 events) through tp3_run and its parts (development aid)."""
+"""Wall time of the whole default run (10^7 events, BASELINE configs[1]) through tp3_run, stage by stage
+(the reference's own timed region is main.rs:83-85,138 = context creation + simulation + finalize).
+usage: default_run_timing.py [features]"""
 import os, sys, time, tempfile, shutil
-sys.path.insert(0, os.getcwd())
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import __graft_entry__ as g
 pkg = g.package()
-text = open("tests/golden/valeurs").read()
-d = tempfile.mkdtemp(); open(os.path.join(d, "valeurs"), "w").write(text)
-for i in range(3):
-    t0 = time.perf_counter(); out, secs = pkg.main_run(os.path.join(d, "valeurs"), d); t1 = time.perf_counter()
-    print(f"tp3_run: wall {1e3*(t1-t0):.1f} ms, reference-style timed region {1e3*secs:.1f} ms")
-cfg = pkg.Configuration.parse(text)
-t0 = time.perf_counter(); sim = pkg.Simulator(cfg); t1 = time.perf_counter()
-for i in range(3):
-    t2 = time.perf_counter(); accs = sim.simulate_batches(0, 1000); t3 = time.perf_counter()
-    print(f"create {1e3*(t1-t0):.1f} ms; simulate_batches(1000 batches) {1e3*(t3-t2):.2f} ms -> {1e7/(t3-t2):.3g} events/s")
-sim.close(); shutil.rmtree(d)
+features = sys.argv[1] if len(sys.argv) > 1 else ""
+text = open(os.path.join(ROOT, "tests", "golden", "valeurs")).read()
+d = tempfile.mkdtemp()
+open(os.path.join(d, "valeurs"), "w").write(text)
+print(f"# tp3_run_stages, default valeurs (1e7 events), features {features!r}; run 0 includes CUDA initialisation and module load")
+for i in range(4):
+    t0 = time.perf_counter()
+    out, secs, stages = pkg.main_run_stages(os.path.join(d, "valeurs"), d, features)
+    wall = time.perf_counter() - t0
+    print(f"run {i}: wall {1e3 * wall:8.2f} ms, reference-style timed region {1e3 * secs:8.2f} ms  |  " +
+          "  ".join(f"{k} {1e3 * v:.2f} ms" for k, v in stages.items()))
+cfg = pkg.Configuration.parse(text, features)
+with pkg.Simulator(cfg) as sim:
+    for i in range(4):
+        t0 = time.perf_counter()
+        acc = sim.simulate_merged(0, 1000)
+        dt = time.perf_counter() - t0
+        print(f"tp3_simulate_merged(1000 batches) on a warm context: {1e3 * dt:.3f} ms -> {1e7 / dt:.3g} events/s")
+shutil.rmtree(d)

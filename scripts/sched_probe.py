@@ -17,7 +17,7 @@ sys.path.insert(0, %(root)r)
 import torch
 import __graft_entry__ as entry
 pkg = entry.package()
-n, features, mode, unit = %(n)d, %(features)r, %(mode)r, %(unit)d
+n, features, mode, unit, grid = %(n)d, %(features)r, %(mode)r, %(unit)d, %(grid)d
 text = open(os.path.join(%(root)r, "tests", "golden", "valeurs")).read()
 cfg = pkg.Configuration.parse(text, features).with_num_events(n * 10000)
 sim = pkg.Simulator(cfg)
@@ -25,6 +25,8 @@ st = torch.cuda.current_stream()
 sim.set_stream(st.cuda_stream)
 if unit >= 0 and hasattr(sim, "set_option"):
     sim.set_option("unit_batches", unit)
+if grid > 0:
+    sim.set_option("grid_warps", grid)
 out13 = torch.zeros(13, dtype=torch.float64, device="cuda")
 def step():
     if mode == "nofold":
@@ -44,19 +46,16 @@ print(json.dumps({"ms": round(ms, 3), "events_per_s": float("%%.4g" %% (n * 1000
 '''
 
 
-def run(lib, mode, unit):
+def run(lib, mode, unit, grid=0):
     env = dict(os.environ)
     if lib:
         env["TP3_LIB"] = lib
-    code = CHILD % {"root": ROOT, "n": n_batches, "features": features, "mode": mode, "unit": unit}
+    code = CHILD % {"root": ROOT, "n": n_batches, "features": features, "mode": mode, "unit": unit, "grid": grid}
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     return r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else "FAILED " + r.stderr[-300:]
 
 
 print(f"# {n_batches} batches, features {features!r}", flush=True)
-r01 = os.path.join(ROOT, "3photons-rust_b200", "_build", "libtp3_r01.so")
-if os.path.exists(r01):
-    print("round-1 library, per-batch accumulators only :", run(r01, "nofold", -1), flush=True)
-for unit in (-1, 1, 2, 4, 16, 64):
-    print(f"round 2, unit_batches={unit:3d}, no fold            :", run(None, "nofold", unit), flush=True)
-    print(f"round 2, unit_batches={unit:3d}, in-kernel fold     :", run(None, "fold", unit), flush=True)
+for unit, grid in ((-1, 0), (8, n_batches // 8), (4, n_batches // 4), (1, n_batches), (8, 2368 * 4), (8, 2368 * 16), (1, 0)):
+    print(f"unit_batches={unit:3d} grid_warps={grid:8d} (0 = resident warps, static), no fold        :", run(None, "nofold", unit, grid), flush=True)
+    print(f"unit_batches={unit:3d} grid_warps={grid:8d} (0 = resident warps, static), in-kernel fold :", run(None, "fold", unit, grid), flush=True)

@@ -51,10 +51,18 @@ def _worker(rank, world, port, valeurs_text, q):
     local = tp3.Histograms(4, [[rank + 1 + b for b in range(4)] for _ in range(tp3.HIST_OBSERVABLES)],
                            [[0.5 * (rank + 1) * (b + 1) for b in range(4)] for _ in range(tp3.HIST_OBSERVABLES)])
     total = tp3.reduce_histograms(local, world, rank, dist, "cpu")
+    # the order-insensitive merge: every rank folds its own range, one reduce(sum) of 13 doubles (the path bench.py times at N > 1)
+    import torch
+    simulate_range = _oracle_range_simulator(tp3, valeurs_text, N_EVENTS)
+
+    def merged13(first, n, last_len):
+        return torch.tensor(tp3.acc_to_f64x13(tp3.fold(simulate_range(first, n, last_len))), dtype=torch.float64)
+
+    red = tp3.run_simulation_reduced(cfg, merged13, world, rank, dist)
     if rank == 0:
-        q.put((fin.selected_events, fin.sigma, fin.res_data(), total.counts, total.weights))
+        q.put((fin.selected_events, fin.sigma, fin.res_data(), total.counts, total.weights, red.selected_events, red.sigma, red.res_data()))
     else:
-        assert fin is None and total is None
+        assert fin is None and total is None and red is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,7 +77,7 @@ def test_sharded_run_is_bit_identical_to_single_process(tp3, oracle, valeurs_tex
     procs = [ctx.Process(target=_worker, args=(r, world, port, valeurs_text, q)) for r in range(world)]
     for p in procs:
         p.start()
-    sel, sigma, res, hist_counts, hist_weights = q.get(timeout=120)
+    sel, sigma, res, hist_counts, hist_weights, red_sel, red_sigma, red_res = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -77,6 +85,9 @@ def test_sharded_run_is_bit_identical_to_single_process(tp3, oracle, valeurs_tex
     ranks = world * (world + 1) // 2  # sum of (rank + 1)
     assert hist_counts == [[ranks + world * b for b in range(4)]] * tp3.HIST_OBSERVABLES
     assert hist_weights == [[0.5 * ranks * (b + 1) for b in range(4)]] * tp3.HIST_OBSERVABLES
-    # and the fold agrees with the oracle's own whole-run text
+    # the reduced (fold of per-rank folds) result: same events, sums equal up to the association of one addition per field
     from numdiff import compare
+    assert red_sel == sel and abs(red_sigma - sigma) <= 1e-14 * abs(sigma)
+    assert compare(red_res, res, rel=1e-13) == []
+    # and the fold agrees with the oracle's own whole-run text
     assert compare(res, oracle.run(valeurs_text, "", num_events=N_EVENTS).res_data) == []

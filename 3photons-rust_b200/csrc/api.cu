@@ -57,18 +57,31 @@ struct DeviceSlot {
     size_t xo_scan_cap = 0;
     void* d_xo_bnd = nullptr;
     size_t xo_bnd_cap = 0;
-    // faster-evgen stream pipeline (fe_stream.cuh): grow-only workspaces
-    FeRecord* d_fs_records = nullptr;
-    size_t fs_records_cap = 0;        // records
-    uint32_t* d_fs_count = nullptr;   // per segment: events started
-    uint8_t *d_fs_exit = nullptr, *d_fs_fail = nullptr;
-    uint64_t* d_fs_seg_events = nullptr;
-    uint32_t* d_fs_redo_list = nullptr;
-    uint8_t* d_fs_redo_entry = nullptr;
-    size_t fs_seg_cap = 0;
-    uint32_t* d_fs_unit_seg = nullptr;
-    tp3_acc* d_fs_parts = nullptr;
-    size_t fs_unit_cap = 0;
+    // faster-evgen stream pipeline (fe_stream.cuh): two sets of grow-only workspaces, so that the walk of pass k + 1
+    // (integer work) runs next to the physics of pass k (FP64 work) on a second stream
+    struct FsBuf {
+        FeRecord* d_records = nullptr;
+        size_t records_cap = 0;
+        uint32_t* d_count = nullptr;     // per segment: events started
+        uint8_t *d_exit = nullptr, *d_fail = nullptr;
+        uint64_t* d_seg_events = nullptr;
+        uint32_t* d_redo_list = nullptr;
+        uint8_t* d_redo_entry = nullptr;
+        size_t seg_cap = 0;
+        uint32_t* d_unit_seg = nullptr;
+        tp3_acc* d_parts = nullptr;
+        size_t unit_cap = 0;
+        cudaStream_t st = nullptr;       // buffer 0: the slot's stream; buffer 1: fs_stream2
+        // host side of the pass in flight on this buffer
+        std::vector<uint32_t> h_count, h_unit_seg;
+        std::vector<uint8_t> h_exit, h_fail;
+        std::vector<uint64_t> h_seg_events;
+        uint64_t first_round = 0, first_events = 0, n_seg = 0;
+        uint32_t seg_rounds = 0;
+        bool count_only = false;
+    } fs[2];
+    cudaStream_t fs_stream2 = nullptr;
+    cudaEvent_t fs_event = nullptr;
     // last launch
     uint64_t last_first = 0, last_n = 0;
 };
@@ -95,6 +108,7 @@ struct tp3_ctx {
     int64_t opt_fe_pass_segments = 0;// faster-evgen stream pipeline: segments per pass (0 = one full wave of lanes)
     int64_t opt_fe_seg_rounds = 0;   // ... rounds per segment (0 = by pass size, <= 1024)
     int64_t opt_fe_warm = 0;         // ... warm-up rounds before a segment (0 = kFeWarm); small values exercise the redo path
+    int64_t opt_fe_serial = 0;       // ... 1: passes one after the other on the slot's stream (no walk / physics overlap)
     int64_t stat_fe_passes = 0, stat_fe_redone = 0;  // passes and redone segments of the last call
     // faster-evgen stream pipeline: a round (segment boundary of an earlier pass) whose absolute event index is known
     uint64_t fs_round = 0, fs_events = 0;
@@ -670,95 +684,130 @@ template <class T> int fs_grow(tp3_ctx* c, T*& ptr, size_t& cap, size_t need) {
 }
 
 int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len) {
+    using FsBuf = DeviceSlot::FsBuf;
     const bool f32 = c->params.flags & TP3_F32;
     const uint64_t B = TP3_EVENT_BATCH_SIZE;
     const uint64_t e_lo = first * B, e_hi = (first + n - 1) * B + last_len;  // events wanted: [e_lo, e_hi)
     if (c->fs_events > e_lo) c->fs_round = c->fs_events = 0;                 // the known point is past the start: from the seed again
     c->stat_fe_passes = c->stat_fe_redone = 0;
     const double kRoundsPerEvent = 0.3252;  // 3.076 events start per round on average (measured); only sizes the passes
-    const uint64_t lanes_per_wave = (uint64_t)s.sm_count * 16 * 32;
+    const uint64_t lanes_per_wave = (uint64_t)s.sm_count * 28 * 32;  // the walk kernel alone holds 7 CTAs of 4 warps per SM
     const uint32_t warm = c->opt_fe_warm > 0 ? (uint32_t)c->opt_fe_warm : (uint32_t)kFeWarm;
-    uint64_t done_batches = 0;  // batches [first, first + done_batches) are in s.d_out
-    std::vector<uint32_t> h_count;
-    std::vector<uint8_t> h_exit, h_fail;
-    std::vector<uint64_t> h_seg_events;
-    std::vector<uint32_t> h_unit_seg;
-    while (done_batches < n) {
-        // ---- size of this pass
-        const uint64_t next_event = (first + done_batches) * B;
-        // far from the first wanted event: count-only passes (no records) until about 400 batches before it
-        const bool skipping = (double)(next_event - c->fs_events) * kRoundsPerEvent > 16.0 * (double)lanes_per_wave;
-        const uint64_t want_events = skipping ? next_event - c->fs_events : e_hi - c->fs_events;
-        uint64_t want_rounds = (uint64_t)((double)want_events * kRoundsPerEvent * 1.002) + 4096;
-        uint64_t max_seg = c->opt_fe_pass_segments > 0 ? (uint64_t)c->opt_fe_pass_segments : lanes_per_wave;
+    const bool overlap = !c->opt_fe_serial;
+    if (!s.fs_stream2) {
+        TP3_CUDA(c, cudaStreamCreateWithFlags(&s.fs_stream2, cudaStreamNonBlocking));
+        TP3_CUDA(c, cudaEventCreateWithFlags(&s.fs_event, cudaEventDisableTiming));
+    }
+    s.fs[0].st = s.stream;
+    s.fs[1].st = overlap ? s.fs_stream2 : s.stream;
+    {
+        // Both kernels ask for the largest shared-memory carve-out: CTAs of two kernels only share an SM if they agree on the
+        // L1 / shared split, and the walk of pass k + 1 is meant to run next to the physics of pass k.
+        static bool once = [] {
+            cudaFuncSetAttribute(fe_walk_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(fe_walk_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(fe_physics_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(fe_physics_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return true;
+        }();
+        (void)once;
+    }
+    // the second stream starts after whatever the caller has queued on the slot's stream
+    TP3_CUDA(c, cudaEventRecord(s.fs_event, s.stream));
+    TP3_CUDA(c, cudaStreamWaitEvent(s.fs_stream2, s.fs_event, 0));
+
+    uint64_t done_batches = 0;  // batches [first, first + done_batches) have their physics launched
+    auto launch_walk = [&](FsBuf& b, const FeWalkArgs& a, uint32_t items) {
+        const unsigned blocks = (items + 127) / 128;
+        if (f32) fe_walk_kernel<float><<<blocks, 128, 0, b.st>>>(a);
+        else fe_walk_kernel<double><<<blocks, 128, 0, b.st>>>(a);
+        ++c->launches;
+    };
+    auto walk_args = [&](FsBuf& b) {
+        FeWalkArgs w;
+        std::memset(&w, 0, sizeof w);
+        w.jump_table = s.d_ranf_table;
+        w.first_round = b.first_round;
+        w.n_seg = (uint32_t)b.n_seg;
+        w.seg_rounds = b.seg_rounds;
+        w.warm = warm;
+        w.warm_first = kFeWarmFirst;
+        w.seg_count = b.d_count;
+        w.seg_exit = b.d_exit;
+        w.seg_fail = b.d_fail;
+        w.records = b.count_only ? nullptr : b.d_records;
+        return w;
+    };
+    auto fetch_counts = [&](FsBuf& b) -> int {
+        TP3_CUDA(c, cudaMemcpyAsync(b.h_count.data(), b.d_count, b.n_seg * 4, cudaMemcpyDeviceToHost, b.st));
+        TP3_CUDA(c, cudaMemcpyAsync(b.h_exit.data(), b.d_exit, b.n_seg, cudaMemcpyDeviceToHost, b.st));
+        TP3_CUDA(c, cudaMemcpyAsync(b.h_fail.data(), b.d_fail, b.n_seg, cudaMemcpyDeviceToHost, b.st));
+        return TP3_OK;
+    };
+    // Size pass `b` from the known point (round, events) towards the first batch that still has to be served, and start its walk.
+    auto start_pass = [&](FsBuf& b, uint64_t round, uint64_t events, uint64_t next_batch) -> int {
+        const uint64_t next_event = (first + next_batch) * B;
+        // far from the first wanted event: count-only passes (no records) until about 800 batches before it
+        b.count_only = (double)(next_event - events) * kRoundsPerEvent > 8.0 * (double)lanes_per_wave;
+        const uint64_t want_events = b.count_only ? next_event - events : e_hi - events;
+        const uint64_t want_rounds = (uint64_t)((double)want_events * kRoundsPerEvent * 1.002) + 4096;
+        const uint64_t max_seg = c->opt_fe_pass_segments > 0 ? (uint64_t)c->opt_fe_pass_segments : lanes_per_wave;
         uint32_t seg_rounds = 64;
         if (c->opt_fe_seg_rounds > 0) seg_rounds = (uint32_t)c->opt_fe_seg_rounds;
         else
-            while (seg_rounds < 1024 && want_rounds / seg_rounds > lanes_per_wave) seg_rounds *= 2;  // fill the device first, then lengthen
+            while (seg_rounds < 512 && want_rounds / seg_rounds > lanes_per_wave) seg_rounds *= 2;  // fill the device first, then lengthen
         uint64_t n_seg = (want_rounds + seg_rounds - 1) / seg_rounds;
         if (n_seg > max_seg) n_seg = max_seg;
-        if (skipping) {  // stop a little before the first wanted event, at a segment boundary
+        if (b.count_only) {  // stop a little before the first wanted event, at a segment boundary
             const uint64_t lim = (uint64_t)((double)want_events * kRoundsPerEvent * 0.99) / seg_rounds;
             if (n_seg > lim) n_seg = lim;
             if (n_seg == 0) n_seg = 1;
         }
-        const size_t slots_per_seg = (size_t)kFeSlotsPerRound * seg_rounds;
+        b.first_round = round;
+        b.first_events = events;
+        b.n_seg = n_seg;
+        b.seg_rounds = seg_rounds;
         int rc = TP3_OK;
-        if (!skipping && (rc = fs_grow(c, s.d_fs_records, s.fs_records_cap, (size_t)n_seg * slots_per_seg))) return rc;
-        if (s.fs_seg_cap < n_seg + 1) {
+        if (!b.count_only && (rc = fs_grow(c, b.d_records, b.records_cap, (size_t)n_seg * kFeSlotsPerRound * seg_rounds))) return rc;
+        if (b.seg_cap < n_seg + 1) {
             size_t cap = 0;
-            if ((rc = fs_grow(c, s.d_fs_count, cap, n_seg + 1))) return rc;
-            cap = 0; if ((rc = fs_grow(c, s.d_fs_exit, cap, n_seg + 1))) return rc;
-            cap = 0; if ((rc = fs_grow(c, s.d_fs_fail, cap, n_seg + 1))) return rc;
-            cap = 0; if ((rc = fs_grow(c, s.d_fs_seg_events, cap, n_seg + 1))) return rc;
-            cap = 0; if ((rc = fs_grow(c, s.d_fs_redo_list, cap, n_seg + 1))) return rc;
-            cap = 0; if ((rc = fs_grow(c, s.d_fs_redo_entry, cap, n_seg + 1))) return rc;
-            s.fs_seg_cap = n_seg + 1;
+            if ((rc = fs_grow(c, b.d_count, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, b.d_exit, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, b.d_fail, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, b.d_seg_events, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, b.d_redo_list, cap, n_seg + 1))) return rc;
+            cap = 0; if ((rc = fs_grow(c, b.d_redo_entry, cap, n_seg + 1))) return rc;
+            b.seg_cap = n_seg + 1;
         }
-        // ---- 1. walk
-        FeWalkArgs w;
-        std::memset(&w, 0, sizeof w);
-        w.jump_table = s.d_ranf_table;
-        w.first_round = c->fs_round;
-        w.n_seg = (uint32_t)n_seg;
-        w.seg_rounds = seg_rounds;
-        w.warm = warm;
-        w.warm_first = kFeWarmFirst;
-        w.seg_count = s.d_fs_count;
-        w.seg_exit = s.d_fs_exit;
-        w.seg_fail = s.d_fs_fail;
-        w.records = skipping ? nullptr : s.d_fs_records;
-        auto walk = [&](const FeWalkArgs& a, uint32_t items) {
-            const unsigned blocks = (items + 127) / 128;
-            if (f32) fe_walk_kernel<float><<<blocks, 128, 0, s.stream>>>(a);
-            else fe_walk_kernel<double><<<blocks, 128, 0, s.stream>>>(a);
-            ++c->launches;
-        };
-        walk(w, (uint32_t)n_seg);
+        b.h_count.resize(n_seg);
+        b.h_exit.resize(n_seg);
+        b.h_fail.resize(n_seg);
+        launch_walk(b, walk_args(b), (uint32_t)n_seg);
         TP3_CUDA(c, cudaGetLastError());
-        h_count.resize(n_seg);
-        h_exit.resize(n_seg);
-        h_fail.resize(n_seg);
-        TP3_CUDA(c, cudaMemcpyAsync(h_count.data(), s.d_fs_count, n_seg * 4, cudaMemcpyDeviceToHost, s.stream));
-        TP3_CUDA(c, cudaMemcpyAsync(h_exit.data(), s.d_fs_exit, n_seg, cudaMemcpyDeviceToHost, s.stream));
-        TP3_CUDA(c, cudaMemcpyAsync(h_fail.data(), s.d_fs_fail, n_seg, cudaMemcpyDeviceToHost, s.stream));
-        TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+        return fetch_counts(b);
+    };
+
+    int cur = 0;
+    int rc = start_pass(s.fs[0], c->fs_round, c->fs_events, 0);
+    if (rc) return rc;
+    while (true) {
+        FsBuf& b = s.fs[cur];
+        TP3_CUDA(c, cudaStreamSynchronize(b.st));  // the walk of this pass is over (the physics of the previous pass may still run)
         ++c->stat_fe_passes;
+        const uint64_t n_seg = b.n_seg;
         // ---- segments whose nine walks had not coincided at their start: redo them from the predecessor's exit state
-        for (int round = 0; round < 64; ++round) {
+        for (int round = 0;; ++round) {
             std::vector<uint32_t> list;
             std::vector<uint8_t> entry;
             for (uint64_t g = 0; g < n_seg; ++g) {
-                if (!h_fail[g]) continue;
-                if (g == 0 || h_fail[g - 1] || h_exit[g - 1] == 0xff) {
-                    if (g == 0) {
-                        c->err = "faster-evgen walk: the warm-up of a pass did not settle";
-                        return TP3_E_CUDA;
-                    }
-                    continue;  // its predecessor is redone first
+                if (!b.h_fail[g]) continue;
+                if (g == 0) {
+                    c->err = "faster-evgen walk: the warm-up of a pass did not settle";
+                    return TP3_E_CUDA;
                 }
+                if (b.h_fail[g - 1] || b.h_exit[g - 1] == 0xff) continue;  // its predecessor is redone first
                 list.push_back((uint32_t)g);
-                entry.push_back(h_exit[g - 1]);
+                entry.push_back(b.h_exit[g - 1]);
             }
             if (list.empty()) break;
             if (round == 63) {
@@ -766,92 +815,95 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
                 return TP3_E_INVALID;
             }
             c->stat_fe_redone += (int64_t)list.size();
-            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_redo_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, s.stream));
-            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_redo_entry, entry.data(), entry.size(), cudaMemcpyHostToDevice, s.stream));
-            FeWalkArgs r = w;
-            r.seg_list = s.d_fs_redo_list;
-            r.seg_entry = s.d_fs_redo_entry;
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_redo_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, b.st));
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_redo_entry, entry.data(), entry.size(), cudaMemcpyHostToDevice, b.st));
+            FeWalkArgs r = walk_args(b);
+            r.seg_list = b.d_redo_list;
+            r.seg_entry = b.d_redo_entry;
             r.n_list = (uint32_t)list.size();
-            walk(r, r.n_list);
+            launch_walk(b, r, r.n_list);
             TP3_CUDA(c, cudaGetLastError());
-            TP3_CUDA(c, cudaMemcpyAsync(h_count.data(), s.d_fs_count, n_seg * 4, cudaMemcpyDeviceToHost, s.stream));
-            TP3_CUDA(c, cudaMemcpyAsync(h_exit.data(), s.d_fs_exit, n_seg, cudaMemcpyDeviceToHost, s.stream));
-            TP3_CUDA(c, cudaMemcpyAsync(h_fail.data(), s.d_fs_fail, n_seg, cudaMemcpyDeviceToHost, s.stream));
-            TP3_CUDA(c, cudaStreamSynchronize(s.stream));
+            if ((rc = fetch_counts(b))) return rc;
+            TP3_CUDA(c, cudaStreamSynchronize(b.st));  // (also: `list` and `entry` die with this iteration)
         }
         // ---- 2. absolute index of every segment's first event (multi_threading.rs:59-64 finds these event by event)
-        h_seg_events.resize(n_seg + 1);
-        h_seg_events[0] = c->fs_events;
-        for (uint64_t g = 0; g < n_seg; ++g) h_seg_events[g + 1] = h_seg_events[g] + h_count[g];
-        const uint64_t pass_end = h_seg_events[n_seg];
-        if (skipping) {
-            c->fs_round += n_seg * seg_rounds;
-            c->fs_events = pass_end;
-            continue;
-        }
+        b.h_seg_events.resize(n_seg + 1);
+        b.h_seg_events[0] = b.first_events;
+        for (uint64_t g = 0; g < n_seg; ++g) b.h_seg_events[g + 1] = b.h_seg_events[g] + b.h_count[g];
+        const uint64_t pass_end = b.h_seg_events[n_seg];
         // ---- batches whose events all start in this pass
         uint64_t b_hi = done_batches;
-        while (b_hi < n) {
-            const uint64_t end = (b_hi + 1 == n) ? e_hi : (first + b_hi + 1) * B;
-            if (end > pass_end) break;
-            ++b_hi;
-        }
-        const bool advanced = b_hi > done_batches;
-        if (advanced) {
-            // ---- 3. physics on the records
-            const uint64_t nb = b_hi - done_batches, n_units = nb * kFeParts;
-            if (s.fs_unit_cap < n_units) {
-                size_t cap = 0;
-                if ((rc = fs_grow(c, s.d_fs_unit_seg, cap, n_units))) return rc;
-                cap = 0; if ((rc = fs_grow(c, s.d_fs_parts, cap, n_units))) return rc;
-                s.fs_unit_cap = n_units;
+        if (!b.count_only) {
+            while (b_hi < n) {
+                const uint64_t end = (b_hi + 1 == n) ? e_hi : (first + b_hi + 1) * B;
+                if (end > pass_end) break;
+                ++b_hi;
             }
-            h_unit_seg.resize(n_units);
-            uint64_t g = 0;
-            for (uint64_t u = 0; u < n_units; ++u) {
-                const uint64_t ev = (first + done_batches + u / kFeParts) * B + (u % kFeParts) * (uint64_t)kFePartLen;
-                while (g + 1 < n_seg && h_seg_events[g + 1] <= ev) ++g;
-                h_unit_seg[u] = (uint32_t)g;
-            }
-            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_seg_events, h_seg_events.data(), (n_seg + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-            TP3_CUDA(c, cudaMemcpyAsync(s.d_fs_unit_seg, h_unit_seg.data(), n_units * 4, cudaMemcpyHostToDevice, s.stream));
-            FePhysArgs ph;
-            std::memset(&ph, 0, sizeof ph);
-            ph.records = s.d_fs_records;
-            ph.slots_per_seg = (uint32_t)slots_per_seg;
-            ph.seg_events = s.d_fs_seg_events;
-            ph.unit_seg = s.d_fs_unit_seg;
-            ph.first_event = (first + done_batches) * B;
-            ph.end_event = e_hi;
-            ph.n_units = (uint32_t)n_units;
-            ph.out_parts = s.d_fs_parts;
-            uint64_t W = (uint64_t)s.sm_count * 16;
-            if (c->opt_grid_warps > 0) W = (uint64_t)c->opt_grid_warps;
-            if (W > n_units) W = n_units;
-            ph.n_warps = (uint32_t)W;
-            if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, 0, s.stream>>>(ph, phys_params<float>(c->params));
-            else fe_physics_kernel<double><<<(unsigned)W, 32, 0, s.stream>>>(ph, phys_params<double>(c->params));
-            ++c->launches;
-            TP3_CUDA(c, cudaGetLastError());
-            const unsigned cb = (unsigned)((nb * 13 + 255) / 256);
-            if (f32) fe_combine_parts_kernel<float><<<cb, 256, 0, s.stream>>>(s.d_fs_parts, nb, s.d_out + done_batches);
-            else fe_combine_parts_kernel<double><<<cb, 256, 0, s.stream>>>(s.d_fs_parts, nb, s.d_out + done_batches);
-            ++c->launches;
-            TP3_CUDA(c, cudaGetLastError());
-            TP3_CUDA(c, cudaStreamSynchronize(s.stream));  // the host vectors are reused by the next pass
-            done_batches = b_hi;
         }
-        // ---- the next pass (or call) starts at the last segment boundary at or before the next batch's first event
-        const uint64_t next = (first + done_batches) * B;
-        uint64_t g = n_seg;
-        while (g > 0 && h_seg_events[g] > next) --g;
-        if (g == 0 && !advanced) {  // the pass holds less than the one batch it was sized for
+        // ---- where the next pass (or call) starts: the last segment boundary at or before the next batch's first event
+        const uint64_t next = (first + b_hi) * B;
+        uint64_t g_next = n_seg;
+        while (g_next > 0 && b.h_seg_events[g_next] > next) --g_next;
+        if (g_next == 0 && b_hi == done_batches) {  // the pass holds less than the one batch it was sized for
             c->err = "faster-evgen stream pipeline: a pass must hold at least one batch (fe_pass_segments x fe_seg_rounds too small)";
             return TP3_E_INVALID;
         }
-        c->fs_round += g * seg_rounds;
-        c->fs_events = h_seg_events[g];
+        c->fs_round = b.first_round + g_next * b.seg_rounds;
+        c->fs_events = b.h_seg_events[g_next];
+        const uint64_t lo_batches = done_batches;
+        done_batches = b_hi;
+        const bool more = done_batches < n;
+        // ---- 3. physics on the records of this pass ...
+        if (b_hi > lo_batches) {
+            const uint64_t nb = b_hi - lo_batches, n_units = nb * kFeParts;
+            if (b.unit_cap < n_units) {
+                size_t cap = 0;
+                if ((rc = fs_grow(c, b.d_unit_seg, cap, n_units))) return rc;
+                cap = 0; if ((rc = fs_grow(c, b.d_parts, cap, n_units))) return rc;
+                b.unit_cap = n_units;
+            }
+            b.h_unit_seg.resize(n_units);
+            uint64_t g = 0;
+            for (uint64_t u = 0; u < n_units; ++u) {
+                const uint64_t ev = (first + lo_batches + u / kFeParts) * B + (u % kFeParts) * (uint64_t)kFePartLen;
+                while (g + 1 < n_seg && b.h_seg_events[g + 1] <= ev) ++g;
+                b.h_unit_seg[u] = (uint32_t)g;
+            }
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_seg_events, b.h_seg_events.data(), (n_seg + 1) * 8, cudaMemcpyHostToDevice, b.st));
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_unit_seg, b.h_unit_seg.data(), n_units * 4, cudaMemcpyHostToDevice, b.st));
+            FePhysArgs ph;
+            std::memset(&ph, 0, sizeof ph);
+            ph.records = b.d_records;
+            ph.slots_per_seg = (uint32_t)(kFeSlotsPerRound * b.seg_rounds);
+            ph.seg_events = b.d_seg_events;
+            ph.unit_seg = b.d_unit_seg;
+            ph.first_event = (first + lo_batches) * B;
+            ph.end_event = e_hi;
+            ph.n_units = (uint32_t)n_units;
+            ph.out_parts = b.d_parts;
+            // 12 of the 16 warp slots of an SM when another pass follows: its walk then runs next to this kernel
+            uint64_t W = (uint64_t)s.sm_count * ((more && overlap) ? 12 : 16);
+            if (c->opt_grid_warps > 0) W = (uint64_t)c->opt_grid_warps;
+            if (W > n_units) W = n_units;
+            ph.n_warps = (uint32_t)W;
+            if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, 0, b.st>>>(ph, phys_params<float>(c->params));
+            else fe_physics_kernel<double><<<(unsigned)W, 32, 0, b.st>>>(ph, phys_params<double>(c->params));
+            ++c->launches;
+            TP3_CUDA(c, cudaGetLastError());
+            const unsigned cb = (unsigned)((nb * 13 + 255) / 256);
+            if (f32) fe_combine_parts_kernel<float><<<cb, 256, 0, b.st>>>(b.d_parts, nb, s.d_out + lo_batches);
+            else fe_combine_parts_kernel<double><<<cb, 256, 0, b.st>>>(b.d_parts, nb, s.d_out + lo_batches);
+            ++c->launches;
+            TP3_CUDA(c, cudaGetLastError());
+        }
+        if (!more) break;
+        // ---- ... while the next pass is walked on the other stream (queued behind the physics that last used that buffer)
+        cur ^= 1;
+        if ((rc = start_pass(s.fs[cur], c->fs_round, c->fs_events, done_batches))) return rc;
     }
+    // the slot's stream owns the result
+    TP3_CUDA(c, cudaEventRecord(s.fs_event, s.fs_stream2));
+    TP3_CUDA(c, cudaStreamWaitEvent(s.stream, s.fs_event, 0));
     return TP3_OK;
 }
 
@@ -1127,22 +1179,22 @@ void tp3_destroy(tp3_ctx* c) {
         cudaFree(s.d_out);
         cudaFree(s.d_fold);
         cudaFree(s.d_unit_done);
-        cudaFree(s.d_fs_records);
-        cudaFree(s.d_fs_count);
-        cudaFree(s.d_fs_exit);
-        cudaFree(s.d_fs_fail);
-        cudaFree(s.d_fs_seg_events);
-        cudaFree(s.d_fs_redo_list);
-        cudaFree(s.d_fs_redo_entry);
-        cudaFree(s.d_fs_unit_seg);
-        cudaFree(s.d_fs_parts);
-        cudaFree(s.d_fe_ranf_states);
-        cudaFree(s.d_fe_bnd);
-        cudaFree(s.d_fe_maps);
-        cudaFree(s.d_fe_seg_exit);
-        cudaFree(s.d_fe_seg_state);
-        cudaFree(s.d_fe_seg_count);
-        cudaFree(s.d_fe_seg_events);
+        for (auto& b : s.fs) {
+            cudaFree(b.d_records);
+            cudaFree(b.d_count);
+            cudaFree(b.d_exit);
+            cudaFree(b.d_fail);
+            cudaFree(b.d_seg_events);
+            cudaFree(b.d_redo_list);
+            cudaFree(b.d_redo_entry);
+            cudaFree(b.d_unit_seg);
+            cudaFree(b.d_parts);
+        }
+        if (s.fs_stream2) {
+            cudaStreamSynchronize(s.fs_stream2);
+            cudaStreamDestroy(s.fs_stream2);
+        }
+        if (s.fs_event) cudaEventDestroy(s.fs_event);
         cudaFree(s.d_hist_counts);
         cudaFree(s.d_hist_weights);
     }
@@ -1369,6 +1421,7 @@ int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
     else if (k == "fe_pass_segments" && value >= 0 && value <= (1 << 24)) c->opt_fe_pass_segments = value;
     else if (k == "fe_seg_rounds" && value >= 0 && value <= 4096) c->opt_fe_seg_rounds = value;
     else if (k == "fe_warm" && value >= 0 && value <= 1024) c->opt_fe_warm = value;
+    else if (k == "fe_serial") c->opt_fe_serial = value != 0;
     else {
         c->err = "tp3_set_option: unknown option or value out of range: " + k;
         return TP3_E_INVALID;
@@ -1477,8 +1530,8 @@ int tp3_peak_probe(tp3_ctx* c, int which, double* tflops) {
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
         TP3_CUDA(c, cudaEventRecord(e0, s.stream));
-        if (which == 0) fma_probe_kernel<double><<<blocks, threads, 0, s.stream>>>((double*)buf, iters, 0.999999, 1e-6);
-        else fma_probe_kernel<float><<<blocks, threads, 0, s.stream>>>((float*)buf, iters, 0.999999f, 1e-6f);
+        if (which == 0) fma_probe_kernel<double><<<blocks, threads, 0, s.stream>>>((double*)buf, iters, 0.999999);
+        else fma_probe_kernel<float><<<blocks, threads, 0, s.stream>>>((float*)buf, iters, 0.999999f);
         ++c->launches;
         TP3_CUDA(c, cudaEventRecord(e1, s.stream));
         TP3_CUDA(c, cudaEventSynchronize(e1));

@@ -46,28 +46,37 @@ constexpr int kFeWarm = 24;                       // warm-up rounds before a seg
 constexpr int kFeWarmFirst = 256;                 // ... before the first segment of a pass, which has no predecessor to redo it from
 constexpr int kFeSlotsPerRound = 4;               // an event takes >= 15 of the 55 numbers of a round: at most 4 start in one
 
-// |X^2 + Y^2 - 1e18| up to which the floating-point test of the reference may disagree with the exact one (bounds derived
-// in DESIGN.md section 3c: 24 eps in f64, 32 eps in f32, times 1e18; the constants below leave a factor 2-3).
-template <class F> struct FeTol;
-template <> struct FeTol<double> { static constexpr long long value = 8192; };
-template <> struct FeTol<float> { static constexpr long long value = 1ll << 42; };
+// The floating-point test of the reference may disagree with the exact one only for |X^2 + Y^2 - 1e18| <= 24 eps 1e18 = 2665
+// in f64 and 32 eps 1e18 = 1.9e12 in f32.  The top bits of S = X^2 + Y^2 settle every case outside a
+// band that contains that interval with a factor >= 2 to spare:
+//   f64: S >> 32 against 1e18 >> 32: undecided only if the high words are equal, |S - 1e18| < 2^31.4 (probability 2e-9)
+//   f32: S >> 43 against (1e18 -+ 2^42) >> 43 = 113686 / 113687 (probability 9e-6)
+// and only then is the reference's own floating-point expression evaluated (out of line: it must not cost the common path).
+template <class F> struct FeBand;
+template <> struct FeBand<double> { static constexpr int shift = 32; static constexpr uint32_t lo = 0x0DE0B6B3u, hi = 0x0DE0B6B3u; };
+template <> struct FeBand<float> { static constexpr int shift = 43; static constexpr uint32_t lo = 113686u, hi = 113687u; };
+static_assert((1000000000000000000ull >> 32) == 0x0DE0B6B3ull, "high word of 1e18");
+static_assert(((1000000000000000000ull - (1ull << 42)) >> 43) == 113686ull && ((1000000000000000000ull + (1ull << 42)) >> 43) == 113687ull, "f32 band");
+
+template <class F> __device__ __noinline__ bool fe_outside_reference(uint32_t a, uint32_t b) { return fe_outside<F>(a, b); }
 
 template <class F> __device__ __forceinline__ bool fe_outside_exact(uint32_t a, uint32_t b) {
     const int x = (int)(a + a) - 1000000000, y = (int)(b + b) - 1000000000;  // 2n - 1e9, in (-1e9, 1e9)
-    const long long s = (long long)x * x + (long long)y * y - 1000000000000000000ll;
-    if (s > FeTol<F>::value) return true;
-    if (s < -FeTol<F>::value) return false;
-    return fe_outside<F>(a, b);  // within rounding of the circle: the reference's own expression decides
+    // high words of the two squares: their sum is the high word of S = x^2 + y^2 or one less (the carry of the low words)
+    const uint32_t top = ((uint32_t)__mulhi(x, x) + (uint32_t)__mulhi(y, y)) >> (FeBand<F>::shift - 32);
+    if (__builtin_expect(top + 1u >= FeBand<F>::lo && top <= FeBand<F>::hi, 0)) return fe_outside_reference<F>(a, b);
+    return top > FeBand<F>::hi;
 }
 
-// State after the six-number request (three points, flags "outside") and after an accepted re-roll (fe_scan.cuh).
-__device__ __forceinline__ int fe_after_six(bool n0, bool n1, bool n2) { return n0 ? 2 + 2 * (int)n1 + (int)n2 : n1 ? 6 + (int)n2 : n2 ? 8 : 0; }
-__device__ __forceinline__ int fe_after_roll(int s) {
-    if (s < 6) {
-        const int f1 = (s - 2) >> 1, f2 = (s - 2) & 1;
-        return f1 ? 6 + f2 : f2 ? 8 : 0;
-    }
-    return (s < 8 && (s - 6)) ? 8 : 0;
+// State after the six-number request (three points, flags "outside") and after an accepted re-roll: the tables of
+// fe_scan.cuh (fe_walk_entry), one nibble per case.
+__device__ __forceinline__ int fe_after_six(bool n0, bool n1, bool n2) {
+    constexpr uint32_t kAfterSix = 0x0u | (2u << 4) | (6u << 8) | (4u << 12) | (8u << 16) | (3u << 20) | (7u << 24) | (5u << 28);
+    return (int)((kAfterSix >> (4 * ((int)n0 | (int)n1 << 1 | (int)n2 << 2))) & 15u);
+}
+__device__ __forceinline__ int fe_after_roll(int s) {  // s in 2..8: the first point still outside is now inside
+    constexpr unsigned long long kAfterRoll = (0ull << 8) | (8ull << 12) | (6ull << 16) | (7ull << 20) | (0ull << 24) | (8ull << 28) | (0ull << 32);
+    return (int)((kAfterRoll >> (4 * s)) & 15ull);
 }
 
 // One round from entry state s with the exact test, nothing recorded (warm-up): exit state, events started.
@@ -239,18 +248,16 @@ __global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
                     active = false;
                 }
             }
-            while (__any_sync(0xffffffffu, active && s >= 2)) {
-                if (active && s >= 2) {
-                    if (idx >= 2) {  // one re-roll of the first point that is still outside (evgen.rs:231-241)
-                        idx -= 2;
-                        const uint32_t x = row[idx], y = row[idx + 1];
-                        if (s < 6) { p0a = x; p0b = y; }
-                        else if (s < 8) { p1a = x; p1b = y; }
-                        else { p2a = x; p2b = y; }
-                        if (!fe_outside_exact<F>(x, y)) s = fe_after_roll(s);
-                    } else {
-                        active = false;
-                    }
+            while (active && s >= 2) {  // (a plain divergent loop: the lanes re-converge behind it)
+                if (idx >= 2) {  // one re-roll of the first point that is still outside (evgen.rs:231-241)
+                    idx -= 2;
+                    const uint32_t x = row[idx], y = row[idx + 1];
+                    if (s < 6) { p0a = x; p0b = y; }
+                    else if (s < 8) { p1a = x; p1b = y; }
+                    else { p2a = x; p2b = y; }
+                    if (!fe_outside_exact<F>(x, y)) s = fe_after_roll(s);
+                } else {
+                    active = false;
                 }
             }
             if (active && s == 0 && rec) {  // the event is complete: its record

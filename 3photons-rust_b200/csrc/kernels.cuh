@@ -999,14 +999,18 @@ __global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __res
     }
 }
 
-// Peak probes: 8 independent FMA chains per thread.
-template <class F> __global__ void fma_probe_kernel(F* out, int iters, F a, F b) {
+// Peak probes: 8 independent FMA chains per thread, x = x * a + 1 with the addend an IMMEDIATE.  Round 1 passed both a
+// and b in registers: DFMA R, R, Ra.reuse, Rb.reuse depends on the operand reuse cache, which does not survive a switch to
+// another warp, so part of the instructions read three register pairs (3 cycles instead of 2) and
+// the probe read 34.2 TFLOP/s.  With two register sources the FP64 pipe issues every 2.0 cycles per sub-partition:
+// 37.1 TFLOP/s at 1965 MHz, the nominal 148 SMs x 64 lanes x 2 flop (scripts/micro/peak64.cu, profiles/r02_peak64_probe.txt).
+template <class F> __global__ void fma_probe_kernel(F* out, int iters, F a) {
     F x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            x0 = fma_t(x0, a, b); x1 = fma_t(x1, a, b); x2 = fma_t(x2, a, b); x3 = fma_t(x3, a, b);
-            x4 = fma_t(x4, a, b); x5 = fma_t(x5, a, b); x6 = fma_t(x6, a, b); x7 = fma_t(x7, a, b);
+            x0 = fma_t(x0, a, (F)1); x1 = fma_t(x1, a, (F)1); x2 = fma_t(x2, a, (F)1); x3 = fma_t(x3, a, (F)1);
+            x4 = fma_t(x4, a, (F)1); x5 = fma_t(x5, a, (F)1); x6 = fma_t(x6, a, (F)1); x7 = fma_t(x7, a, (F)1);
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));

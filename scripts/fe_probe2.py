@@ -16,9 +16,9 @@ text = open(os.path.join(ROOT, "tests", "golden", "valeurs")).read()
 for n_events in (10**7, 2 * 10**8, 2 * 10**9):
     cfg = pkg.Configuration.parse(text, features).with_num_events(n_events)
     nb, last = pkg.batch_layout(n_events)
-    for legacy in (0, 1):
+    for legacy, serial in ((0, 0), (0, 1), (1, 0)):
         with pkg.Simulator(cfg) as sim:
-            sim.set_option("fe_legacy", legacy)
+            sim.set_option("fe_legacy", legacy).set_option("fe_serial", serial)
             sim.simulate_merged(0, min(nb, 2000), 10000)  # warm-up: allocations, module load
             best = 1e30
             for _ in range(3):
@@ -26,5 +26,5 @@ for n_events in (10**7, 2 * 10**8, 2 * 10**9):
                 acc = sim.simulate_merged(0, nb, last)
                 best = min(best, time.perf_counter() - t0)
             extra = "" if legacy else f" passes {sim.get_stat('fe_passes')} redone segments {sim.get_stat('fe_redone')}"
-            print(f"{features} {n_events:.0e} events, {'round-1 pipeline' if legacy else 'stream pipeline '}: {best * 1e3:9.2f} ms  "
+            print(f"{features} {n_events:.0e} events, {'round-1 pipeline' if legacy else 'stream pipeline, passes one after the other' if serial else 'stream pipeline, walk next to physics    '}: {best * 1e3:9.2f} ms  "
                   f"{n_events / best:.4g} events/s  selected {acc.selected_events}{extra}", flush=True)

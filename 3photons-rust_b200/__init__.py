@@ -168,6 +168,7 @@ def lib() -> C.CDLL:
         "tp3_simulate_merged": (C.c_int, [vp, u64, u64, u32, P(Acc)]),
         "tp3_simulate_merged_device": (C.c_int, [vp, u64, u64, u32, vp]),
         "tp3_fold_batches": (C.c_int, [P(Acc), u64, u32, P(Acc)]),
+        "tp3_fe_tile_device": (C.c_int, [vp, u64, u64, u64, vp, P(u64)]),
         "tp3_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
         "tp3_get_stat": (C.c_int, [vp, C.c_char_p, P(C.c_int64)]),
         "tp3_kernel_arg_bytes": (C.c_size_t, []),
@@ -206,6 +207,7 @@ ABI_SYMBOLS = [
     "tp3_finalize", "tp3_format_res_data", "tp3_format_stdout", "tp3_run", "tp3_host_ranf_round",
     "tp3_host_xoshiro_state", "tp3_histograms_enable", "tp3_histograms_reset", "tp3_histograms_fetch",
     "tp3_simulate_merged_device", "tp3_fold_batches", "tp3_set_option", "tp3_get_stat", "tp3_kernel_arg_bytes", "tp3_run_stages",
+    "tp3_fe_tile_device",
 ]
 
 
@@ -376,6 +378,13 @@ class Simulator:
         """Asynchronous: the merged accumulator as 13 doubles in the caller's device buffer (one ncclReduce operand)."""
         self._check(lib().tp3_simulate_merged_device(self._h, first_batch, n_batches, last_batch_len, C.c_void_p(device_ptr)))
 
+    def fe_tile_device(self, first_round: int, n_rounds: int, max_events: int, device_ptr: int) -> int:
+        """faster-evgen stream tile (tp3_fe_tile_device): every event that starts in rounds [first_round, first_round +
+        n_rounds), at most max_events; the merged accumulator goes to the device buffer, the event count is returned."""
+        done = C.c_uint64()
+        self._check(lib().tp3_fe_tile_device(self._h, first_round, n_rounds, max_events, C.c_void_p(device_ptr), C.byref(done)))
+        return int(done.value)
+
     def synchronize(self):
         self._check(lib().tp3_synchronize(self._h))
 
@@ -510,6 +519,45 @@ def run_simulation_reduced(cfg: Configuration, merged13, world_size: int, rank: 
     lo, cnt = shard_range(nb, world_size, rank)
     my_last = last if lo + cnt == nb else EVENT_BATCH_SIZE
     t = merged13(lo, cnt, my_last)
+    if world_size > 1:
+        dist.reduce(t, dst=0)
+        if rank != 0:
+            return None
+    return finalize(cfg, acc_from_f64x13(t.cpu().tolist()))
+
+
+FE_ROUNDS_PER_EVENT = 0.325121  # rounds of 55 RANF numbers per faster-evgen event (measured over 2e9 events; sizes the tiles only)
+FE_TILE_ALIGN = 512
+
+
+def fe_tile_bounds(num_events: int, world_size: int, margin: float = 5e-4):
+    """Round boundaries T_0 = 0 < T_1 < ... < T_W of the stream tiles of a `num_events`-event faster-evgen run: equal shares
+    of the rounds the run is expected to need, less `margin` so that the last tile surely ends before event num_events
+    (the last rank then adds the exact remainder)."""
+    total = num_events * FE_ROUNDS_PER_EVENT * (1.0 - margin)
+    return [int(total * r / world_size) // FE_TILE_ALIGN * FE_TILE_ALIGN for r in range(world_size + 1)]
+
+
+def run_simulation_tiles(cfg: Configuration, tile13, world_size: int, rank: int, dist=None, device="cpu"):
+    """scheduling::run_simulation for `faster-evgen` over `world_size` processes by sharding the STREAM instead of the
+    batches (include/tp3.h, tp3_fe_tile_device).  `tile13(first_round, n_rounds, max_events) -> (tensor of 13 float64,
+    events simulated)` is Simulator.fe_tile_device into a CUDA tensor on a GPU.  Exchanges: one all_reduce of the event
+    counts (8 bytes), one reduce(sum) of 13 doubles.  Returns FinalResults on rank 0, None elsewhere."""
+    import torch
+    bounds = fe_tile_bounds(cfg.num_events, world_size)
+    t, count = tile13(bounds[rank], bounds[rank + 1] - bounds[rank], 0)
+    t = t.clone()
+    total = torch.tensor([count], dtype=torch.int64, device=device)
+    if world_size > 1:
+        dist.all_reduce(total)
+    remaining = cfg.num_events - int(total.item())
+    if remaining < 0:
+        raise Tp3Error(E_INVALID, f"faster-evgen tiles overshoot the run by {-remaining} events: FE_ROUNDS_PER_EVENT / margin need adjusting")
+    if rank == world_size - 1 and remaining > 0:  # the exact remainder, from the end of the last tile
+        t2, count2 = tile13(bounds[world_size], 0, remaining)
+        if count2 != remaining:
+            raise Tp3Error(E_INVALID, "faster-evgen remainder tile came back short")
+        t = t + t2
     if world_size > 1:
         dist.reduce(t, dst=0)
         if rank != 0:

@@ -683,15 +683,32 @@ template <class T> int fs_grow(tp3_ctx* c, T*& ptr, size_t& cap, size_t need) {
     return TP3_OK;
 }
 
-int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len) {
+// A TILE of the stream (tp3_fe_tile_device): every event that STARTS in rounds [first_round, first_round + n_rounds), at most
+// max_events of them, counted from 0 at the tile start.  Tiles of consecutive round ranges partition the events of the
+// run exactly, so G ranks can each take one without knowing how many events precede it (the reference's scheduler needs
+// exactly that knowledge, evgen.rs:257-267, which is why its reproducible mode does not scale).
+struct FeTile {
+    uint64_t first_round, n_rounds, max_events;  // n_rounds = 0: no round limit; max_events = 0: no event limit
+    uint64_t events_done, batches_done;          // out
+};
+
+int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len, FeTile* tile = nullptr) {
     using FsBuf = DeviceSlot::FsBuf;
     const bool f32 = c->params.flags & TP3_F32;
     const uint64_t B = TP3_EVENT_BATCH_SIZE;
-    const uint64_t e_lo = first * B, e_hi = (first + n - 1) * B + last_len;  // events wanted: [e_lo, e_hi)
-    if (c->fs_events > e_lo) c->fs_round = c->fs_events = 0;                 // the known point is past the start: from the seed again
+    const uint64_t kNoLimit = ~0ull;
+    // events wanted: [e_lo, e_hi); in a tile limited by rounds e_hi is only known once the walk has reached the tile's end
+    const uint64_t e_lo = first * B;
+    uint64_t e_hi = tile ? (tile->max_events ? tile->max_events : kNoLimit) : (first + n - 1) * B + last_len;
+    const uint64_t stop_round = (tile && tile->n_rounds) ? tile->first_round + tile->n_rounds : kNoLimit;
+    uint64_t tile_round = tile ? tile->first_round : 0, tile_events = 0;
+    uint64_t& pos_round = tile ? tile_round : c->fs_round;    // a round (segment boundary) whose event index is known ...
+    uint64_t& pos_events = tile ? tile_events : c->fs_events;  // ... and that index
+    if (!tile && pos_events > e_lo) pos_round = pos_events = 0;  // the known point is past the start: from the seed again
+    if (tile) n = e_hi == kNoLimit ? kNoLimit : (e_hi + B - 1) / B;
     c->stat_fe_passes = c->stat_fe_redone = 0;
     const double kRoundsPerEvent = 0.3252;  // 3.076 events start per round on average (measured); only sizes the passes
-    const uint64_t lanes_per_wave = (uint64_t)s.sm_count * 28 * 32;  // the walk kernel alone holds 7 CTAs of 4 warps per SM
+    const uint64_t lanes_per_wave = (uint64_t)s.sm_count * 28 * 32;  // the walk kernel alone holds 7 CTAs of 4 warps per SM (shared memory)
     const uint32_t warm = c->opt_fe_warm > 0 ? (uint32_t)c->opt_fe_warm : (uint32_t)kFeWarm;
     const bool overlap = !c->opt_fe_serial;
     if (!s.fs_stream2) {
@@ -750,12 +767,15 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         // far from the first wanted event: count-only passes (no records) until about 800 batches before it
         b.count_only = (double)(next_event - events) * kRoundsPerEvent > 8.0 * (double)lanes_per_wave;
         const uint64_t want_events = b.count_only ? next_event - events : e_hi - events;
-        const uint64_t want_rounds = (uint64_t)((double)want_events * kRoundsPerEvent * 1.002) + 4096;
+        uint64_t want_rounds = e_hi == kNoLimit ? kNoLimit : (uint64_t)((double)want_events * kRoundsPerEvent * 1.002) + 4096;
+        if (stop_round != kNoLimit && want_rounds > stop_round - round) want_rounds = stop_round - round;  // a tile ends at its last round
         const uint64_t max_seg = c->opt_fe_pass_segments > 0 ? (uint64_t)c->opt_fe_pass_segments : lanes_per_wave;
         uint32_t seg_rounds = 64;
         if (c->opt_fe_seg_rounds > 0) seg_rounds = (uint32_t)c->opt_fe_seg_rounds;
         else
             while (seg_rounds < 512 && want_rounds / seg_rounds > lanes_per_wave) seg_rounds *= 2;  // fill the device first, then lengthen
+        if (stop_round != kNoLimit)
+            while ((stop_round - round) % seg_rounds) seg_rounds /= 2;  // a tile ends on a segment boundary
         uint64_t n_seg = (want_rounds + seg_rounds - 1) / seg_rounds;
         if (n_seg > max_seg) n_seg = max_seg;
         if (b.count_only) {  // stop a little before the first wanted event, at a segment boundary
@@ -788,7 +808,7 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
     };
 
     int cur = 0;
-    int rc = start_pass(s.fs[0], c->fs_round, c->fs_events, 0);
+    int rc = start_pass(s.fs[0], pos_round, pos_events, 0);
     if (rc) return rc;
     while (true) {
         FsBuf& b = s.fs[cur];
@@ -831,11 +851,15 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         b.h_seg_events[0] = b.first_events;
         for (uint64_t g = 0; g < n_seg; ++g) b.h_seg_events[g + 1] = b.h_seg_events[g] + b.h_count[g];
         const uint64_t pass_end = b.h_seg_events[n_seg];
+        if (b.first_round + n_seg * b.seg_rounds == stop_round && e_hi > pass_end) {  // the tile ends here: now its size is known
+            e_hi = pass_end;
+            n = (e_hi + B - 1) / B;
+        }
         // ---- batches whose events all start in this pass
         uint64_t b_hi = done_batches;
         if (!b.count_only) {
             while (b_hi < n) {
-                const uint64_t end = (b_hi + 1 == n) ? e_hi : (first + b_hi + 1) * B;
+                const uint64_t end = std::min((first + b_hi + 1) * B, e_hi);
                 if (end > pass_end) break;
                 ++b_hi;
             }
@@ -844,12 +868,12 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         const uint64_t next = (first + b_hi) * B;
         uint64_t g_next = n_seg;
         while (g_next > 0 && b.h_seg_events[g_next] > next) --g_next;
-        if (g_next == 0 && b_hi == done_batches) {  // the pass holds less than the one batch it was sized for
+        if (g_next == 0 && b_hi == done_batches && b_hi < n) {  // the pass holds less than the one batch it was sized for
             c->err = "faster-evgen stream pipeline: a pass must hold at least one batch (fe_pass_segments x fe_seg_rounds too small)";
             return TP3_E_INVALID;
         }
-        c->fs_round = b.first_round + g_next * b.seg_rounds;
-        c->fs_events = b.h_seg_events[g_next];
+        pos_round = b.first_round + g_next * b.seg_rounds;
+        pos_events = b.h_seg_events[g_next];
         const uint64_t lo_batches = done_batches;
         done_batches = b_hi;
         const bool more = done_batches < n;
@@ -881,10 +905,11 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
             ph.end_event = e_hi;
             ph.n_units = (uint32_t)n_units;
             ph.out_parts = b.d_parts;
-            // 12 of the 16 warp slots of an SM when another pass follows: its walk then runs next to this kernel
-            uint64_t W = (uint64_t)s.sm_count * ((more && overlap) ? 12 : 16);
-            if (c->opt_grid_warps > 0) W = (uint64_t)c->opt_grid_warps;
-            if (W > n_units) W = n_units;
+            // One CTA per unit (2500 events), dispatched by the hardware: warps that start at staggered times do not run in
+            // lock step (the static split, as many CTAs as the device holds, was 11 % slower for the default kernel), and as
+            // they retire the blocks of the next pass's walk, queued on the other stream, move in next to them.
+            uint64_t W = n_units;
+            if (c->opt_grid_warps > 0 && (uint64_t)c->opt_grid_warps < W) W = (uint64_t)c->opt_grid_warps;
             ph.n_warps = (uint32_t)W;
             if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, 0, b.st>>>(ph, phys_params<float>(c->params));
             else fe_physics_kernel<double><<<(unsigned)W, 32, 0, b.st>>>(ph, phys_params<double>(c->params));
@@ -899,7 +924,11 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         if (!more) break;
         // ---- ... while the next pass is walked on the other stream (queued behind the physics that last used that buffer)
         cur ^= 1;
-        if ((rc = start_pass(s.fs[cur], c->fs_round, c->fs_events, done_batches))) return rc;
+        if ((rc = start_pass(s.fs[cur], pos_round, pos_events, done_batches))) return rc;
+    }
+    if (tile) {
+        tile->events_done = e_hi;
+        tile->batches_done = done_batches;
     }
     // the slot's stream owns the result
     TP3_CUDA(c, cudaEventRecord(s.fs_event, s.fs_stream2));
@@ -1400,6 +1429,37 @@ int tp3_simulate_merged_device(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t 
     int rc = enqueue_merged(c, first, n, last_len);
     if (rc) return rc;
     DeviceSlot& s = c->devs[0];
+    export_merged_kernel<<<1, 32, 0, s.stream>>>(s.d_fold, d_out13);
+    ++c->launches;
+    TP3_CUDA(c, cudaGetLastError());
+    return TP3_OK;
+}
+
+int tp3_fe_tile_device(tp3_ctx* c, uint64_t first_round, uint64_t n_rounds, uint64_t max_events, double* d_out13, uint64_t* events_done) {
+    const uint32_t need = TP3_FASTER_EVGEN, bad = TP3_STANDARD_RANDOM | TP3_FASTER_THREADING;
+    if (!c || !d_out13 || !events_done || c->devs.size() != 1 || (c->params.flags & need) != need || (c->params.flags & bad) ||
+        (n_rounds == 0 && max_events == 0) || first_round % 64 || n_rounds % 64) {
+        if (c) c->err = "tp3_fe_tile_device: needs a single-device faster-evgen context on the sequential RANF stream, a round or an "
+                        "event limit, and round numbers that are multiples of 64";
+        return TP3_E_INVALID;
+    }
+    DeviceSlot& s = c->devs[0];
+    TP3_CUDA(c, cudaSetDevice(s.dev));
+    // accumulators per group of 10 000 consecutive events of the tile: at most 4 events start in a round
+    const uint64_t cap = (max_events ? max_events : n_rounds * kFeSlotsPerRound) / TP3_EVENT_BATCH_SIZE + 2;
+    int rc = ensure_out(c, s, cap);
+    if (rc) return rc;
+    FeTile t{first_round, n_rounds, max_events, 0, 0};
+    rc = fe_stream_simulate(c, s, 0, 0, 0, &t);
+    if (rc) return rc;
+    *events_done = t.events_done;
+    TP3_CUDA(c, cudaMemsetAsync(s.d_fold, 0, sizeof(FoldState), s.stream));
+    if (t.batches_done) {
+        if (c->params.flags & TP3_F32) merge_kernel<float><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, t.batches_done, &s.d_fold->running, true);
+        else merge_kernel<double><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, t.batches_done, &s.d_fold->running, true);
+        ++c->launches;
+        TP3_CUDA(c, cudaGetLastError());
+    }
     export_merged_kernel<<<1, 32, 0, s.stream>>>(s.d_fold, d_out13);
     ++c->launches;
     TP3_CUDA(c, cudaGetLastError());

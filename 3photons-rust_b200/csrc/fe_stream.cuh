@@ -34,7 +34,7 @@
 
 namespace tp3 {
 
-struct alignas(16) FeRecord {
+struct alignas(32) FeRecord {
     // w[0..8]: random_array::<9>() in the reference's order (evgen.rs:149-153: column-major 3x3 -> cos_theta of the three
     // photons, then the two factors of each exp(-E)); w[9 + 2k], w[10 + 2k]: the numbers behind (x, y) of accepted point k.
     uint32_t w[16];
@@ -68,6 +68,17 @@ template <class F> __device__ __forceinline__ bool fe_outside_exact(uint32_t a, 
     return top > FeBand<F>::hi;
 }
 
+// Branch-free form for the hot loops: the decision where it is certain, `amb` raised where the reference's expression has to
+// decide (the caller then redoes the test with fe_outside_exact, once, out of the common path).
+template <class F> __device__ __forceinline__ bool fe_outside_fast(uint32_t a, uint32_t b, bool& amb) {
+    constexpr uint32_t width = FeBand<F>::hi - FeBand<F>::lo + 1u;
+    const int x = (int)(a + a) - 1000000000, y = (int)(b + b) - 1000000000;
+    const uint32_t top = ((uint32_t)__mulhi(x, x) + (uint32_t)__mulhi(y, y)) >> (FeBand<F>::shift - 32);
+    const uint32_t d = top - (FeBand<F>::lo - 1u);  // wraps (negative) below the band: inside; above `width`: outside
+    amb |= d <= width;
+    return (int)d > (int)width;
+}
+
 // State after the six-number request (three points, flags "outside") and after an accepted re-roll: the tables of
 // fe_scan.cuh (fe_walk_entry), one nibble per case.
 __device__ __forceinline__ int fe_after_six(bool n0, bool n1, bool n2) {
@@ -78,6 +89,9 @@ __device__ __forceinline__ int fe_after_roll(int s) {  // s in 2..8: the first p
     constexpr unsigned long long kAfterRoll = (0ull << 8) | (8ull << 12) | (6ull << 16) | (7ull << 20) | (0ull << 24) | (8ull << 28) | (0ull << 32);
     return (int)((kAfterRoll >> (4 * s)) & 15ull);
 }
+
+// numbers[i + 1] of this lane's private generator (see FeWalkSmem: lane l owns bank l)
+#define FE_ROW(i) row[(i) << 5]
 
 // One round from entry state s with the exact test, nothing recorded (warm-up): exit state, events started.
 template <class F> __device__ __forceinline__ int fe_walk_round_exact(const uint32_t* row, int s, int& count) {
@@ -92,16 +106,20 @@ template <class F> __device__ __forceinline__ int fe_walk_round_exact(const uint
         } else if (s == 1) {
             if (idx < 6) break;
             idx -= 6;
-            s = fe_after_six(fe_outside_exact<F>(row[idx], row[idx + 3]), fe_outside_exact<F>(row[idx + 1], row[idx + 4]),
-                             fe_outside_exact<F>(row[idx + 2], row[idx + 5]));
+            s = fe_after_six(fe_outside_exact<F>(FE_ROW(idx), FE_ROW(idx + 3)), fe_outside_exact<F>(FE_ROW(idx + 1), FE_ROW(idx + 4)),
+                             fe_outside_exact<F>(FE_ROW(idx + 2), FE_ROW(idx + 5)));
         } else {
             if (idx < 2) break;
             idx -= 2;
-            if (!fe_outside_exact<F>(row[idx], row[idx + 1])) s = fe_after_roll(s);
+            if (!fe_outside_exact<F>(FE_ROW(idx), FE_ROW(idx + 1))) s = fe_after_roll(s);
         }
     }
     return s;
 }
+
+#ifndef TP3_FE_GEN_REGS
+#define TP3_FE_GEN_REGS 0   // 1: generator state in registers (fewer shared-memory accesses, but 96 registers: 20 warps per SM instead of 28: slower)
+#endif
 
 struct FeWalkArgs {
     const uint32_t* jump_table;   // [kRanfDigits][256][55], the seeded round 0 behind it (api.cu)
@@ -119,19 +137,22 @@ struct FeWalkArgs {
 
 struct FeWalkSmem {
     uint32_t win[2 * kRanfLag + 2];
-    uint32_t tile[32][kRanfLag + 2];  // one private generator per lane, row[k] = numbers[k + 1]; odd row stride: conflict free
+    // one private generator per lane, numbers[k + 1] of lane l at tile[k][l]: every lane owns a bank, so the walk's
+    // data-dependent indices are as conflict free as the generator's fixed ones (rows with an odd stride made the walk's
+    // loads 3-4 wavefronts each: the MIO queue was 20 % of the stalls, profiles/r02_fe_walk_*.txt)
+    uint32_t tile[kRanfLag][32];
 };
 
 // ranf.rs:106-119 in place on a lane's private row.
 __device__ __forceinline__ void fe_next_round(uint32_t* row) {
 #pragma unroll
-    for (int k = 0; k < 24; ++k) row[k] = ranf_sub(row[k], row[k + 31]);
+    for (int k = 0; k < 24; ++k) FE_ROW(k) = ranf_sub(FE_ROW(k), FE_ROW(k + 31));
 #pragma unroll
-    for (int k = 24; k < kRanfLag; ++k) row[k] = ranf_sub(row[k], row[k - 24]);
+    for (int k = 24; k < kRanfLag; ++k) FE_ROW(k) = ranf_sub(FE_ROW(k), FE_ROW(k - 24));
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
+__global__ void __launch_bounds__(128, TP3_FE_GEN_REGS ? 5 : 7) fe_walk_kernel(const FeWalkArgs a) {
     __shared__ FeWalkSmem sm[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FeWalkSmem& w = sm[warp];
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
         if (k == 0 || redo) ranf_jump_to_round(w.win, base, start, a.jump_table, lane);
         else ranf_jump_to_round(w.win, w.win, start - prev_start, a.jump_table, lane);  // segments of a warp are consecutive
         prev_start = start;
-        for (int i = lane; i < kRanfLag; i += 32) w.tile[k][i] = w.win[i];
+        for (int i = lane; i < kRanfLag; i += 32) w.tile[i][k] = w.win[i];
         if (lane == k) {
             my_seg = g;
             my_start = start;
@@ -164,7 +185,7 @@ __global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
         __syncwarp();
     }
     const bool live = item0 + lane < n_items;
-    uint32_t* const row = w.tile[lane];
+    uint32_t* const row = &w.tile[0][lane];
     FeRecord* const rec_base = (a.records && live) ? a.records + (size_t)my_seg * kFeSlotsPerRound * a.seg_rounds : nullptr;
 
     // consumer state: where each of the nine possible entry states is now (warm-up), then the single true state
@@ -179,59 +200,77 @@ __global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
         s = 0;
     }
     uint32_t count = 0;
-    bool done = !live, rec = false, failed = false;
+    bool done = !live, rec = false, in_event = false, failed = false;
     uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0, u4 = 0, u5 = 0, u6 = 0, u7 = 0, u8 = 0, p0a = 0, p0b = 0, p1a = 0, p1b = 0, p2a = 0, p2b = 0;
     const int seg_end = my_warm + (int)a.seg_rounds;
 
+#if TP3_FE_GEN_REGS
+    // The generator lives in REGISTERS (55 of them) and a round is copied to shared memory only for the walk's data-dependent
+    // indices: 55 shared-memory stores per round instead of 110 loads + 55 stores.
+    uint32_t g[kRanfLag];
+#pragma unroll
+    for (int k = 0; k < kRanfLag; ++k) g[k] = FE_ROW(k);
+#endif
     for (int t = 0; !__all_sync(0xffffffffu, done); ++t) {
+#if TP3_FE_GEN_REGS
+        if (t > 0) {  // ranf.rs:106-119
+#pragma unroll
+            for (int k = 0; k < 24; ++k) g[k] = ranf_sub(g[k], g[k + 31]);
+#pragma unroll
+            for (int k = 24; k < kRanfLag; ++k) g[k] = ranf_sub(g[k], g[k - 24]);
+#pragma unroll
+            for (int k = 0; k < kRanfLag; ++k) FE_ROW(k) = g[k];
+        }
+#else
         if (t > 0 && !done) fe_next_round(row);
-        const bool warming = !done && t < my_warm;
-        if (warming) {  // ---- warm-up: follow every state that is still possible, record nothing
-            if (single) {
-                int c;
-                s = fe_walk_round_exact<F>(row, s, c);
-            } else {
-                uint32_t img = 0;
-#pragma unroll
-                for (int q = 0; q < 9; ++q) img |= 1u << ((cur >> (4 * q)) & 15u);
-                uint64_t m = 0;
-                while (img) {
-                    const int q = __ffs(img) - 1;
-                    img &= img - 1;
-                    int c;
-                    m |= (uint64_t)fe_walk_round_exact<F>(row, q, c) << (4 * q);
-                }
-                uint64_t nxt = 0;
-#pragma unroll
-                for (int q = 0; q < 9; ++q) nxt |= ((m >> (4 * ((cur >> (4 * q)) & 15u))) & 15ull) << (4 * q);
-                cur = nxt;
-                if (cur == (cur & 15u) * kFeNine4) {
-                    single = true;
-                    s = (int)(cur & 15u);
-                }
-            }
-        }  // (no `continue`: the other lanes of the warp may be in their segment already, and the votes below are warp-wide)
+#endif
         if (!done && t == my_warm && !single) {  // the segment starts and its state is still ambiguous: the host redoes it
             failed = true;
             done = true;
         }
+        // ---- warm-up, while several entry states are still possible (2.2 rounds on average): every candidate walked, slowly
+        const bool many = !done && !single;
+        if (many) {
+            uint32_t img = 0;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) img |= 1u << ((cur >> (4 * q)) & 15u);
+            uint64_t m = 0;
+            while (img) {
+                const int q = __ffs(img) - 1;
+                img &= img - 1;
+                int c;
+                m |= (uint64_t)fe_walk_round_exact<F>(row, q, c) << (4 * q);
+            }
+            uint64_t nxt = 0;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) nxt |= ((m >> (4 * ((cur >> (4 * q)) & 15u))) & 15ull) << (4 * q);
+            cur = nxt;
+            if (cur == (cur & 15u) * kFeNine4) {
+                single = true;
+                s = (int)(cur & 15u);
+            }
+        }  // (no `continue`: the other lanes of the warp may be further on, and the votes below are warp-wide)
         if (!done && t == seg_end) {
             if (a.seg_exit) a.seg_exit[my_seg] = (uint8_t)s;  // state at the end of the segment = entry state of the next one
-            if (!rec) done = true;                             // no event in progress: nothing left to do
+            if (!in_event) done = true;                        // no event in progress: nothing left to do
         }
-        const bool in_seg = t < seg_end;
-        bool active = !done && !warming;
+        // ---- one state: the stream is served exactly as the reference serves it.  Before the segment (the rest of the warm-up)
+        // nothing is counted or recorded; in the segment every event that starts is counted and its record written; past the
+        // segment's end only the event in progress is finished.
+        const bool may_start = t < seg_end, counting = t >= my_warm;
+        bool active = !done && !many;
         int idx = kRanfLag;
         // One round, request by request, the lanes of the warp in step: [pending requests] then up to four times
         // [9 numbers][6 numbers + three tests][re-rolls]; a lane whose next request does not fit is finished with the round.
         for (int e = 0; e < 6; ++e) {
             if (e > 0 && active && s == 0) {
-                if (idx >= 9 && in_seg) {  // a new event starts here (random_array::<9>, evgen.rs:149)
+                if (idx >= 9 && may_start) {  // a new event starts here (random_array::<9>, evgen.rs:149)
                     idx -= 9;
-                    u0 = row[idx]; u1 = row[idx + 1]; u2 = row[idx + 2]; u3 = row[idx + 3]; u4 = row[idx + 4];
-                    u5 = row[idx + 5]; u6 = row[idx + 6]; u7 = row[idx + 7]; u8 = row[idx + 8];
-                    ++count;
-                    rec = true;
+                    u0 = FE_ROW(idx); u1 = FE_ROW(idx + 1); u2 = FE_ROW(idx + 2); u3 = FE_ROW(idx + 3); u4 = FE_ROW(idx + 4);
+                    u5 = FE_ROW(idx + 5); u6 = FE_ROW(idx + 6); u7 = FE_ROW(idx + 7); u8 = FE_ROW(idx + 8);
+                    in_event = true;
+                    rec = counting;
+                    count += counting ? 1u : 0u;
                     s = 1;
                 } else {
                     active = false;
@@ -240,8 +279,14 @@ __global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
             if (active && s == 1) {
                 if (idx >= 6) {  // the three points, column-major 3x2 (evgen.rs:223-225): point k = (v[k], v[3 + k])
                     idx -= 6;
-                    const uint32_t a0 = row[idx], a1 = row[idx + 1], a2 = row[idx + 2], a3 = row[idx + 3], a4 = row[idx + 4], a5 = row[idx + 5];
-                    const bool n0 = fe_outside_exact<F>(a0, a3), n1 = fe_outside_exact<F>(a1, a4), n2 = fe_outside_exact<F>(a2, a5);
+                    const uint32_t a0 = FE_ROW(idx), a1 = FE_ROW(idx + 1), a2 = FE_ROW(idx + 2), a3 = FE_ROW(idx + 3), a4 = FE_ROW(idx + 4), a5 = FE_ROW(idx + 5);
+                    bool amb = false;
+                    bool n0 = fe_outside_fast<F>(a0, a3, amb), n1 = fe_outside_fast<F>(a1, a4, amb), n2 = fe_outside_fast<F>(a2, a5, amb);
+                    if (__builtin_expect(amb, 0)) {
+                        n0 = fe_outside_exact<F>(a0, a3);
+                        n1 = fe_outside_exact<F>(a1, a4);
+                        n2 = fe_outside_exact<F>(a2, a5);
+                    }
                     p0a = a0; p0b = a3; p1a = a1; p1b = a4; p2a = a2; p2b = a5;  // re-rolled points are overwritten below
                     s = fe_after_six(n0, n1, n2);
                 } else {
@@ -251,25 +296,33 @@ __global__ void __launch_bounds__(128) fe_walk_kernel(const FeWalkArgs a) {
             while (active && s >= 2) {  // (a plain divergent loop: the lanes re-converge behind it)
                 if (idx >= 2) {  // one re-roll of the first point that is still outside (evgen.rs:231-241)
                     idx -= 2;
-                    const uint32_t x = row[idx], y = row[idx + 1];
+                    const uint32_t x = FE_ROW(idx), y = FE_ROW(idx + 1);
                     if (s < 6) { p0a = x; p0b = y; }
                     else if (s < 8) { p1a = x; p1b = y; }
                     else { p2a = x; p2b = y; }
-                    if (!fe_outside_exact<F>(x, y)) s = fe_after_roll(s);
+                    bool amb = false;
+                    bool out = fe_outside_fast<F>(x, y, amb);
+                    if (__builtin_expect(amb, 0)) out = fe_outside_exact<F>(x, y);
+                    if (!out) s = fe_after_roll(s);
                 } else {
                     active = false;
                 }
             }
-            if (active && s == 0 && rec) {  // the event is complete: its record
-                rec = false;
-                if (rec_base) {
-                    uint4* o = reinterpret_cast<uint4*>(rec_base + (count - 1));
-                    o[0] = make_uint4(u0, u1, u2, u3);
-                    o[1] = make_uint4(u4, u5, u6, u7);
-                    o[2] = make_uint4(u8, p0a, p0b, p1a);
-                    o[3] = make_uint4(p1b, p2a, p2b, 0u);
+            if (active && s == 0 && in_event) {  // the event is complete: its record
+                in_event = false;
+                if (rec && rec_base) {
+                    // two 256-bit stores (STG.E.256): every lane writes to another line, and what bounds this kernel is the
+                    // number of (lane, store instruction) pairs the L1TEX tag stage sees, not the bytes
+                    FeRecord* o = rec_base + (count - 1);
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(u0), "r"(u1), "r"(u2), "r"(u3), "r"(u4),
+                                 "r"(u5), "r"(u6), "r"(u7)
+                                 : "memory");
+                    asm volatile("st.global.v8.b32 [%0+32], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(u8), "r"(p0a), "r"(p0b), "r"(p1a),
+                                 "r"(p1b), "r"(p2a), "r"(p2b), "r"(0u)
+                                 : "memory");
                 }
-                if (!in_seg) {  // that was the event straddling the end of the segment
+                rec = false;
+                if (!may_start) {  // that was the event straddling the end of the segment
                     active = false;
                     done = true;
                 }

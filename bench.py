@@ -239,7 +239,17 @@ def main():
         out13 = torch.zeros(13, dtype=torch.float64, device="cuda")
         res = {"n_events": n_events, "nb": nb, "cfg": cfg, "sim": sim}
 
+        # faster-evgen on the sequential RANF stream at N > 1: the STREAM is sharded, not the batches (tp3_fe_tile_device):
+        # a rank cannot reach "its" batches without walking everything before them, but it can take a range of rounds
+        f = set(args.features.split(","))
+        fe_tiles = world > 1 and "faster-evgen" in f and "standard-random" not in f and not {"multi-threading", "faster-threading"} <= f
+
+        def tile13(first_round, n_rounds, max_events):
+            return out13, sim.fe_tile_device(first_round, n_rounds, max_events, out13.data_ptr())
+
         def step_device():
+            if fe_tiles:  # includes the 8-byte count exchange and the reduce of 13 doubles: there is no device-only form
+                return pkg.run_simulation_tiles(cfg, tile13, world, rank, dist, "cuda")
             sim.simulate_merged_device(lo, cnt, my_last, out13.data_ptr())
 
         # ---- device-resident timing ("value") ----
@@ -270,6 +280,11 @@ def main():
             return out13
 
         def e2e_step():
+            if fe_tiles:
+                fin_ = step_device()
+                if rank != 0:
+                    torch.cuda.synchronize()
+                return fin_
             if world == 1:
                 return pkg.finalize(cfg, sim.simulate_merged(lo, cnt, my_last))
             # tp3_simulate_merged_device + the run's one inter-GPU exchange (ncclReduce of 13 doubles) + 104-byte D2H + finalize
@@ -293,6 +308,8 @@ def main():
         host = (pkg.Acc * cnt)()
 
         def per_batch_step():
+            if fe_tiles:  # per-batch accumulators by absolute batch index need the whole prefix of the stream: not sharded
+                return e2e_step()
             sim._check(pkg.lib().tp3_simulate_batches(sim._h, lo, cnt, my_last, host))
             mine = pkg.fold(host, cfg.flags)
             if world == 1:

@@ -113,6 +113,20 @@ int  tp3_simulate_merged(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
  * ranks -- the whole inter-GPU exchange of a run. */
 int  tp3_simulate_merged_device(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
                                 uint32_t last_batch_len, double* device_out13);
+/* faster-evgen on several GPUs (sequential RANF stream; single-device contexts).  Under this feature the position of
+ * an event in the random stream depends on every earlier event, so a rank cannot start at "its" batches without walking
+ * everything before them (the reference's scheduler thread does exactly that: evgen.rs:257-267, multi_threading.rs:59-64).
+ * Instead the STREAM is sharded: this call simulates every event that STARTS in RANF rounds
+ * [first_round, first_round + n_rounds) (a round = 55 numbers, ranf.rs:106-119; multiples of 64), at most max_events of
+ * them (0 = no limit; n_rounds = 0 = no round limit), in groups of 10 000 consecutive events counted from the tile's first
+ * event, and leaves the merged accumulator in the caller's device buffer as 13 doubles (see tp3_simulate_merged_device).
+ * *events_done = the number of events simulated (synchronises the walk, not the physics).  Consecutive tiles partition
+ * the events of the run exactly: ranks take one tile each, exchange their event counts (8 bytes), the last rank adds
+ * the remaining events with a second call limited by max_events, and one reduce(sum) of 13 doubles finishes the run
+ * (run_simulation_tiles in the Python mirror).  The events, the selected-event count and every sum are those of the
+ * sequential run up to the order of the additions. */
+int  tp3_fe_tile_device(tp3_ctx* ctx, uint64_t first_round, uint64_t n_rounds, uint64_t max_events,
+                        double* device_out13, uint64_t* events_done);
 /* Host left fold of per-batch accumulators in batch order, starting FROM the first one
  * (sequential.rs:24-36), in the run's Float (flags & TP3_F32). */
 int  tp3_fold_batches(const tp3_acc* per_batch, uint64_t n_batches, uint32_t flags, tp3_acc* out);

@@ -205,6 +205,21 @@ static void copy_text(const std::string& s, char* buf, size_t cap) {
     buf[n] = 0;
 }
 
+// The oracle's own Ranf, wrapped only to count its refills (rounds): see oracle_fe_tile.
+template <class F> struct CountingRanf {
+    Ranf<F> g;
+    uint64_t round = 0;
+    template <int N> void random_array(F* out, int32_t* raw = nullptr) {
+        if (g.index < N) ++round;  // ranf.rs:87-92: this request does not fit, the rest of the round is discarded
+        g.template random_array<N>(out, raw);
+    }
+    F random() {
+        F r;
+        random_array<1>(&r);
+        return r;
+    }
+};
+
 extern "C" {
 
 // Whole run. Returns 0 on success; per_batch may be NULL. *n_batches in: capacity, out: count.
@@ -277,6 +292,55 @@ int oracle_events(const char* valeurs_text, uint32_t feature_mask, uint32_t n, d
     if (ft.standard_random)
         return ft.f32 ? go(0.0f, Xoshiro<float>()) : go(0.0, Xoshiro<double>());
     return ft.f32 ? go(0.0f, Ranf<float>()) : go(0.0, Ranf<double>());
+}
+
+// The events of the sequential faster-evgen RANF stream that START in rounds [first_round, first_round + n_rounds)
+// (n_rounds = 0: no round limit), at most max_events of them (0: no limit), accumulated in groups of 10 000 consecutive
+// events counted from the first one and merged in order: the checker of tp3_fe_tile_device.  A "round" is one refill of the
+// generator (ranf.rs:87-92,106-119), round 0 the state after seeding; an event starts in the round that serves its
+// random_array::<9>() (evgen.rs:149).  The generator is the oracle's own Ranf, wrapped only to count its refills.
+int oracle_fe_tile(const char* valeurs_text, uint32_t feature_mask, uint64_t first_round, uint64_t n_rounds, uint64_t max_events,
+                   oracle_acc* merged, uint64_t* events_done) {
+    Features ft = features_from_mask(feature_mask);
+    if (!ft.faster_evgen || ft.standard_random) return 2;
+    auto go = [&](auto fzero) -> int {
+        using F = decltype(fzero);
+        Config<F> cfg;
+        if (!load_config<F>(valeurs_text, cfg).empty()) return 1;
+        Couplings<F> cp(cfg);
+        const F w = event_weight<F>(cfg.e_total);
+        CountingRanf<F> rng;
+        Accumulator<F> total(cfg, w), batch(cfg, w);
+        uint64_t done = 0, in_batch = 0;
+        bool first_batch = true;
+        auto flush = [&]() {
+            if (first_batch) total = batch;
+            else total.merge(batch);
+            first_batch = false;
+            batch = Accumulator<F>(cfg, w);
+            in_batch = 0;
+        };
+        for (;;) {
+            if (max_events && done == max_events) break;
+            // where would the next event start?  (the 9-number request moves to the next round if fewer than 9 are left)
+            const uint64_t start_round = rng.round + (rng.g.index < 9 ? 1 : 0);
+            if (n_rounds && start_round >= first_round + n_rounds) break;
+            Event<F> ev = generate<F>(rng, ft, cfg.e_total);
+            if (start_round < first_round) continue;  // an event of an earlier tile
+            if (keep(cfg, ft, ev)) {
+                F m[5];
+                m2_sums(cp, ev, m);
+                batch.integrate(m);
+            }
+            ++done;
+            if (++in_batch == EVENT_BATCH_SIZE) flush();
+        }
+        if (in_batch || first_batch) flush();
+        *merged = widen(total);
+        *events_done = done;
+        return 0;
+    };
+    return ft.f32 ? go(0.0f) : go(0.0);
 }
 
 // finalize (resacc.rs:142-223) + the text surfaces (resfin.rs:66-194, output.rs:30-177) applied to GIVEN sums: lets the

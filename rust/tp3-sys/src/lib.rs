@@ -110,6 +110,8 @@ extern "C" {
                                out_merged: *mut tp3_acc) -> c_int;
     pub fn tp3_simulate_merged_device(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
                                       device_out13: *mut f64) -> c_int;
+    pub fn tp3_fe_tile_device(ctx: *mut tp3_ctx, first_round: u64, n_rounds: u64, max_events: u64, device_out13: *mut f64,
+                              events_done: *mut u64) -> c_int;
     pub fn tp3_fold_batches(per_batch: *const tp3_acc, n_batches: u64, flags: u32, out: *mut tp3_acc) -> c_int;
     pub fn tp3_synchronize(ctx: *mut tp3_ctx) -> c_int;
     pub fn tp3_launch_count(ctx: *const tp3_ctx) -> u64;

@@ -50,6 +50,8 @@ def lib():
                                     C.POINTER(C.c_double)]
         L.oracle_finalize_text.restype = C.c_int
         L.oracle_finalize_text.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Acc), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.oracle_fe_tile.restype = C.c_int
+        L.oracle_fe_tile.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Acc), C.POINTER(C.c_uint64)]
         L.oracle_constants.restype = C.c_int
         L.oracle_constants.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_double)]
         _lib = L
@@ -96,6 +98,16 @@ def events(valeurs_text, features, n):
     rc = lib().oracle_events(valeurs_text.encode(), mask(features), n, mom, kept, m2)
     assert rc == 0
     return list(mom), list(kept), list(m2)
+
+
+def fe_tile(valeurs_text, features, first_round, n_rounds, max_events):
+    """(merged accumulator, number of events) of the faster-evgen events that start in RANF rounds
+    [first_round, first_round + n_rounds), at most max_events of them (0 = no limit): the checker of tp3_fe_tile_device."""
+    acc = Acc()
+    done = C.c_uint64()
+    rc = lib().oracle_fe_tile(valeurs_text.encode(), mask(features), first_round, n_rounds, max_events, C.byref(acc), C.byref(done))
+    assert rc == 0, rc
+    return acc, int(done.value)
 
 
 def constants(valeurs_text, features=""):

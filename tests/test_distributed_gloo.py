@@ -67,6 +67,53 @@ def _worker(rank, world, port, valeurs_text, q):
     dist.destroy_process_group()
 
 
+def _tiles_worker(rank, world, port, valeurs_text, n_events, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    tp3 = load_package()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    cfg = tp3.Configuration.parse(valeurs_text, "faster-evgen").with_num_events(n_events)
+
+    def tile13(first_round, n_rounds, max_events):  # the oracle stands in for tp3_fe_tile_device
+        acc, n = oracle_lib.fe_tile(valeurs_text, "faster-evgen", first_round, n_rounds, max_events)
+        return torch.tensor(tp3.acc_to_f64x13(acc), dtype=torch.float64), n
+
+    fin = tp3.run_simulation_tiles(cfg, tile13, world, rank, dist, "cpu")
+    if rank == 0:
+        q.put((fin.selected_events, fin.sigma))
+    else:
+        assert fin is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_faster_evgen_stream_tiles_over_ranks(tp3, oracle, valeurs_text, world):
+    """faster-evgen at N > 1 shards the STREAM: run_simulation_tiles (tile bounds, the 8-byte count exchange, the last
+    rank's remainder, the reduce of 13 doubles) over a world_size-2 gloo group, with the oracle's tile walk standing in
+    for the GPU.  Same events as the sequential run: same selected-event count, sigma equal up to the order of additions."""
+    n_events = 123_456
+    cfg = tp3.Configuration.parse(valeurs_text, "faster-evgen").with_num_events(n_events)
+    whole, n = oracle.fe_tile(valeurs_text, "faster-evgen", 0, 0, n_events)
+    assert n == n_events
+    want = tp3.finalize(cfg, tp3.Acc.from_buffer_copy(bytes(whole)))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tiles_worker, args=(r, world, port, valeurs_text, n_events, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    sel, sigma = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sel == want.selected_events
+    assert abs(sigma - want.sigma) <= 1e-12 * abs(want.sigma)
+
+
 @pytest.mark.parametrize("world", [2])
 def test_sharded_run_is_bit_identical_to_single_process(tp3, oracle, valeurs_text, world):
     cfg = tp3.Configuration.parse(valeurs_text).with_num_events(N_EVENTS)

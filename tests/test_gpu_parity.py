@@ -537,6 +537,71 @@ def test_faster_evgen_stream_pipeline_equals_host_pre_advance(tp3, valeurs_text,
         assert bytes(plain) == bytes(dev)
 
 
+@pytest.mark.parametrize("first_round,n_rounds,max_events", [(0, 7168, 0), (7168, 4096, 0), (7168, 0, 12345), (64, 640, 0), (5120, 2048, 3000)])
+def test_faster_evgen_stream_tile_matches_oracle(tp3, oracle, valeurs_text, first_round, n_rounds, max_events):
+    """tp3_fe_tile_device against the oracle's own walk of the generator (oracle_fe_tile: the oracle's Ranf, wrapped only
+    to count its refills): the same number of events start in the tile, the same ones are selected, the sums agree to
+    1e-10 -- for tiles limited by rounds, by events, and by both."""
+    import torch
+    cfg = tp3.Configuration.parse(valeurs_text, "faster-evgen")
+    want, want_n = oracle.fe_tile(valeurs_text, "faster-evgen", first_round, n_rounds, max_events)
+    out = torch.zeros(13, dtype=torch.float64, device="cuda")
+    with tp3.Simulator(cfg) as sim:
+        n = sim.fe_tile_device(first_round, n_rounds, max_events, out.data_ptr())
+        sim.synchronize()
+    got = tp3.acc_from_f64x13(out.cpu().tolist())
+    assert n == want_n
+    assert got.selected_events == want.selected_events
+    assert_acc_close(got, want, REL_F64, n_events=want_n, what="tile vs oracle")
+
+
+@pytest.mark.parametrize("features", ["faster-evgen", "faster-evgen,f32"])
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_faster_evgen_stream_tiles_partition_the_run(tp3, valeurs_text, features, world):
+    """faster-evgen on several GPUs shards the STREAM (tp3_fe_tile_device): rank r takes the events that start in its
+    range of RANF rounds, the last rank adds the exact remainder, one sum of 13 doubles finishes the run.  Here the `world`
+    tiles are simulated one after the other on one GPU and summed: the events are exactly those of the sequential run
+    (same number of events, same selected-event count) and the sums agree up to the order of the additions."""
+    import torch
+    n_events = 3_456_789
+    cfg = tp3.Configuration.parse(valeurs_text, features).with_num_events(n_events)
+    nb, last = tp3.batch_layout(n_events)
+    with tp3.Simulator(cfg) as sim:
+        want = sim.simulate_merged(0, nb, last)
+        out = torch.zeros(13, dtype=torch.float64, device="cuda")
+
+        def tile13(first_round, n_rounds, max_events):
+            count = sim.fe_tile_device(first_round, n_rounds, max_events, out.data_ptr())
+            sim.synchronize()
+            return out.clone(), count
+
+        bounds = tp3.fe_tile_bounds(n_events, world)
+        assert bounds[0] == 0 and all(b % 512 == 0 for b in bounds) and sorted(bounds) == bounds
+        total = torch.zeros(13, dtype=torch.float64, device="cuda")
+        counted = 0
+        for r in range(world):
+            t, c = tile13(bounds[r], bounds[r + 1] - bounds[r], 0)
+            total += t
+            counted += c
+        remaining = n_events - counted
+        assert 0 < remaining < 0.002 * n_events + 20000, (counted, n_events)
+        t, c = tile13(bounds[world], 0, remaining)
+        assert c == remaining
+        total += t
+        got = tp3.acc_from_f64x13(total.cpu().tolist())
+        # and through the function bench.py uses (single process: no collective)
+        if world == 1:
+            fin = tp3.run_simulation_tiles(cfg, tile13, 1, 0, device="cuda")
+            assert fin.selected_events == want.selected_events
+    assert got.selected_events == want.selected_events
+    if "f32" not in features:
+        assert_acc_close(got, want, REL_F64, n_events=n_events, what="tiles vs sequential run")
+    else:
+        g, w = acc_fields(got), acc_fields(want)
+        for k in (0, 1, 2, 5, 6, 7, 10, 11):
+            assert abs(g[k] - w[k]) <= 1e-3 * abs(w[k]), f"field {k}: {g[k]} vs {w[k]}"
+
+
 @pytest.mark.parametrize("features,first,nb", [("faster-evgen,standard-random", 0, 300), ("faster-evgen,standard-random", 1990, 130),
                                                ("faster-evgen,standard-random,f32", 7, 64)])
 @pytest.mark.parametrize("split", [1, 32])

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "jump_tables.hpp"
@@ -71,7 +72,8 @@ struct DeviceSlot {
         uint32_t* d_unit_seg = nullptr;
         tp3_acc* d_parts = nullptr;
         size_t unit_cap = 0;
-        cudaStream_t st = nullptr;       // buffer 0: the slot's stream; buffer 1: fs_stream2
+        cudaEvent_t phys_done = nullptr; // the physics kernel that last read this buffer's records
+        bool phys_pending = false;
         // host side of the pass in flight on this buffer
         std::vector<uint32_t> h_count, h_unit_seg;
         std::vector<uint8_t> h_exit, h_fail;
@@ -84,6 +86,10 @@ struct DeviceSlot {
     cudaEvent_t fs_event = nullptr;
     // last launch
     uint64_t last_first = 0, last_n = 0;
+    SimArgs last_args;                       // its schedule (fused default kernel)
+    cudaStream_t copy_stream = nullptr;      // tp3_simulate_batches: accumulators go to the host while the kernel runs
+    cudaEvent_t copy_event = nullptr;
+    unsigned long long* h_progress = nullptr;  // pinned
 };
 
 }  // namespace
@@ -177,6 +183,7 @@ struct Sched {
     int64_t grid_warps;    // 0 = auto
     bool stream_continues; // sequential RANF: a warp's next batch continues the stream, so units of several batches pay
     int64_t dynamic;       // 1: one unit per warp, dispatched by the hardware (kernels.cuh)
+    SimArgs* filled;       // out (may be null): the schedule the launcher chose
 };
 
 // Fill the schedule fields of `a` for a kernel that runs `warps`-warp CTAs, `ctas_per_sm` of them per SM.
@@ -195,6 +202,7 @@ cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& s
         a.unit_batches = (uint32_t)unit;
         a.full_rounds = (uint32_t)big;
         a.n_warps = (uint32_t)((units + warps - 1) / warps * warps);
+        if (sc.filled) *sc.filled = a;
         return cudaSuccess;
     }
     if (a.n_batches < W) W = (a.n_batches + warps - 1) / warps * warps;  // one batch per warp, no full round
@@ -207,6 +215,7 @@ cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& s
     a.n_warps = (uint32_t)W;
     a.unit_batches = (uint32_t)unit;
     a.full_rounds = (uint32_t)(a.n_batches / (W * unit));
+    if (sc.filled) *sc.filled = a;
     return cudaSuccess;
 }
 // Resident CTAs per SM of a kernel (asked once per kernel and dynamic shared memory size).
@@ -708,15 +717,20 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
     if (tile) n = e_hi == kNoLimit ? kNoLimit : (e_hi + B - 1) / B;
     c->stat_fe_passes = c->stat_fe_redone = 0;
     const double kRoundsPerEvent = 0.3252;  // 3.076 events start per round on average (measured); only sizes the passes
-    const uint64_t lanes_per_wave = (uint64_t)s.sm_count * 28 * 32;  // the walk kernel alone holds 7 CTAs of 4 warps per SM (shared memory)
+    const uint64_t lanes_per_wave = (uint64_t)s.sm_count * 26 * 32;  // the walk kernel alone holds 26 one-warp CTAs per SM (shared memory)
     const uint32_t warm = c->opt_fe_warm > 0 ? (uint32_t)c->opt_fe_warm : (uint32_t)kFeWarm;
     const bool overlap = !c->opt_fe_serial;
     if (!s.fs_stream2) {
-        TP3_CUDA(c, cudaStreamCreateWithFlags(&s.fs_stream2, cudaStreamNonBlocking));
+        // The walks run on a HIGH-PRIORITY stream of their own, the physics kernels on the slot's stream: the blocks of the walk
+        // of pass k + 1 (integer work) are placed as soon as CTAs of the physics kernel of pass k (FP64 work) retire.
+        int prio_lo = 0, prio_hi = 0;
+        TP3_CUDA(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        TP3_CUDA(c, cudaStreamCreateWithPriority(&s.fs_stream2, cudaStreamNonBlocking, prio_hi));
         TP3_CUDA(c, cudaEventCreateWithFlags(&s.fs_event, cudaEventDisableTiming));
+        for (auto& b : s.fs) TP3_CUDA(c, cudaEventCreateWithFlags(&b.phys_done, cudaEventDisableTiming));
     }
-    s.fs[0].st = s.stream;
-    s.fs[1].st = overlap ? s.fs_stream2 : s.stream;
+    cudaStream_t const sw = overlap ? s.fs_stream2 : s.stream, sp = s.stream;  // walks / physics
+    for (auto& b : s.fs) b.phys_pending = false;
     {
         // Both kernels ask for the largest shared-memory carve-out: CTAs of two kernels only share an SM if they agree on the
         // L1 / shared split, and the walk of pass k + 1 is meant to run next to the physics of pass k.
@@ -729,15 +743,15 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         }();
         (void)once;
     }
-    // the second stream starts after whatever the caller has queued on the slot's stream
+    // the walk stream starts after whatever the caller has queued on the slot's stream
     TP3_CUDA(c, cudaEventRecord(s.fs_event, s.stream));
     TP3_CUDA(c, cudaStreamWaitEvent(s.fs_stream2, s.fs_event, 0));
 
     uint64_t done_batches = 0;  // batches [first, first + done_batches) have their physics launched
     auto launch_walk = [&](FsBuf& b, const FeWalkArgs& a, uint32_t items) {
-        const unsigned blocks = (items + 127) / 128;
-        if (f32) fe_walk_kernel<float><<<blocks, 128, 0, b.st>>>(a);
-        else fe_walk_kernel<double><<<blocks, 128, 0, b.st>>>(a);
+        const unsigned blocks = (items + 31) / 32;
+        if (f32) fe_walk_kernel<float><<<blocks, kFeWalkThreads, 0, sw>>>(a);
+        else fe_walk_kernel<double><<<blocks, kFeWalkThreads, 0, sw>>>(a);
         ++c->launches;
     };
     auto walk_args = [&](FsBuf& b) {
@@ -756,9 +770,9 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         return w;
     };
     auto fetch_counts = [&](FsBuf& b) -> int {
-        TP3_CUDA(c, cudaMemcpyAsync(b.h_count.data(), b.d_count, b.n_seg * 4, cudaMemcpyDeviceToHost, b.st));
-        TP3_CUDA(c, cudaMemcpyAsync(b.h_exit.data(), b.d_exit, b.n_seg, cudaMemcpyDeviceToHost, b.st));
-        TP3_CUDA(c, cudaMemcpyAsync(b.h_fail.data(), b.d_fail, b.n_seg, cudaMemcpyDeviceToHost, b.st));
+        TP3_CUDA(c, cudaMemcpyAsync(b.h_count.data(), b.d_count, b.n_seg * 4, cudaMemcpyDeviceToHost, sw));
+        TP3_CUDA(c, cudaMemcpyAsync(b.h_exit.data(), b.d_exit, b.n_seg, cudaMemcpyDeviceToHost, sw));
+        TP3_CUDA(c, cudaMemcpyAsync(b.h_fail.data(), b.d_fail, b.n_seg, cudaMemcpyDeviceToHost, sw));
         return TP3_OK;
     };
     // Size pass `b` from the known point (round, events) towards the first batch that still has to be served, and start its walk.
@@ -802,6 +816,10 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         b.h_count.resize(n_seg);
         b.h_exit.resize(n_seg);
         b.h_fail.resize(n_seg);
+        if (b.phys_pending) {  // the records of this buffer are still being read by the physics kernel of two passes ago
+            TP3_CUDA(c, cudaStreamWaitEvent(sw, b.phys_done, 0));
+            b.phys_pending = false;
+        }
         launch_walk(b, walk_args(b), (uint32_t)n_seg);
         TP3_CUDA(c, cudaGetLastError());
         return fetch_counts(b);
@@ -812,7 +830,7 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
     if (rc) return rc;
     while (true) {
         FsBuf& b = s.fs[cur];
-        TP3_CUDA(c, cudaStreamSynchronize(b.st));  // the walk of this pass is over (the physics of the previous pass may still run)
+        TP3_CUDA(c, cudaStreamSynchronize(sw));  // the walk of this pass is over (the physics of the previous pass may still run)
         ++c->stat_fe_passes;
         const uint64_t n_seg = b.n_seg;
         // ---- segments whose nine walks had not coincided at their start: redo them from the predecessor's exit state
@@ -835,8 +853,8 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
                 return TP3_E_INVALID;
             }
             c->stat_fe_redone += (int64_t)list.size();
-            TP3_CUDA(c, cudaMemcpyAsync(b.d_redo_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, b.st));
-            TP3_CUDA(c, cudaMemcpyAsync(b.d_redo_entry, entry.data(), entry.size(), cudaMemcpyHostToDevice, b.st));
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_redo_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, sw));
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_redo_entry, entry.data(), entry.size(), cudaMemcpyHostToDevice, sw));
             FeWalkArgs r = walk_args(b);
             r.seg_list = b.d_redo_list;
             r.seg_entry = b.d_redo_entry;
@@ -844,7 +862,7 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
             launch_walk(b, r, r.n_list);
             TP3_CUDA(c, cudaGetLastError());
             if ((rc = fetch_counts(b))) return rc;
-            TP3_CUDA(c, cudaStreamSynchronize(b.st));  // (also: `list` and `entry` die with this iteration)
+            TP3_CUDA(c, cudaStreamSynchronize(sw));  // (also: `list` and `entry` die with this iteration)
         }
         // ---- 2. absolute index of every segment's first event (multi_threading.rs:59-64 finds these event by event)
         b.h_seg_events.resize(n_seg + 1);
@@ -893,8 +911,8 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
                 while (g + 1 < n_seg && b.h_seg_events[g + 1] <= ev) ++g;
                 b.h_unit_seg[u] = (uint32_t)g;
             }
-            TP3_CUDA(c, cudaMemcpyAsync(b.d_seg_events, b.h_seg_events.data(), (n_seg + 1) * 8, cudaMemcpyHostToDevice, b.st));
-            TP3_CUDA(c, cudaMemcpyAsync(b.d_unit_seg, b.h_unit_seg.data(), n_units * 4, cudaMemcpyHostToDevice, b.st));
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_seg_events, b.h_seg_events.data(), (n_seg + 1) * 8, cudaMemcpyHostToDevice, sp));
+            TP3_CUDA(c, cudaMemcpyAsync(b.d_unit_seg, b.h_unit_seg.data(), n_units * 4, cudaMemcpyHostToDevice, sp));
             FePhysArgs ph;
             std::memset(&ph, 0, sizeof ph);
             ph.records = b.d_records;
@@ -910,16 +928,33 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
             // they retire the blocks of the next pass's walk, queued on the other stream, move in next to them.
             uint64_t W = n_units;
             if (c->opt_grid_warps > 0 && (uint64_t)c->opt_grid_warps < W) W = (uint64_t)c->opt_grid_warps;
-            ph.n_warps = (uint32_t)W;
-            if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, 0, b.st>>>(ph, phys_params<float>(c->params));
-            else fe_physics_kernel<double><<<(unsigned)W, 32, 0, b.st>>>(ph, phys_params<double>(c->params));
+            if (c->hist_bins) {
+                // per-event observables: as many CTAs as the device holds, each flushes its shared-memory counts once
+                W = std::min<uint64_t>(W, (uint64_t)s.sm_count * 16);
+                ph.hist_bins = c->hist_bins;
+                ph.hist_counts = s.d_hist_counts;
+                ph.hist_weights = s.d_hist_weights;
+                ph.n_warps = (uint32_t)W;
+                const size_t dyn = (size_t)TP3_HIST_OBSERVABLES * c->hist_bins * sizeof(uint32_t);
+                const bool sorted = !(c->params.flags & TP3_NO_PHOTON_SORTING);
+                if (f32 && sorted) fe_physics_kernel<float, 2><<<(unsigned)W, 32, dyn, sp>>>(ph, phys_params<float>(c->params));
+                else if (f32) fe_physics_kernel<float, 1><<<(unsigned)W, 32, dyn, sp>>>(ph, phys_params<float>(c->params));
+                else if (sorted) fe_physics_kernel<double, 2><<<(unsigned)W, 32, dyn, sp>>>(ph, phys_params<double>(c->params));
+                else fe_physics_kernel<double, 1><<<(unsigned)W, 32, dyn, sp>>>(ph, phys_params<double>(c->params));
+            } else {
+                ph.n_warps = (uint32_t)W;
+                if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, 0, sp>>>(ph, phys_params<float>(c->params));
+                else fe_physics_kernel<double><<<(unsigned)W, 32, 0, sp>>>(ph, phys_params<double>(c->params));
+            }
             ++c->launches;
             TP3_CUDA(c, cudaGetLastError());
             const unsigned cb = (unsigned)((nb * 13 + 255) / 256);
-            if (f32) fe_combine_parts_kernel<float><<<cb, 256, 0, b.st>>>(b.d_parts, nb, s.d_out + lo_batches);
-            else fe_combine_parts_kernel<double><<<cb, 256, 0, b.st>>>(b.d_parts, nb, s.d_out + lo_batches);
+            if (f32) fe_combine_parts_kernel<float><<<cb, 256, 0, sp>>>(b.d_parts, nb, s.d_out + lo_batches);
+            else fe_combine_parts_kernel<double><<<cb, 256, 0, sp>>>(b.d_parts, nb, s.d_out + lo_batches);
             ++c->launches;
             TP3_CUDA(c, cudaGetLastError());
+            TP3_CUDA(c, cudaEventRecord(b.phys_done, sp));
+            b.phys_pending = true;
         }
         if (!more) break;
         // ---- ... while the next pass is walked on the other stream (queued behind the physics that last used that buffer)
@@ -930,9 +965,7 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
         tile->events_done = e_hi;
         tile->batches_done = done_batches;
     }
-    // the slot's stream owns the result
-    TP3_CUDA(c, cudaEventRecord(s.fs_event, s.fs_stream2));
-    TP3_CUDA(c, cudaStreamWaitEvent(s.stream, s.fs_event, 0));
+    // (every physics kernel ran on the slot's stream, behind the walk it depends on: the slot's stream owns the result)
     return TP3_OK;
 }
 
@@ -1006,6 +1039,14 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     std::vector<uint64_t> fe_xo;
     const bool device_scan = seq_faster && !(c->params.flags & TP3_STANDARD_RANDOM) && !c->opt_fe_host_scan;
     uint32_t fe_split = 1;
+    if (device_scan && (c->opt_fe_legacy || c->opt_fe_split) && c->hist_bins) {
+        c->err = "per-event observables under faster-evgen need the stream pipeline (fe_legacy / fe_split are set)";
+        return TP3_E_INVALID;
+    }
+    if (seq_faster && !device_scan && c->hist_bins) {
+        c->err = "per-event observables under faster-evgen need the stream pipeline (fe_host_scan is set)";
+        return TP3_E_INVALID;
+    }
     if (device_scan && !c->opt_fe_legacy && !c->opt_fe_split) {
         // walk -> event records -> physics (fe_stream.cuh): the shipped path for the sequential RANF stream
         rc = fe_stream_simulate(c, s, first, n, last_len);
@@ -1092,7 +1133,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         a.hist_counts = s.d_hist_counts;
         a.hist_weights = s.d_hist_weights;
         const Sched sc{s.sm_count, c->opt_unit_batches, c->opt_grid_warps,
-                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic};
+                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic, &s.last_args};
         if (fold) {
             // Completion marks: one word per unit, compared with this launch's epoch (no memset per launch).  The number
             // of units is at most n + the grid's warps; the grid never exceeds 64 warps per SM.
@@ -1224,6 +1265,11 @@ void tp3_destroy(tp3_ctx* c) {
             cudaStreamDestroy(s.fs_stream2);
         }
         if (s.fs_event) cudaEventDestroy(s.fs_event);
+        if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+        if (s.copy_event) cudaEventDestroy(s.copy_event);
+        if (s.h_progress) cudaFreeHost(s.h_progress);
+        for (auto& b : s.fs)
+            if (b.phys_done) cudaEventDestroy(b.phys_done);
         cudaFree(s.d_hist_counts);
         cudaFree(s.d_hist_weights);
     }
@@ -1249,8 +1295,12 @@ int tp3_histograms_enable(tp3_ctx* c, uint32_t num_bins) {
         c->err = "tp3_histograms_enable: at most " + std::to_string(TP3_HIST_MAX_BINS) + " bins";
         return TP3_E_INVALID;
     }
-    if (num_bins && ((c->params.flags & TP3_FASTER_EVGEN) || c->params.kernel != TP3_KERNEL_FAST)) {
-        c->err = "per-event observables need the fast kernel with the default event generator";
+    // faster-evgen: the stream pipeline of the sequential RANF stream has the epilogue (fe_stream.cuh), the kernels that serve
+    // xoshiro and jump() seeding (one thread per batch / one lane per 313 events) do not
+    const bool fe = c->params.flags & TP3_FASTER_EVGEN;
+    const bool fe_stream = fe && !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING));
+    if (num_bins && ((fe && !fe_stream) || c->params.kernel != TP3_KERNEL_FAST)) {
+        c->err = "per-event observables need the fast kernel and, under faster-evgen, the sequential RANF stream";
         return TP3_E_INVALID;
     }
     for (auto& s : c->devs) {
@@ -1354,8 +1404,57 @@ int tp3_fetch(tp3_ctx* c, tp3_acc* out, uint64_t n) {
     return tp3_synchronize(c);
 }
 
+// Large single-device launches of the fused kernel: the per-batch accumulators are copied to the caller's array WHILE the
+// kernel runs.  The in-kernel ordered fold doubles as the progress indicator: units [0, next_unit) are complete, in batch
+// order, so their accumulators can go (104 MB per 1e6 batches would otherwise be copied after the kernel: 5 % of a run).
+static int simulate_batches_streamed(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
+    TP3_CUDA(c, cudaSetDevice(s.dev));
+    if (!s.copy_stream) {
+        TP3_CUDA(c, cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+        TP3_CUDA(c, cudaEventCreateWithFlags(&s.copy_event, cudaEventDisableTiming));
+        TP3_CUDA(c, cudaHostAlloc(&s.h_progress, sizeof(unsigned long long), cudaHostAllocDefault));
+    }
+    int rc = enqueue_range(c, s, first, n, last_len, /*fold=*/true);
+    if (rc) return rc;
+    TP3_CUDA(c, cudaEventRecord(s.copy_event, s.stream));
+    const SimArgs& a = s.last_args;
+    auto batches_of = [&](uint64_t units) -> uint64_t {  // batches covered by units [0, units) of the dynamic schedule (kernels.cuh)
+        const uint64_t big = a.full_rounds;
+        return units <= big ? units * a.unit_batches : std::min<uint64_t>(n, big * a.unit_batches + (units - big));
+    };
+    uint64_t copied = 0;
+    const uint64_t chunk = std::max<uint64_t>(n / 64, 4096);
+    for (;;) {
+        const bool finished = cudaEventQuery(s.copy_event) == cudaSuccess;
+        uint64_t ready = n;
+        if (!finished) {
+            TP3_CUDA(c, cudaMemcpyAsync(s.h_progress, &s.d_fold->next_unit, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.copy_stream));
+            TP3_CUDA(c, cudaStreamSynchronize(s.copy_stream));
+            ready = batches_of(*s.h_progress);
+        }
+        if (ready - copied >= chunk || (finished && ready > copied)) {
+            TP3_CUDA(c, cudaMemcpyAsync(out + copied, s.d_out + copied, (ready - copied) * sizeof(tp3_acc), cudaMemcpyDeviceToHost, s.copy_stream));
+            TP3_CUDA(c, cudaStreamSynchronize(s.copy_stream));
+            copied = ready;
+        }
+        if (finished && copied == n) break;
+        if (!finished) std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess) {
+        c->err = std::string("tp3_simulate_batches: ") + cudaGetErrorString(e);
+        return TP3_E_CUDA;
+    }
+    return TP3_OK;
+}
+
 int tp3_simulate_batches(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
     if (!out) return TP3_E_INVALID;
+    if (c && c->devs.size() == 1 && n >= 32768 && n <= 0x7fffffffull && last_len >= 1 && last_len <= TP3_EVENT_BATCH_SIZE &&
+        !(c->params.flags & TP3_FASTER_EVGEN) && c->opt_sched_dynamic && !c->hist_bins) {
+        c->devs[0].last_n = 0;
+        return simulate_batches_streamed(c, c->devs[0], first, n, last_len, out);
+    }
     int rc = tp3_simulate_batches_device(c, first, n, last_len);
     if (rc) return rc;
     return tp3_fetch(c, out, n);

@@ -151,14 +151,16 @@ __device__ __forceinline__ void fe_next_round(uint32_t* row) {
     for (int k = 24; k < kRanfLag; ++k) FE_ROW(k) = ranf_sub(FE_ROW(k), FE_ROW(k - 24));
 }
 
+// ONE WARP = ONE CTA (7.5 KB of shared memory, 56 registers): a block fits wherever one CTA of the physics kernel retires,
+// which is what lets the walk of the next pass run next to the physics of this one (api.cu: fe_stream_simulate).
+constexpr int kFeWalkThreads = 32;
 template <class F>
-__global__ void __launch_bounds__(128, TP3_FE_GEN_REGS ? 5 : 7) fe_walk_kernel(const FeWalkArgs a) {
-    __shared__ FeWalkSmem sm[4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FeWalkSmem& w = sm[warp];
+__global__ void __launch_bounds__(kFeWalkThreads, TP3_FE_GEN_REGS ? 20 : 28) fe_walk_kernel(const FeWalkArgs a) {
+    __shared__ FeWalkSmem w;
+    const int lane = threadIdx.x & 31;
     const bool redo = a.seg_list != nullptr;
     const uint32_t n_items = redo ? a.n_list : a.n_seg;
-    const uint32_t item0 = (blockIdx.x * 4 + warp) * 32;
+    const uint32_t item0 = blockIdx.x * 32;
     if (item0 >= n_items) return;
     const uint32_t* base = a.jump_table + (size_t)kRanfDigits * 256 * kRanfLag;  // the seeded round 0
 
@@ -382,6 +384,10 @@ struct FePhysArgs {
     uint32_t n_units;              // kFeParts per batch
     uint32_t n_warps;
     tp3_acc* out_parts;            // [n_units]
+    // per-event observables (tp3.h): device histograms, or null
+    uint32_t hist_bins;
+    unsigned long long* hist_counts;   // [TP3_HIST_OBSERVABLES][hist_bins]
+    double* hist_weights;              // [kHistReplicas][TP3_HIST_OBSERVABLES][hist_bins]
 };
 
 template <class F> struct FePhysSmem {
@@ -395,9 +401,17 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 
 // ONE WARP = ONE CTA, like the fused default kernel; warp w takes units [n_units w / W, n_units (w + 1) / W).
-template <class F> __global__ void __launch_bounds__(32, 16) fe_physics_kernel(const FePhysArgs a, const PhysParams<F> P) {
+// HIST: 0 = none; 1 / 2 = the per-event observable epilogue of the default kernel (kernels.cuh: hist_fill) with the photons in
+// generation order / sorted by decreasing energy.
+template <class F, int HIST = 0> __global__ void __launch_bounds__(32, 16) fe_physics_kernel(const FePhysArgs a, const PhysParams<F> P) {
     __shared__ FePhysSmem<F> sm;
+    extern __shared__ __align__(16) unsigned char fe_hist_raw[];
     const int lane = threadIdx.x;
+    const int hist_n = HIST ? TP3_HIST_OBSERVABLES * (int)a.hist_bins : 0;
+    uint32_t* const hist_c = reinterpret_cast<uint32_t*>(fe_hist_raw);
+    double* const hist_w = HIST ? a.hist_weights + (size_t)(blockIdx.x % kHistReplicas) * hist_n : nullptr;
+    if (HIST)
+        for (int i = lane; i < hist_n; i += 32) hist_c[i] = 0u;
     for (int i = lane; i < 128; i += 32) sm.log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
     __syncwarp();
     static_assert(offsetof(FastMathSmem, log_tab) == 0, "log_tab must lead FastMathSmem");
@@ -450,6 +464,7 @@ template <class F> __global__ void __launch_bounds__(32, 16) fe_physics_kernel(c
                 F m[5];
                 me_fast<F>(e, P, m);
                 acc.integrate(m, P.sigma_contribs);
+                if (HIST) hist_fill<F, HIST == 2>(e, m, P, hist_c, hist_w, (int)a.hist_bins);
             }
         }
         if (lane < q_count) {  // drain
@@ -458,6 +473,7 @@ template <class F> __global__ void __launch_bounds__(32, 16) fe_physics_kernel(c
             F m[5];
             me_fast<F>(e, P, m);
             acc.integrate(m, P.sigma_contribs);
+            if (HIST) hist_fill<F, HIST == 2>(e, m, P, hist_c, hist_w, (int)a.hist_bins);
         }
         __syncwarp();
         F v[12];
@@ -479,6 +495,13 @@ template <class F> __global__ void __launch_bounds__(32, 16) fe_physics_kernel(c
             }
             o->sigma = (double)v[10];
             o->variance = (double)v[11];
+        }
+    }
+    if (HIST) {  // CTA histograms -> device histograms
+        __syncwarp();
+        for (int i = lane; i < hist_n; i += 32) {
+            const uint32_t n = hist_c[i];
+            if (n) atomicAdd(a.hist_counts + i, (unsigned long long)n);
         }
     }
 }

@@ -164,7 +164,8 @@ int  tp3_get_stat(tp3_ctx* ctx, const char* name, int64_t* value);
  * with num_bins uniform bins over the stated range, bin = min(num_bins - 1, floor(t * num_bins)), t the value
  * mapped to [0, 1].  Histograms accumulate over all simulate calls of the context (all devices) until reset.
  * Event counts are exact; the weight sums are accumulated with floating-point reductions (order not fixed:
- * equal to ~1e-13 relative between runs).  Available for the fast kernel with the default event generator. */
+ * equal to ~1e-13 relative between runs).  Available for the fast kernel: default event generator (any generator and
+ * seeding) and faster-evgen on the sequential RANF stream. */
 #define TP3_HIST_OBSERVABLES 6
 #define TP3_HIST_MAX_BINS 1024
 /* num_bins = 0 switches the epilogue off again. */

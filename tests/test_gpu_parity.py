@@ -698,7 +698,7 @@ def _oracle_histograms(oracle, tp3, valeurs_text, features, n_events, bins):
     return cfg, np.array(counts), np.array(weights), int(sel.sum())
 
 
-@pytest.mark.parametrize("features", ["", "no-photon-sorting", "standard-random", "f32"])
+@pytest.mark.parametrize("features", ["", "no-photon-sorting", "standard-random", "f32", "faster-evgen", "faster-evgen,no-photon-sorting"])
 def test_histograms_match_oracle_events(tp3, oracle, valeurs_text, features):
     """the histogram hook the reference leaves empty (main.rs:117-122,133), filled in the fused
     kernel.  Event counts per bin are exact (a value within rounding of a bin edge may move one event: slack 2 per
@@ -736,10 +736,15 @@ def test_histograms_match_oracle_events(tp3, oracle, valeurs_text, features):
 
 
 def test_histograms_refused_where_unsupported(tp3, valeurs_text):
-    cfg = tp3.Configuration.parse(valeurs_text, "faster-evgen")
-    with tp3.Simulator(cfg) as sim:
+    for features in ("faster-evgen,standard-random", "faster-evgen,multi-threading,faster-threading"):
+        with tp3.Simulator(tp3.Configuration.parse(valeurs_text, features)) as sim:
+            with pytest.raises(tp3.Tp3Error):
+                sim.histograms_enable(200)
+    with tp3.Simulator(tp3.Configuration.parse(valeurs_text, "faster-evgen")) as sim:
+        sim.histograms_enable(200)
+        sim.set_option("fe_legacy", 1)
         with pytest.raises(tp3.Tp3Error):
-            sim.histograms_enable(200)
+            sim.simulate_batches(0, 2)
     cfg = tp3.Configuration.parse(valeurs_text, "")
     with tp3.Simulator(cfg) as sim:
         with pytest.raises(tp3.Tp3Error):

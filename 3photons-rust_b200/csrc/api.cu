@@ -88,7 +88,7 @@ struct DeviceSlot {
     uint64_t last_first = 0, last_n = 0;
     SimArgs last_args;                       // its schedule (fused default kernel)
     cudaStream_t copy_stream = nullptr;      // tp3_simulate_batches: accumulators go to the host while the kernel runs
-    cudaEvent_t copy_event = nullptr;
+    cudaEvent_t copy_event = nullptr, copy_event2 = nullptr;
     unsigned long long* h_progress = nullptr;  // pinned
 };
 
@@ -1154,6 +1154,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
             a.unit_done = s.d_unit_done;
             a.fold = s.d_fold;
             TP3_CUDA(c, cudaMemsetAsync(s.d_fold, 0, sizeof(FoldState), s.stream));
+            if (s.copy_event2) TP3_CUDA(c, cudaEventRecord(s.copy_event2, s.stream));  // the fold state of THIS launch starts here
         }
         TP3_CUDA(c, pick_sim(c->params, c->hist_bins != 0, c->opt_f32_scalar != 0)(a, c->params, s.stream, sc));
         ++c->launches;
@@ -1267,6 +1268,7 @@ void tp3_destroy(tp3_ctx* c) {
         if (s.fs_event) cudaEventDestroy(s.fs_event);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
         if (s.copy_event) cudaEventDestroy(s.copy_event);
+        if (s.copy_event2) cudaEventDestroy(s.copy_event2);
         if (s.h_progress) cudaFreeHost(s.h_progress);
         for (auto& b : s.fs)
             if (b.phys_done) cudaEventDestroy(b.phys_done);
@@ -1412,11 +1414,14 @@ static int simulate_batches_streamed(tp3_ctx* c, DeviceSlot& s, uint64_t first, 
     if (!s.copy_stream) {
         TP3_CUDA(c, cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
         TP3_CUDA(c, cudaEventCreateWithFlags(&s.copy_event, cudaEventDisableTiming));
+        TP3_CUDA(c, cudaEventCreateWithFlags(&s.copy_event2, cudaEventDisableTiming));
         TP3_CUDA(c, cudaHostAlloc(&s.h_progress, sizeof(unsigned long long), cudaHostAllocDefault));
     }
     int rc = enqueue_range(c, s, first, n, last_len, /*fold=*/true);
     if (rc) return rc;
     TP3_CUDA(c, cudaEventRecord(s.copy_event, s.stream));
+    // the progress word is only meaningful once this launch's reset of the fold state has run (earlier work may still be queued)
+    TP3_CUDA(c, cudaStreamWaitEvent(s.copy_stream, s.copy_event2, 0));
     const SimArgs& a = s.last_args;
     auto batches_of = [&](uint64_t units) -> uint64_t {  // batches covered by units [0, units) of the dynamic schedule (kernels.cuh)
         const uint64_t big = a.full_rounds;
@@ -1430,7 +1435,7 @@ static int simulate_batches_streamed(tp3_ctx* c, DeviceSlot& s, uint64_t first, 
         if (!finished) {
             TP3_CUDA(c, cudaMemcpyAsync(s.h_progress, &s.d_fold->next_unit, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.copy_stream));
             TP3_CUDA(c, cudaStreamSynchronize(s.copy_stream));
-            ready = batches_of(*s.h_progress);
+            ready = std::max(copied, batches_of(*s.h_progress));
         }
         if (ready - copied >= chunk || (finished && ready > copied)) {
             TP3_CUDA(c, cudaMemcpyAsync(out + copied, s.d_out + copied, (ready - copied) * sizeof(tp3_acc), cudaMemcpyDeviceToHost, s.copy_stream));

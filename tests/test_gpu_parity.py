@@ -323,6 +323,21 @@ def test_batch_range_offsets_and_device_merge(sims, tp3):
     assert bytes(sim.simulate_batches(0, 40)) == bytes(whole)
 
 
+def test_streamed_per_batch_copy(sims, tp3):
+    """tp3_simulate_batches on a large single-device range copies the accumulators to the host WHILE the kernel runs, using
+    the in-kernel fold's progress as the completion mark.  Back-to-back calls (the second polls while the first launch's
+    fold state may still be the last thing written) must return exactly what small, unstreamed calls return."""
+    sim = sims("")
+    n = 40000
+    a = sim.simulate_batches(0, n)
+    b = sim.simulate_batches(n, n, 4321)
+    for lo, arr, base in ((0, a, 0), (n - 7, a, 0), (n, b, n), (2 * n - 50, b, n)):
+        small = sim.simulate_batches(lo, 50 if lo + 50 <= base + n else 7, 4321 if lo == 2 * n - 50 else 10000)
+        for i in range(len(small)):
+            assert bytes(small[i]) == bytes(arr[lo - base + i]), (lo, i)
+    assert bytes(sim.simulate_merged(n, n, 4321)) == bytes(tp3.fold(b))
+
+
 def test_bad_arguments_are_reported(sims, tp3):
     sim = sims("")
     with pytest.raises(tp3.Tp3Error):

@@ -103,6 +103,7 @@ struct tp3_ctx {
     // tp3_set_option: test / A-B switches, read once here instead of from the environment on every launch
     int64_t opt_unit_batches = 0;    // consecutive batches per scheduling unit (0 = by launch size)
     int64_t opt_grid_warps = 0;      // warps in the grid (0 = what the device holds at once)
+    int64_t opt_ramp_units = 0;      // dynamic schedule: ramp units of 1, 2, .., 8 batches at the head of the launch (A/B only)
     int64_t opt_sched_dynamic = 1;   // 1 (default): one unit per warp, dispatched by the hardware in unit order; 0: static balanced schedule (kernels.cuh)
     int64_t opt_f32_scalar = 0;      // f32: one event per lane instead of the packed two-events-per-lane kernel
     int64_t opt_fe_split = 0;        // faster-evgen: 1 = one thread per batch, 32 = one lane per 313 events, 0 = by launch size
@@ -184,6 +185,7 @@ struct Sched {
     bool stream_continues; // sequential RANF: a warp's next batch continues the stream, so units of several batches pay
     int64_t dynamic;       // 1: one unit per warp, dispatched by the hardware (kernels.cuh)
     SimArgs* filled;       // out (may be null): the schedule the launcher chose
+    int64_t ramp_units;    // 0 = none
 };
 
 // Fill the schedule fields of `a` for a kernel that runs `warps`-warp CTAs, `ctas_per_sm` of them per SM.
@@ -195,10 +197,15 @@ cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& s
         // Units in batch order, one warp each: big units of `unit` batches, then single batches for the last ~4 waves.
         uint64_t unit = sc.stream_continues ? 8 : 1;
         if (sc.unit_batches > 0) unit = (uint64_t)sc.unit_batches;
-        const uint64_t singles = std::min<uint64_t>(a.n_batches, 4 * W);
-        const uint64_t big = unit > 1 ? (a.n_batches - singles) / unit : 0;
-        const uint64_t units = big + (a.n_batches - big * unit);
-        a.dynamic = 1;
+        // ramp: the first wave's warps start together; unequal first units (1, 2, .., 8 batches) take them out of step at once
+        // (measured: it does not pay, profiles/r02_schedule_ab.txt: the first wave drifts apart quickly enough on its own; off by default)
+        uint64_t ramp = sc.ramp_units > 0 ? (uint64_t)sc.ramp_units / 8 * 8 : 0;
+        if (ramp / 8 * 36 > a.n_batches) ramp = 0;
+        const uint64_t ramp_batches = ramp / 8 * 36;
+        const uint64_t singles = std::min<uint64_t>(a.n_batches - ramp_batches, 4 * W);
+        const uint64_t big = unit > 1 ? (a.n_batches - ramp_batches - singles) / unit : 0;
+        const uint64_t units = ramp + big + (a.n_batches - ramp_batches - big * unit);
+        a.dynamic = 1 + (uint32_t)ramp;
         a.unit_batches = (uint32_t)unit;
         a.full_rounds = (uint32_t)big;
         a.n_warps = (uint32_t)((units + warps - 1) / warps * warps);
@@ -1133,7 +1140,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         a.hist_counts = s.d_hist_counts;
         a.hist_weights = s.d_hist_weights;
         const Sched sc{s.sm_count, c->opt_unit_batches, c->opt_grid_warps,
-                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic, &s.last_args};
+                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic, &s.last_args, c->opt_ramp_units};
         if (fold) {
             // Completion marks: one word per unit, compared with this launch's epoch (no memset per launch).  The number
             // of units is at most n + the grid's warps; the grid never exceeds 64 warps per SM.
@@ -1424,8 +1431,10 @@ static int simulate_batches_streamed(tp3_ctx* c, DeviceSlot& s, uint64_t first, 
     TP3_CUDA(c, cudaStreamWaitEvent(s.copy_stream, s.copy_event2, 0));
     const SimArgs& a = s.last_args;
     auto batches_of = [&](uint64_t units) -> uint64_t {  // batches covered by units [0, units) of the dynamic schedule (kernels.cuh)
-        const uint64_t big = a.full_rounds;
-        return units <= big ? units * a.unit_batches : std::min<uint64_t>(n, big * a.unit_batches + (units - big));
+        if (units == 0) return 0;
+        uint64_t lo, hi;
+        unit_range_dynamic(a.dynamic - 1, a.full_rounds, a.unit_batches, units - 1, lo, hi);
+        return std::min<uint64_t>(n, hi);
     };
     uint64_t copied = 0;
     const uint64_t chunk = std::max<uint64_t>(n / 64, 4096);
@@ -1576,6 +1585,7 @@ int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
     if (k == "unit_batches" && value >= 0 && value <= 4096) c->opt_unit_batches = value;
     else if (k == "grid_warps" && value >= 0 && value <= (1 << 20)) c->opt_grid_warps = value;
     else if (k == "sched_dynamic") c->opt_sched_dynamic = value != 0;
+    else if (k == "ramp_units" && value >= 0 && value <= (1 << 20)) c->opt_ramp_units = value;
     else if (k == "f32_scalar") c->opt_f32_scalar = value != 0;
     else if (k == "fe_split" && (value == 0 || value == 1 || value == 32)) c->opt_fe_split = value;
     else if (k == "fe_host_scan") c->opt_fe_host_scan = value != 0;

@@ -84,8 +84,10 @@ struct SimArgs {
     uint32_t n_warps;          // W: warps in the grid
     uint32_t unit_batches;     // consecutive batches per unit in the full rounds (the RANF stream simply continues inside a unit)
     uint32_t full_rounds;      // rounds of W full units; the rest is split evenly in one more round
-    uint32_t dynamic;          // 1: one unit per warp, n_warps units dispatched by the hardware in unit order: `full_rounds` units of
-                               //    unit_batches batches first, then single batches (the last waves are short, so the tail is < 1 batch)
+    uint32_t dynamic;          // >= 1: one unit per warp, n_warps units dispatched by the hardware in unit order: dynamic - 1 RAMP units
+                               //    of 1, 2, .., 8, 1, 2, .. batches (an A/B option: unequal first units to take the first wave out of
+                               //    step at once; it does not pay), then `full_rounds` units of unit_batches batches, then single
+                               //    batches (the last waves are short, so the tail is < 1 batch)
     uint32_t epoch;            // value that marks a unit of THIS launch as done in unit_done
     uint32_t* unit_done;       // [(full_rounds + 1) * W], or null: no in-kernel fold
     struct FoldState* fold;    // running accumulator of the ordered fold, or null
@@ -367,14 +369,28 @@ __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
 }
 
 // Batches [lo, hi) of the launch that make up unit u.
-// (dynamic schedule: n_warps has its top bit set, `full_rounds` is the number of big units, the rest are single batches)
+// (dynamic schedule: the first argument has its top bit set and carries the number of ramp units, a multiple of 8, in its
+// other bits; `full_rounds` is the number of big units; the rest are single batches)
 constexpr uint32_t kSchedDynamic = 0x80000000u;
+__host__ __device__ __forceinline__ void unit_range_dynamic(uint64_t ramp, uint64_t big, uint64_t unit_batches, uint64_t u, uint64_t& lo,
+                                                            uint64_t& hi) {
+    const uint64_t ramp_batches = (ramp >> 3) * 36;  // 1 + 2 + .. + 8 per group of eight ramp units
+    if (u < ramp) {
+        const uint64_t j = u & 7;
+        lo = (u >> 3) * 36 + j * (j + 1) / 2;
+        hi = lo + j + 1;
+    } else if (u < ramp + big) {
+        lo = ramp_batches + (u - ramp) * unit_batches;
+        hi = lo + unit_batches;
+    } else {
+        lo = ramp_batches + big * unit_batches + (u - ramp - big);
+        hi = lo + 1;
+    }
+}
 __device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint64_t n_batches, uint64_t u,
                                            uint64_t& lo, uint64_t& hi) {
     if (n_warps & kSchedDynamic) {
-        const uint64_t big = full_rounds;
-        lo = u < big ? u * unit_batches : big * unit_batches + (u - big);
-        hi = u < big ? lo + unit_batches : lo + 1;
+        unit_range_dynamic(n_warps & ~kSchedDynamic, full_rounds, unit_batches, u, lo, hi);
         return;
     }
     const uint64_t W = n_warps, full = (uint64_t)full_rounds * W;
@@ -388,11 +404,14 @@ __device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_round
     }
 }
 __device__ __forceinline__ void unit_range(const SimArgs& a, uint64_t u, uint64_t& lo, uint64_t& hi) {
-    unit_range(a.dynamic ? (a.n_warps | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.n_batches, u, lo, hi);
+    unit_range(a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.n_batches, u, lo, hi);
 }
 // Number of units of a launch.
 __device__ __forceinline__ uint64_t unit_count(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint64_t n_batches) {
-    if (n_warps & kSchedDynamic) return (uint64_t)full_rounds + (n_batches - (uint64_t)full_rounds * unit_batches);
+    if (n_warps & kSchedDynamic) {
+        const uint64_t ramp = n_warps & ~kSchedDynamic;
+        return ramp + full_rounds + (n_batches - (ramp >> 3) * 36 - (uint64_t)full_rounds * unit_batches);
+    }
     return ((uint64_t)full_rounds + 1) * n_warps;
 }
 
@@ -616,7 +635,7 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
     }
     __syncwarp();
   }
-    if (a.fold) fold_publish<F>(a.fold, a.unit_done, a.out, a.dynamic ? (a.n_warps | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+    if (a.fold) fold_publish<F>(a.fold, a.unit_done, a.out, a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
   }
     if (HIST) {  // CTA histograms -> device histograms
         __syncthreads();
@@ -786,7 +805,7 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
         }
         __syncwarp();
     }
-    if (a.fold) fold_publish<float>(a.fold, a.unit_done, a.out, a.dynamic ? (a.n_warps | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+    if (a.fold) fold_publish<float>(a.fold, a.unit_done, a.out, a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
   }
 }
 

@@ -186,8 +186,8 @@ def run_reference(args, rank):
 
 # FP64 work the shipped fast f64 kernel EXECUTES per generated event (SASS-counted from the committed ncu capture:
 # DFMA = 2 flops, DMUL / DADD = 1), and the ncu FP64-pipe active fraction of the bench's own launch.
-EXECUTED = {"source": "profiles/r01_final2_fast_f64_ranf.txt, profiles/r01_bench_kernel_1e10_events.txt",
-            "dfma": 161.0, "dmul": 108.0, "dadd": 54.0, "pipe_active": 0.693}
+EXECUTED = {"source": "profiles/r02_bench_kernel_1e10_events.txt (ncu --set full of this launch: 1e6 batches, in-kernel fold on)",
+            "dfma": 161.2, "dmul": 107.7, "dadd": 54.0, "pipe_active": 0.683, "traffic": 3963392 + 59656192}
 
 
 def main():
@@ -361,7 +361,7 @@ def main():
         acc_bytes = ctypes.sizeof(pkg.Acc)
         exec_flop = 2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]
         # bytes per launch, from the committed ncu capture of exactly this launch shape (default features, 1e6 batches)
-        ncu_traffic = 58799360 if (default_f64 and nb // world == 1000000) else None
+        ncu_traffic = EXECUTED["traffic"] if (default_f64 and nb // world == 1000000) else None
         fin, fin_pb = main_res["fin"], main_res["fin_pb"]
         line = {
             "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,

@@ -141,6 +141,8 @@ size_t tp3_kernel_arg_bytes(void);
  * beyond the order of floating-point additions, and none selects a CPU path for the simulation:
  *   "unit_batches"     consecutive batches per scheduling unit of the fused kernel (0 = by launch size)
  *   "grid_warps"       warps in the grid (0 = as many as the device holds at once)
+ *   "sched_dynamic"    1 (default): one unit per warp, dispatched by the hardware; 0: static balanced schedule
+ *   "ramp_units"       dynamic schedule: that many units of 1, 2, .., 8 batches at the head of the launch (0 = none, the default)
  *   "f32_scalar"       f32: one event per lane instead of the packed two-events-per-lane kernel
  *   "fe_split"         faster-evgen: 1 = one thread per batch, 32 = one lane per 313 events, 0 = by launch size
  *   "fe_host_scan"     faster-evgen: batch start states from the reference's own method, the event-by-event

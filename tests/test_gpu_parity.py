@@ -210,12 +210,14 @@ def test_batches_match_oracle_f64(sims, oracle, valeurs_text, features, kernel):
         assert_acc_close(accs[b], want, REL_F64, what=f"batch {b}")
 
 
-@pytest.mark.parametrize("unit,grid,dynamic", [(2, 2, 0), (3, 1, 0), (5, 0, 0), (16, 0, 0), (2, 3, 0), (2, 0, 1), (3, 1, 1), (8, 0, 1)])
-def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, dynamic):
+@pytest.mark.parametrize("unit,grid,dynamic,ramp", [(2, 2, 0, 0), (3, 1, 0, 0), (5, 0, 0, 0), (16, 0, 0, 0), (2, 3, 0, 0), (2, 0, 1, 0),
+                                                    (3, 1, 1, 0), (8, 0, 1, 0), (3, 1, 1, 8), (8, 2, 1, 8)])
+def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, dynamic, ramp):
     """A warp that handles several consecutive batches (a scheduling unit) continues the sequential RANF stream instead
     of jumping again; the per-batch accumulators must not depend on how the launch is cut into units, rounds and warps,
     nor on the schedule (static: grids of 1, 2 and 3 warps give several full rounds plus the evenly split last round;
-    dynamic: big units, then single batches; a 1-warp resident set makes every batch of this launch a tail batch) --
+    dynamic: [ramp units of 1, 2, .., 8 batches,] big units, then single batches; a 1-warp resident set makes every batch
+    of this launch a tail batch) --
     bit for bit -- and must match the oracle.  The in-kernel ordered fold equals the host fold for every shape."""
     nb = 43 if dynamic else 11
     cfg = tp3.Configuration.parse(valeurs_text)
@@ -223,7 +225,7 @@ def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, 
         sim.set_option("unit_batches", 1).set_option("sched_dynamic", 0)
         ref = sim.simulate_batches(3, nb, 7777)
     with tp3.Simulator(cfg) as sim:
-        sim.set_option("unit_batches", unit).set_option("grid_warps", grid).set_option("sched_dynamic", dynamic)
+        sim.set_option("unit_batches", unit).set_option("grid_warps", grid).set_option("sched_dynamic", dynamic).set_option("ramp_units", ramp)
         got = sim.simulate_batches(3, nb, 7777)
         merged = sim.simulate_merged(3, nb, 7777)
     assert bytes(got) == bytes(ref)
@@ -283,16 +285,17 @@ def test_other_configurations_match_oracle(tp3, oracle, valeurs_text, name, edit
     for b in range(nb):
         want = run.per_batch[b]
         assert accs[b].selected_events == want.selected_events, f"{name} batch {b}"
-        # Without cuts the matrix elements are singular for photons collinear with the beam and a handful of
-        # such events dominate the sums; their value depends on the last bits of the generated momenta (CUDA vs
-        # glibc sin/cos/log), so only ~1e-8 can be promised there. Every regularised configuration holds 1e-10.
-        rel = 1e-7 if name == "no-cuts" else REL_F64
+        # Without cuts the matrix elements are singular for photons collinear with the beam and a handful of such events
+        # carry 5-7 % of a batch's sums each.  Measured (profiles/r02_nocuts.txt): the literal kernel stays at 1e-13 of the
+        # oracle; the fast kernel at 8e-12 on the A / sigma sums and 1.5e-10 on the variance of the fully cancelling I_MX
+        # sum, hence 1e-9 for it there.  Every regularised configuration holds 1e-10.
+        rel = 1e-9 if (name == "no-cuts" and kernel == 0) else REL_F64
         if want.selected_events:
             assert_acc_close(accs[b], want, rel, what=f"{name} batch {b}")
     if name == "no-cuts":
         assert all(a.selected_events == 10000 for a in accs)
     fin, ofin = tp3.finalize(cfg, tp3.fold(accs)), oracle.run(text, "")
-    assert compare(fin.res_data(), ofin.res_data, rel=1e-6 if name == "no-cuts" else REL_F64) == []
+    assert compare(fin.res_data(), ofin.res_data, rel=1e-8 if (name == "no-cuts" and kernel == 0) else REL_F64) == []
 
 
 # ------------------------------------------------------------- ragged / edge-case geometry

@@ -262,10 +262,11 @@ __global__ void __launch_bounds__(kFeWalkThreads, TP3_FE_GEN_REGS ? 20 : 28) fe_
         const bool may_start = t < seg_end, counting = t >= my_warm;
         bool active = !done && !many;
         int idx = kRanfLag;
-        // One round, request by request, the lanes of the warp in step: [pending requests] then up to four times
-        // [9 numbers][6 numbers + three tests][re-rolls]; a lane whose next request does not fit is finished with the round.
+        // One round, request by request, the lanes of the warp in step: up to four times [9 numbers][6 numbers + three tests]
+        // [re-rolls]; a lane that enters the round with requests pending skips what is already served in its first turn (it then
+        // has room for at most three event starts: 2 + 3 x 15 + 9 > 55), a lane whose next request does not fit is finished.
         for (int e = 0; e < 6; ++e) {
-            if (e > 0 && active && s == 0) {
+            if (active && s == 0) {
                 if (idx >= 9 && may_start) {  // a new event starts here (random_array::<9>, evgen.rs:149)
                     idx -= 9;
                     u0 = FE_ROW(idx); u1 = FE_ROW(idx + 1); u2 = FE_ROW(idx + 2); u3 = FE_ROW(idx + 3); u4 = FE_ROW(idx + 4);

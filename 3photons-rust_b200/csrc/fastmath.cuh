@@ -103,6 +103,17 @@ __device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs)
     s = g;
     rs = h + h;
 }
+// 1/sqrt(x) alone, x > 0 finite normal: the h half of the Goldschmidt pair above (the last update of g is not needed)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    const double y = mufu_rsqrt(x);
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    h = fma(h, r, h);
+    return h + h;
+}
 // sqrt(x), x >= 0; x is biased by 1e-300 so that 0 gives 1e-150 (0 for every use in this kernel) instead of
 // 0 * inf; the nonzero arguments here are >= 4e-9 and unchanged by the bias
 #ifndef TP3_SQRT_RESIDUAL

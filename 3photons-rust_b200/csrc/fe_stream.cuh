@@ -350,11 +350,12 @@ template <> __device__ __forceinline__ void fe_event_from_record<double>(const u
         const double c = fma((double)(int)w[k], fm.fc->u_scale2, -1.0);
         const double e = fma((double)(int)w[3 + k] * (double)(int)w[6 + k], fm.fc->u_scale_sq, Num<double>::MIN_POSITIVE);
         const double x = fma((double)(int)w[9 + 2 * k], fm.fc->u_scale2, -1.0), y = fma((double)(int)w[10 + 2 * k], fm.fc->u_scale2, -1.0);
-        const double st = fast_sqrt(fma(-c, c, 1.0));
         const double en = fast_neg_log(e, fm);
-        double s_, n;
-        fast_sqrt_rsqrt(fma(x, x, y * y), s_, n);  // n = 1 / sqrt(r2)
-        const double esn = (en * st) * n;
+        // sin(theta) / |(x, y)| = sqrt(a) / sqrt(r2) = a / sqrt(a r2), a = 1 - c^2: ONE reciprocal square root instead of a
+        // square root and a reciprocal square root (7 FP64 instructions less per photon).  The bias keeps a = 0 (c = -1: the
+        // draw 0) away from 0 x inf: the factor is then exactly 0, as in the reference; a r2 >= 1.6e-26 otherwise.
+        const double a = fma(-c, c, 1.0);
+        const double esn = (en * a) * fast_rsqrt(fma(a, fma(x, x, y * y), 1e-290));
         q[k][0] = esn * x;
         q[k][1] = esn * y;
         q[k][2] = en * c;

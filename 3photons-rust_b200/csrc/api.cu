@@ -115,8 +115,6 @@ struct tp3_ctx {
     int64_t opt_fe_pass_segments = 0;// faster-evgen stream pipeline: segments per pass (0 = one full wave of lanes)
     int64_t opt_fe_seg_rounds = 0;   // ... rounds per segment (0 = by pass size, <= 1024)
     int64_t opt_fe_warm = 0;         // ... warm-up rounds before a segment (0 = kFeWarm); small values exercise the redo path
-    int64_t opt_fe_walk_pad = 0;     // ... extra dynamic shared memory per CTA of the walk / physics kernel, bytes: caps the CTAs an SM
-    int64_t opt_fe_phys_pad = 0;     //     holds of each (A/B of how the two kernels share the SMs, scripts/fe_corun_probe.py)
     int64_t opt_fe_serial = 0;       // ... 1: passes one after the other on the slot's stream (no walk / physics overlap)
     int64_t stat_fe_passes = 0, stat_fe_redone = 0;  // passes and redone segments of the last call
     // faster-evgen stream pipeline: a round (segment boundary of an earlier pass) whose absolute event index is known
@@ -759,8 +757,8 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
     uint64_t done_batches = 0;  // batches [first, first + done_batches) have their physics launched
     auto launch_walk = [&](FsBuf& b, const FeWalkArgs& a, uint32_t items) {
         const unsigned blocks = (items + 31) / 32;
-        if (f32) fe_walk_kernel<float><<<blocks, kFeWalkThreads, (size_t)c->opt_fe_walk_pad, sw>>>(a);
-        else fe_walk_kernel<double><<<blocks, kFeWalkThreads, (size_t)c->opt_fe_walk_pad, sw>>>(a);
+        if (f32) fe_walk_kernel<float><<<blocks, kFeWalkThreads, 0, sw>>>(a);
+        else fe_walk_kernel<double><<<blocks, kFeWalkThreads, 0, sw>>>(a);
         ++c->launches;
     };
     auto walk_args = [&](FsBuf& b) {
@@ -952,8 +950,8 @@ int fe_stream_simulate(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, ui
                 else fe_physics_kernel<double, 1><<<(unsigned)W, 32, dyn, sp>>>(ph, phys_params<double>(c->params));
             } else {
                 ph.n_warps = (uint32_t)W;
-                if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, (size_t)c->opt_fe_phys_pad, sp>>>(ph, phys_params<float>(c->params));
-                else fe_physics_kernel<double><<<(unsigned)W, 32, (size_t)c->opt_fe_phys_pad, sp>>>(ph, phys_params<double>(c->params));
+                if (f32) fe_physics_kernel<float><<<(unsigned)W, 32, 0, sp>>>(ph, phys_params<float>(c->params));
+                else fe_physics_kernel<double><<<(unsigned)W, 32, 0, sp>>>(ph, phys_params<double>(c->params));
             }
             ++c->launches;
             TP3_CUDA(c, cudaGetLastError());
@@ -1598,8 +1596,6 @@ int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
     else if (k == "fe_seg_rounds" && value >= 0 && value <= 4096) c->opt_fe_seg_rounds = value;
     else if (k == "fe_warm" && value >= 0 && value <= 1024) c->opt_fe_warm = value;
     else if (k == "fe_serial") c->opt_fe_serial = value != 0;
-    else if (k == "fe_walk_pad" && value >= 0 && value <= 32768) c->opt_fe_walk_pad = value;
-    else if (k == "fe_phys_pad" && value >= 0 && value <= 32768) c->opt_fe_phys_pad = value;
     else {
         c->err = "tp3_set_option: unknown option or value out of range: " + k;
         return TP3_E_INVALID;

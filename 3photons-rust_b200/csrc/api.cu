@@ -30,6 +30,9 @@ struct DeviceSlot {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint32_t* d_ranf_table = nullptr;
+    tp3_acc* d_batch_parts = nullptr;  // [n * parts] part accumulators of a launch with batch_parts > 1
+    size_t batch_parts_cap = 0;
+    bool fold_in_kernel = false;       // the last launch folded inside the simulation kernel (else: merge_kernel behind it)
     uint64_t* d_xo_digit_polys = nullptr;
     uint64_t* d_xo_lane_polys = nullptr;
     uint64_t* d_xo_states = nullptr;
@@ -103,6 +106,8 @@ struct tp3_ctx {
     // tp3_set_option: test / A-B switches, read once here instead of from the environment on every launch
     int64_t opt_unit_batches = 0;    // consecutive batches per scheduling unit (0 = by launch size)
     int64_t opt_grid_warps = 0;      // warps in the grid (0 = what the device holds at once)
+    int64_t opt_batch_parts = 1;     // parts per batch (1, 2, 5, 10; 0 = as many of those as still fit one wave of warps): small runs
+                                     //    then fill the device; the per-batch sums depend on it in their last bits (tp3.h)
     int64_t opt_ramp_units = 0;      // dynamic schedule: ramp units of 1, 2, .., 8 batches at the head of the launch (A/B only)
     int64_t opt_sched_dynamic = 1;   // 1 (default): one unit per warp, dispatched by the hardware in unit order; 0: static balanced schedule (kernels.cuh)
     int64_t opt_f32_scalar = 0;      // f32: one event per lane instead of the packed two-events-per-lane kernel
@@ -1006,6 +1011,8 @@ SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     a.first_batch = first;
     a.n_batches = n;
     a.last_batch_len = last_len;
+    a.batch_events = TP3_EVENT_BATCH_SIZE;
+    a.batch_parts = 1;
     a.jump_seeding = (c->params.flags & TP3_FASTER_THREADING) ? 1u : 0u;
     a.ranf_table = s.d_ranf_table;
     a.xo_batch_states = s.d_xo_states;
@@ -1056,6 +1063,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     }
     if (device_scan && !c->opt_fe_legacy && !c->opt_fe_split) {
         // walk -> event records -> physics (fe_stream.cuh): the shipped path for the sequential RANF stream
+        s.fold_in_kernel = false;
         rc = fe_stream_simulate(c, s, first, n, last_len);
         if (rc) return rc;
         if (fold) {
@@ -1113,6 +1121,7 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         ++c->launches;
     }
     if (faster) {
+        s.fold_in_kernel = false;
         FeArgs f;
         std::memset(&f, 0, sizeof f);
         f.first_batch = first;
@@ -1141,6 +1150,52 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         a.hist_weights = s.d_hist_weights;
         const Sched sc{s.sm_count, c->opt_unit_batches, c->opt_grid_warps,
                        !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic, &s.last_args, c->opt_ramp_units};
+        // Small runs (the default 1e7 events are 1000 batches on 2368 warp slots): cut every batch into equal parts, one warp
+        // each, and add the parts of a batch in part order afterwards.  Only where a part's start is a plain stream position
+        // (sequential RANF stream), and only on request: the sums of a batch then depend on the number of parts in their last
+        // bits, so a fixed setting is the caller's choice (tp3_run asks for 0 = auto, it has one launch).
+        uint32_t parts = 1;
+        if (c->opt_batch_parts != 1 && !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING))) {
+            if (c->opt_batch_parts > 1) parts = (uint32_t)c->opt_batch_parts;
+            else
+                for (uint32_t p : {2u, 5u, 10u})  // (part sizes whose last warp iteration ends >= 55 draws in: RanfWarpStream::advance)
+                    if (n * p <= (uint64_t)s.sm_count * 16) parts = p;
+        }
+        if (parts > 1) {
+            if (n * parts > 0x7fffffffull) {
+                c->err = "too many batch parts in one launch";
+                return TP3_E_INVALID;
+            }
+            if (s.batch_parts_cap < n * parts) {
+                if (s.d_batch_parts) TP3_CUDA(c, cudaFree(s.d_batch_parts));
+                s.d_batch_parts = nullptr;
+                s.batch_parts_cap = 0;
+                TP3_CUDA(c, cudaMalloc(&s.d_batch_parts, n * parts * sizeof(tp3_acc)));
+                s.batch_parts_cap = n * parts;
+            }
+            a.first_batch = first * parts;
+            a.n_batches = n * parts;
+            a.batch_events = TP3_EVENT_BATCH_SIZE / parts;
+            a.batch_parts = parts;
+            a.out = s.d_batch_parts;
+            TP3_CUDA(c, pick_sim(c->params, c->hist_bins != 0, c->opt_f32_scalar != 0)(a, c->params, s.stream, sc));
+            const unsigned cb = (unsigned)((n * 13 + 255) / 256);
+            if (c->params.flags & TP3_F32) fe_combine_parts_kernel<float><<<cb, 256, 0, s.stream>>>(s.d_batch_parts, n, s.d_out, (int)parts);
+            else fe_combine_parts_kernel<double><<<cb, 256, 0, s.stream>>>(s.d_batch_parts, n, s.d_out, (int)parts);
+            c->launches += 2;
+            TP3_CUDA(c, cudaGetLastError());
+            if (fold) {
+                if (c->params.flags & TP3_F32) merge_kernel<float><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, n, &s.d_fold->running, true);
+                else merge_kernel<double><<<1, kMergeThreads, 0, s.stream>>>(s.d_out, n, &s.d_fold->running, true);
+                ++c->launches;
+                TP3_CUDA(c, cudaGetLastError());
+            }
+            s.fold_in_kernel = false;
+            s.last_first = first;
+            s.last_n = n;
+            return TP3_OK;
+        }
+        s.fold_in_kernel = fold;
         if (fold) {
             // Completion marks: one word per unit, compared with this launch's epoch (no memset per launch).  The number
             // of units is at most n + the grid's warps; the grid never exceeds 64 warps per SM.
@@ -1214,10 +1269,14 @@ int tp3_create(const tp3_params* params, int n_dev, const int* dev_ids, tp3_ctx*
         DeviceSlot s;
         s.dev = dev_ids ? dev_ids[i] : i;
         if (s.dev < 0 || s.dev >= count) return fail(TP3_E_NO_DEVICE, "device id out of range");
-        cudaDeviceProp prop;
-        if ((e = cudaGetDeviceProperties(&prop, s.dev)) != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
-        if (prop.major != 10) return fail(TP3_E_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
-        s.sm_count = prop.multiProcessorCount;
+        // (two attributes, not cudaGetDeviceProperties: that call alone was most of the 2.7 ms a context took to create,
+        // profiles/r02_default_run.txt)
+        int major = 0, sms = 0;
+        if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, s.dev)) != cudaSuccess ||
+            (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.dev)) != cudaSuccess)
+            return fail(TP3_E_CUDA, cudaGetErrorString(e));
+        if (major != 10) return fail(TP3_E_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+        s.sm_count = sms;
         if ((e = cudaSetDevice(s.dev)) != cudaSuccess) return fail(TP3_E_CUDA, cudaGetErrorString(e));
         if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
             return fail(TP3_E_CUDA, cudaGetErrorString(e));
@@ -1249,6 +1308,7 @@ void tp3_destroy(tp3_ctx* c) {
         if (s.stream) cudaStreamSynchronize(s.stream);  // nothing of this context is in flight when its buffers go
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_ranf_table);
+        cudaFree(s.d_batch_parts);
         cudaFree(s.d_xo_digit_polys);
         cudaFree(s.d_xo_lane_polys);
         cudaFree(s.d_xo_states);
@@ -1465,7 +1525,7 @@ static int simulate_batches_streamed(tp3_ctx* c, DeviceSlot& s, uint64_t first, 
 int tp3_simulate_batches(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
     if (!out) return TP3_E_INVALID;
     if (c && c->devs.size() == 1 && n >= 32768 && n <= 0x7fffffffull && last_len >= 1 && last_len <= TP3_EVENT_BATCH_SIZE &&
-        !(c->params.flags & TP3_FASTER_EVGEN) && c->opt_sched_dynamic && !c->hist_bins) {
+        !(c->params.flags & TP3_FASTER_EVGEN) && c->opt_sched_dynamic && !c->hist_bins && c->opt_batch_parts <= 1) {
         c->devs[0].last_n = 0;
         return simulate_batches_streamed(c, c->devs[0], first, n, last_len, out);
     }
@@ -1497,7 +1557,6 @@ int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_le
     }
     int rc = enqueue_merged(c, first, n, last_len);
     if (rc) return rc;
-    const bool in_kernel = !(c->params.flags & TP3_FASTER_EVGEN);
     std::vector<FoldState> parts(c->devs.size());
     for (size_t g = 0; g < c->devs.size(); ++g) {
         DeviceSlot& s = c->devs[g];
@@ -1511,7 +1570,7 @@ int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_le
         if (!s.last_n) continue;
         TP3_CUDA(c, cudaSetDevice(s.dev));
         TP3_CUDA(c, cudaStreamSynchronize(s.stream));
-        if (in_kernel && (parts[g].lock != 0 || parts[g].next_unit == 0)) {  // every unit was folded and the lock released
+        if (s.fold_in_kernel && (parts[g].lock != 0 || parts[g].next_unit == 0)) {  // every unit was folded and the lock released
             c->err = "ordered fold did not complete";
             return TP3_E_CUDA;
         }
@@ -1586,6 +1645,7 @@ int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
     else if (k == "grid_warps" && value >= 0 && value <= (1 << 20)) c->opt_grid_warps = value;
     else if (k == "sched_dynamic") c->opt_sched_dynamic = value != 0;
     else if (k == "ramp_units" && value >= 0 && value <= (1 << 20)) c->opt_ramp_units = value;
+    else if (k == "batch_parts" && (value == 0 || value == 1 || value == 2 || value == 5 || value == 10)) c->opt_batch_parts = value;
     else if (k == "f32_scalar") c->opt_f32_scalar = value != 0;
     else if (k == "fe_split" && (value == 0 || value == 1 || value == 32)) c->opt_fe_split = value;
     else if (k == "fe_host_scan") c->opt_fe_host_scan = value != 0;

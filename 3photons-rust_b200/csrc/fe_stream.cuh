@@ -508,21 +508,22 @@ template <class F, int HIST = 0> __global__ void __launch_bounds__(32, 16) fe_ph
     }
 }
 
-// Batch accumulator = its kFeParts part accumulators merged in part order, in the run's Float (resacc.rs:133-139).
-template <class F> __global__ void fe_combine_parts_kernel(const tp3_acc* __restrict__ parts, uint64_t n_batches, tp3_acc* __restrict__ out) {
+// Batch accumulator = its part accumulators merged in part order, in the run's Float (resacc.rs:133-139).
+template <class F>
+__global__ void fe_combine_parts_kernel(const tp3_acc* __restrict__ parts, uint64_t n_batches, tp3_acc* __restrict__ out, int n_parts = kFeParts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t b = i / 13;
     const int f = (int)(i % 13);
     if (b >= n_batches) return;
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(parts + b * kFeParts);
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(parts + b * n_parts);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + b);
     if (f == 0) {
         unsigned long long n = 0;
-        for (int k = 0; k < kFeParts; ++k) n += src[k * 13];
+        for (int k = 0; k < n_parts; ++k) n += src[k * 13];
         dst[0] = n;
     } else {
         F s = (F)__longlong_as_double((long long)src[f]);
-        for (int k = 1; k < kFeParts; ++k) s += (F)__longlong_as_double((long long)src[k * 13 + f]);
+        for (int k = 1; k < n_parts; ++k) s += (F)__longlong_as_double((long long)src[k * 13 + f]);
         dst[f] = (unsigned long long)__double_as_longlong((double)s);
     }
 }

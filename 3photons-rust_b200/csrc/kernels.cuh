@@ -80,6 +80,11 @@ struct SimArgs {
     uint64_t n_batches;        // batches in this launch
     uint32_t last_batch_len;   // events in the last batch of the launch
     uint32_t jump_seeding;     // TP3_FASTER_THREADING: batch b starts after b rng.jump()s
+    // A batch can be cut into `batch_parts` equal PARTS of `batch_events` events (sequential RANF stream only): the launch then
+    // runs over part indices -- first_batch, n_batches and `out` count parts, consecutive parts are consecutive in the stream
+    // exactly as consecutive batches are -- and a combine kernel adds the parts of a batch in part order (api.cu).
+    uint32_t batch_events;     // events per slot of the launch: TP3_EVENT_BATCH_SIZE / batch_parts
+    uint32_t batch_parts;      // 1: a slot is a batch
     // static schedule (see the head of this file)
     uint32_t n_warps;          // W: warps in the grid
     uint32_t unit_batches;     // consecutive batches per unit in the full rounds (the RANF stream simply continues inside a unit)
@@ -164,7 +169,7 @@ template <class F> struct WarpRng<F, RNG_RANF> {
             ranf_seed_warp(y, y + 64, (int32_t)((uint32_t)a.ranf_seed + 123456u * (uint32_t)batch), lane);
             s.init(&sm->ranf, y, 0, a.ranf_table, lane);
         } else {
-            s.init(&sm->ranf, a.ranf_base, (uint64_t)kDrawsPerEvent * kBatch * batch, a.ranf_table, lane);
+            s.init(&sm->ranf, a.ranf_base, (uint64_t)kDrawsPerEvent * a.batch_events * batch, a.ranf_table, lane);
         }
     }
     __device__ int iterations() const { return (n + 31) / 32; }
@@ -180,6 +185,12 @@ template <class F> struct WarpRng<F, RNG_RANF> {
     // the (possibly partial) last warp iteration instead of jumping again.
     __device__ bool next_batch(const SimArgs& a, int n_next, int lane) {
         if (a.jump_seeding) return false;
+        if (n_next == 0 || n == 0) {  // the empty trailing parts of a short last batch (batch_parts): no draw is read any more
+            n = 0;
+            return n_next == 0;
+        }
+        // (advance() needs the step to leave the first buffered round: true for whole batches, 192 draws into the last warp
+        // iteration, and for the part sizes api.cu allows: 5000, 2000 and 1000 events end 96, 192 and 96 draws into theirs)
         s.advance(kDrawsPerEvent * (n - 32 * (iterations() - 1)), lane);
         n = n_next;
         return true;
@@ -365,7 +376,11 @@ template <class F, class Q> __device__ __forceinline__ void queue_pop(Q queue, i
 
 // Number of events of batch `slot` of the launch.
 __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
-    return (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
+    if (a.batch_parts <= 1) return (slot + 1 == a.n_batches) ? (int)a.last_batch_len : kBatch;
+    if (slot + a.batch_parts < a.n_batches) return (int)a.batch_events;  // a part of a full batch
+    // the parts of the launch's last batch share its last_batch_len events, in order
+    const int before = (int)((slot + a.batch_parts - a.n_batches) * a.batch_events);
+    return max(0, min((int)a.batch_events, (int)a.last_batch_len - before));
 }
 
 // Batches [lo, hi) of the launch that make up unit u.

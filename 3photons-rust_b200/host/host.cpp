@@ -591,6 +591,9 @@ int tp3_run_stages(const char* valeurs_path, const char* out_dir, uint32_t flags
     const uint64_t nb = (cfg.num_events + TP3_EVENT_BATCH_SIZE - 1) / TP3_EVENT_BATCH_SIZE;
     const uint32_t last = (uint32_t)(cfg.num_events - (nb - 1) * TP3_EVENT_BATCH_SIZE);
     // (tp3_simulate_merged: the same left fold, done on the device while the batches are simulated)
+    // A run too small to give every resident warp a batch (the default 1e7 events are 1000 batches for 2368 warp slots) is cut
+    // into parts of batches, added in part order: this program issues one launch, so the choice is reproducible.
+    tp3_set_option(ctx, "batch_parts", 0);
     tp3_acc total;
     rc = tp3_simulate_merged(ctx, 0, nb, last, &total);
     if (rc) {

@@ -143,6 +143,12 @@ size_t tp3_kernel_arg_bytes(void);
  *   "grid_warps"       warps in the grid (0 = as many as the device holds at once)
  *   "sched_dynamic"    1 (default): one unit per warp, dispatched by the hardware; 0: static balanced schedule
  *   "ramp_units"       dynamic schedule: that many units of 1, 2, .., 8 batches at the head of the launch (0 = none, the default)
+ *   "batch_parts"      sequential RANF stream, default event generator: every batch is cut into that many equal parts (1 = whole
+ *                      batches, the default; 2, 5, 10; 0 = the largest of those for which the launch still fits one
+ *                      wave of resident warps), one warp each, and the parts of a batch are added in part order: a small run
+ *                      (the default 1e7 events are 1000 batches for 2368 warp slots) then fills the device.  Same events,
+ *                      same selected-event counts; the sums of a batch differ between settings by the order of additions,
+ *                      so a caller that compares sub-ranges bit for bit keeps one setting.  tp3_run uses 0.
  *   "f32_scalar"       f32: one event per lane instead of the packed two-events-per-lane kernel
  *   "fe_split"         faster-evgen: 1 = one thread per batch, 32 = one lane per 313 events, 0 = by launch size
  *   "fe_host_scan"     faster-evgen: batch start states from the reference's own method, the event-by-event

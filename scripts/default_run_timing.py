@@ -18,10 +18,13 @@ for i in range(4):
     print(f"run {i}: wall {1e3 * wall:8.2f} ms, reference-style timed region {1e3 * secs:8.2f} ms  |  " +
           "  ".join(f"{k} {1e3 * v:.2f} ms" for k, v in stages.items()))
 cfg = pkg.Configuration.parse(text, features)
-with pkg.Simulator(cfg) as sim:
-    for i in range(4):
-        t0 = time.perf_counter()
-        acc = sim.simulate_merged(0, 1000)
-        dt = time.perf_counter() - t0
-        print(f"tp3_simulate_merged(1000 batches) on a warm context: {1e3 * dt:.3f} ms -> {1e7 / dt:.3g} events/s")
+for parts in (1, 2, 5, 10, 0):
+    with pkg.Simulator(cfg) as sim:
+        sim.set_option("batch_parts", parts)
+        best = 1e30
+        for i in range(6):
+            t0 = time.perf_counter()
+            acc = sim.simulate_merged(0, 1000)
+            best = min(best, time.perf_counter() - t0)
+        print(f"tp3_simulate_merged(1000 batches) on a warm context, batch_parts = {parts}: {1e3 * best:.3f} ms -> {1e7 / best:.3g} events/s  (selected {acc.selected_events}, sigma sum {acc.sigma!r})")
 shutil.rmtree(d)

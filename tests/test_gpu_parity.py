@@ -240,6 +240,46 @@ def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, 
         assert_acc_close(got[b], want, REL_F64, what=f"batch {3 + b}")
 
 
+@pytest.mark.parametrize("features", ["", "f32", "no-photon-sorting"])
+@pytest.mark.parametrize("parts,last", [(2, 10000), (2, 5001), (5, 1234), (5, 7000), (10, 9999), (10, 1234), (0, 2001)])
+def test_batch_parts(tp3, valeurs_text, features, parts, last):
+    """`batch_parts`: every batch cut into equal parts, one warp each, added in part order (the default run's 1000 batches
+    then fill the device; tp3_run asks for 0 = auto).  The parts are plain positions of the sequential RANF stream, so the
+    events are the same: identical selected-event counts in every batch (a short last batch leaves its trailing parts
+    empty), sums equal up to the order of the additions; the merged result is the left fold of the per-batch results;
+    independent of the schedule; without effect where a part's start is not a plain stream position (xoshiro)."""
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    first, nb = 3, 7
+    with tp3.Simulator(cfg) as sim:
+        want = sim.simulate_batches(first, nb, last)
+    with tp3.Simulator(cfg) as sim:
+        sim.set_option("batch_parts", parts)
+        got = sim.simulate_batches(first, nb, last)
+        merged = sim.simulate_merged(first, nb, last)
+        sim.set_option("unit_batches", 3).set_option("grid_warps", 2).set_option("sched_dynamic", 0)
+        other = sim.simulate_batches(first, nb, last)
+    assert bytes(got) != bytes(want)  # (the parts really were used)
+    f32 = "f32" in features
+    for b, (g, w) in enumerate(zip(got, want)):
+        assert g.selected_events == w.selected_events, f"batch {first + b}"
+        if not f32:
+            assert_acc_close(g, w, 1e-12, what=f"batch {first + b}")
+        else:  # the non-cancelling sums, as in test_batches_match_oracle_f32
+            gf, wf = acc_fields(g), acc_fields(w)
+            for k in (0, 1, 2, 5, 6, 7, 10, 11):
+                assert abs(gf[k] - wf[k]) <= 1e-4 * abs(wf[k]), f"batch {first + b} field {k}: {gf[k]} vs {wf[k]}"
+    assert bytes(merged) == bytes(tp3.fold(got, cfg.flags))
+    assert bytes(other) == bytes(got)
+    with tp3.Simulator(cfg) as sim:
+        with pytest.raises(tp3.Tp3Error):
+            sim.set_option("batch_parts", 4)  # 2500 events end 48 draws into their last warp iteration: not a supported size
+    xo = tp3.Configuration.parse(valeurs_text, "standard-random")
+    with tp3.Simulator(xo) as sim:
+        plain = sim.simulate_batches(first, 3)
+        sim.set_option("batch_parts", parts)
+        assert bytes(sim.simulate_batches(first, 3)) == bytes(plain)
+
+
 @pytest.mark.parametrize("features", ["f32", "standard-random,f32"])
 def test_batches_match_oracle_f32(sims, oracle, valeurs_text, features):
     nb = 12

@@ -167,6 +167,7 @@ def lib() -> C.CDLL:
         "tp3_fetch": (C.c_int, [vp, P(Acc), u64]),
         "tp3_simulate_merged": (C.c_int, [vp, u64, u64, u32, P(Acc)]),
         "tp3_simulate_merged_device": (C.c_int, [vp, u64, u64, u32, vp]),
+        "tp3_simulate_batches_merged": (C.c_int, [vp, u64, u64, u32, P(Acc), P(Acc)]),
         "tp3_fold_batches": (C.c_int, [P(Acc), u64, u32, P(Acc)]),
         "tp3_fe_tile_device": (C.c_int, [vp, u64, u64, u64, vp, P(u64)]),
         "tp3_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
@@ -206,7 +207,7 @@ ABI_SYMBOLS = [
     "tp3_rng_dump", "tp3_events_dump", "tp3_peak_probe", "tp3_fastmath_probe", "tp3_config_parse", "tp3_params_from_config", "tp3_merge",
     "tp3_finalize", "tp3_format_res_data", "tp3_format_stdout", "tp3_run", "tp3_host_ranf_round",
     "tp3_host_xoshiro_state", "tp3_histograms_enable", "tp3_histograms_reset", "tp3_histograms_fetch",
-    "tp3_simulate_merged_device", "tp3_fold_batches", "tp3_set_option", "tp3_get_stat", "tp3_kernel_arg_bytes", "tp3_run_stages",
+    "tp3_simulate_merged_device", "tp3_simulate_batches_merged", "tp3_fold_batches", "tp3_set_option", "tp3_get_stat", "tp3_kernel_arg_bytes", "tp3_run_stages",
     "tp3_fe_tile_device",
 ]
 
@@ -373,6 +374,13 @@ class Simulator:
         out = Acc()
         self._check(lib().tp3_simulate_merged(self._h, first_batch, n_batches, last_batch_len, C.byref(out)))
         return out
+
+    def simulate_batches_merged(self, first_batch: int, n_batches: int, last_batch_len: int = EVENT_BATCH_SIZE):
+        """tp3_simulate_batches_merged: (one accumulator per batch on the host, their left fold in batch order done on the device)."""
+        out = (Acc * n_batches)()
+        merged = Acc()
+        self._check(lib().tp3_simulate_batches_merged(self._h, first_batch, n_batches, last_batch_len, out, C.byref(merged)))
+        return out, merged
 
     def simulate_merged_device(self, first_batch: int, n_batches: int, last_batch_len: int, device_ptr: int):
         """Asynchronous: the merged accumulator as 13 doubles in the caller's device buffer (one ncclReduce operand)."""

@@ -1522,10 +1522,15 @@ static int simulate_batches_streamed(tp3_ctx* c, DeviceSlot& s, uint64_t first, 
     return TP3_OK;
 }
 
+// Long single-device launches of the fused kernel copy their accumulators to the host while the kernel runs.
+static bool streamed_per_batch(const tp3_ctx* c, uint64_t n, uint32_t last_len) {
+    return c && c->devs.size() == 1 && n >= 32768 && n <= 0x7fffffffull && last_len >= 1 && last_len <= TP3_EVENT_BATCH_SIZE &&
+           !(c->params.flags & TP3_FASTER_EVGEN) && c->opt_sched_dynamic && !c->hist_bins && c->opt_batch_parts <= 1;
+}
+
 int tp3_simulate_batches(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
     if (!out) return TP3_E_INVALID;
-    if (c && c->devs.size() == 1 && n >= 32768 && n <= 0x7fffffffull && last_len >= 1 && last_len <= TP3_EVENT_BATCH_SIZE &&
-        !(c->params.flags & TP3_FASTER_EVGEN) && c->opt_sched_dynamic && !c->hist_bins && c->opt_batch_parts <= 1) {
+    if (streamed_per_batch(c, n, last_len)) {
         c->devs[0].last_n = 0;
         return simulate_batches_streamed(c, c->devs[0], first, n, last_len, out);
     }
@@ -1550,13 +1555,8 @@ static int enqueue_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_
     return TP3_OK;
 }
 
-int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
-    if (!c || !out || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE) {
-        if (c) c->err = "tp3_simulate_merged: bad range";
-        return TP3_E_INVALID;
-    }
-    int rc = enqueue_merged(c, first, n, last_len);
-    if (rc) return rc;
+// Waits for the launches of enqueue_merged / simulate_batches_streamed and collects the folded accumulator of every device.
+static int collect_merged(tp3_ctx* c, tp3_acc* out) {
     std::vector<FoldState> parts(c->devs.size());
     for (size_t g = 0; g < c->devs.size(); ++g) {
         DeviceSlot& s = c->devs[g];
@@ -1583,6 +1583,35 @@ int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_le
         have = true;
     }
     return TP3_OK;
+}
+
+int tp3_simulate_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out) {
+    if (!c || !out || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE) {
+        if (c) c->err = "tp3_simulate_merged: bad range";
+        return TP3_E_INVALID;
+    }
+    int rc = enqueue_merged(c, first, n, last_len);
+    if (rc) return rc;
+    return collect_merged(c, out);
+}
+
+int tp3_simulate_batches_merged(tp3_ctx* c, uint64_t first, uint64_t n, uint32_t last_len, tp3_acc* out, tp3_acc* merged) {
+    if (!c || !out || !merged || n == 0 || last_len == 0 || last_len > TP3_EVENT_BATCH_SIZE) {
+        if (c) c->err = "tp3_simulate_batches_merged: bad range";
+        return TP3_E_INVALID;
+    }
+    if (streamed_per_batch(c, n, last_len)) {
+        // the accumulators are copied while the kernel runs, and that launch already carries the ordered fold
+        DeviceSlot& s = c->devs[0];
+        s.last_n = 0;
+        int rc = simulate_batches_streamed(c, s, first, n, last_len, out);
+        if (rc) return rc;
+        return collect_merged(c, merged);
+    }
+    int rc = enqueue_merged(c, first, n, last_len);
+    if (rc) return rc;
+    if ((rc = tp3_fetch(c, out, n))) return rc;
+    return collect_merged(c, merged);
 }
 
 // 13 doubles for one ncclReduce(sum): the event count is exact as a double below 2^53.

@@ -674,7 +674,15 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
     using Word = typename RawWord<F, RNG>::type;
     __shared__ WarpSmem<F, kQueue2, 3> smw[kWarps];
     const int warp = kWarps == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
-    float2(*queue)[kQueue2] = smw[warp].queue;
+    // Survivor queue, component-major: row 4 k + c holds component c (X, Y, Z, E) of photon k.  Queue slot s lives at word
+    // (s & 64) | (s & 31) << 1 | (s >> 5 & 1) of its row, so that the two events a lane takes when 64 survivors are popped
+    // (slots q_head + lane and q_head + 32 + lane, q_head = 0 or 64) are ADJACENT words: one 64-bit load per component
+    // delivers the packed pair as the arithmetic wants it (event a in the low half, event b in the high half), and a
+    // survivor is pushed with 32-bit stores straight from the half it sits in.  (Photon-major float2 pairs cost 81
+    // register moves per pop to transpose, profiles/r02_f32x2_xoshiro_kernel.txt.)
+    float(*qf)[kQueue2] = reinterpret_cast<float(*)[kQueue2]>(&smw[warp].queue[0][0]);
+    static_assert(sizeof(smw[0].queue) == 12 * kQueue2 * sizeof(float) && kQueue2 == 128, "12 component rows of 128 slots");
+    auto qword = [](int s) { return (s & 64) | ((s & 31) << 1) | ((s >> 5) & 1); };
     const FastMath fm{nullptr, nullptr};  // the f32 elementary functions are SFU instructions, no tables
 
     WarpRng<F, RNG> rng;
@@ -709,13 +717,11 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
             variance += w * w;
             selected += (uint32_t)valid.x + (uint32_t)valid.y;
         };
-        auto pop = [&](int slot_a, int slot_b, f2 (&e)[3][4]) {
+        auto pop = [&](int head, f2 (&e)[3][4]) {  // slots head + lane (low halves) and head + 32 + lane (high halves)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float2 xa = queue[2 * k][slot_a], za = queue[2 * k + 1][slot_a];
-                const float2 xb = queue[2 * k][slot_b], zb = queue[2 * k + 1][slot_b];
-                e[k][0] = f2(xa.x, xb.x); e[k][1] = f2(xa.y, xb.y); e[k][2] = f2(za.x, zb.x); e[k][3] = f2(za.y, zb.y);
-            }
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) e[k][c].v = *reinterpret_cast<const unsigned long long*>(&qf[4 * k + c][head + 2 * lane]);
         };
 
         int q_head = 0, q_count = 0;  // survivor queue (warp-uniform)
@@ -748,27 +754,25 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
             const unsigned mask_a = __ballot_sync(0xffffffffu, keep_a), mask_b = __ballot_sync(0xffffffffu, keep_b);
             const unsigned below = (1u << lane) - 1u;
             if (keep_a) {
-                const int s = (q_head + q_count + __popc(mask_a & below)) & (kQueue2 - 1);
+                const int w = qword((q_head + q_count + __popc(mask_a & below)) & (kQueue2 - 1));
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    queue[2 * k][s] = make_float2(p[k][0].lo(), p[k][1].lo());
-                    queue[2 * k + 1][s] = make_float2(p[k][2].lo(), p[k][3].lo());
-                }
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) qf[4 * k + c][w] = p[k][c].lo();
             }
             q_count += __popc(mask_a);
             if (keep_b) {
-                const int s = (q_head + q_count + __popc(mask_b & below)) & (kQueue2 - 1);
+                const int w = qword((q_head + q_count + __popc(mask_b & below)) & (kQueue2 - 1));
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    queue[2 * k][s] = make_float2(p[k][0].hi(), p[k][1].hi());
-                    queue[2 * k + 1][s] = make_float2(p[k][2].hi(), p[k][3].hi());
-                }
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) qf[4 * k + c][w] = p[k][c].hi();
             }
             q_count += __popc(mask_b);
             __syncwarp();
             if (q_count >= 64) {
                 f2 e[3][4];
-                pop((q_head + lane) & (kQueue2 - 1), (q_head + 32 + lane) & (kQueue2 - 1), e);
+                pop(q_head, e);
                 __syncwarp();
                 q_head = (q_head + 64) & (kQueue2 - 1);
                 q_count -= 64;
@@ -777,7 +781,7 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
         }
         if (q_count > 0) {  // drain (warp-uniform condition; fewer than 64 events)
             f2 e[3][4];
-            pop((q_head + lane) & (kQueue2 - 1), (q_head + 32 + lane) & (kQueue2 - 1), e);
+            pop(q_head, e);
             // lanes without an event still hold finite momenta of earlier events or zeros: give them a harmless event
             const m2 valid{lane < q_count, 32 + lane < q_count};
             const f2 one(1.0f), zero(0.0f);

@@ -19,8 +19,9 @@ A "step" is one pass of the fused kernel (with its in-kernel ordered fold) over 
   e2e   : the same metric through the call INTEGRATION.md tells a maintainer to bind: tp3_simulate_merged
           into a HOST accumulator (N = 1), or tp3_simulate_merged_device + ONE ncclReduce(sum) of the 13
           doubles to rank 0 + a 104-byte device->host copy (N > 1), then finalize() on the host.
-  e2e_per_batch : the per-batch form of the boundary (tp3_simulate_batches into a host array of one
-          accumulator per batch + the host left fold tp3_fold_batches + finalize).
+  e2e_per_batch : the per-batch form of the boundary: one accumulator per batch into a host array AND the
+          merged result, finalize()d -- value through tp3_simulate_batches_merged (the ordered fold comes from
+          the same launch), host_fold_value through tp3_simulate_batches + the host left fold tp3_fold_batches.
   roofline: the path is FP64-pipe bound (no tensor cores, ~0.01 B/event of HBM traffic).  `achieved` /
           `frac` follow SURVEY.md section 8d: algorithmic FP64 TFLOP/s (833 flop per generated event as
           the reference writes them) over the DFMA peak measured live on this GPU by tp3_peak_probe
@@ -307,11 +308,15 @@ def main():
         # ---- the per-batch form of the boundary: one accumulator per batch into a host array + host left fold ----
         host = (pkg.Acc * cnt)()
 
-        def per_batch_step():
+        def per_batch_step(host_fold):
             if fe_tiles:  # per-batch accumulators by absolute batch index need the whole prefix of the stream: not sharded
                 return e2e_step()
-            sim._check(pkg.lib().tp3_simulate_batches(sim._h, lo, cnt, my_last, host))
-            mine = pkg.fold(host, cfg.flags)
+            if host_fold:  # the north star's wording: one accumulator per batch to the host, the host merges in the reference's order
+                sim._check(pkg.lib().tp3_simulate_batches(sim._h, lo, cnt, my_last, host))
+                mine = pkg.fold(host, cfg.flags)
+            else:          # the same accumulators on the host, their ordered fold from the same launch (tp3_simulate_batches_merged)
+                mine = pkg.Acc()
+                sim._check(pkg.lib().tp3_simulate_batches_merged(sim._h, lo, cnt, my_last, host, ctypes.byref(mine)))
             if world == 1:
                 return pkg.finalize(cfg, mine)
             t = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).cuda()
@@ -322,14 +327,15 @@ def main():
             accs = [pkg.Acc.from_buffer_copy(p.cpu().numpy().tobytes()) for p in parts]
             return pkg.finalize(cfg, pkg.fold(accs, cfg.flags))
 
-        per_batch_step()
-        barrier()
         n_pb = max(1, min(steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(n_pb):
-            fin_pb = per_batch_step()
-        barrier()
-        res["e2e_per_batch"] = n_events * n_pb / over_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX)
+        for host_fold, key in ((False, "e2e_per_batch"), (True, "e2e_per_batch_host_fold")):
+            per_batch_step(host_fold)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_pb):
+                fin_pb = per_batch_step(host_fold)
+            barrier()
+            res[key] = n_events * n_pb / over_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX)
         res["fin_pb"] = fin_pb
         res["d2h_per_batch"] = nb * ctypes.sizeof(pkg.Acc)
         return res
@@ -374,7 +380,10 @@ def main():
                     "note": "tp3_simulate_merged into a host tp3_acc + finalize() (N = 1); tp3_simulate_merged_device + one ncclReduce(sum) of 13 "
                             "doubles + 104-byte D2H on rank 0 + finalize() (N > 1). The only host->device payload is the kernel argument block."},
             "e2e_per_batch": {"value": main_res["e2e_per_batch"], "unit": "events/s", "d2h_bytes_per_step": main_res["d2h_per_batch"],
-                              "note": "tp3_simulate_batches into a host array (one 104-byte accumulator per batch) + tp3_fold_batches on the host + finalize()"},
+                              "host_fold_value": main_res["e2e_per_batch_host_fold"],
+                              "note": "value: tp3_simulate_batches_merged = one 104-byte accumulator per batch into a host array (copied while the kernel "
+                                      "runs) + their ordered fold from the same launch + finalize(); host_fold_value: tp3_simulate_batches into the "
+                                      "host array + tp3_fold_batches on the host + finalize()"},
             "gpu_launches": main_res["launches"],
             "roofline": {"bound": "fp64" if not f32 else "fp32", "achieved": achieved, "peak": peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": ncu_traffic,

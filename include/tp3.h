@@ -107,6 +107,12 @@ int  tp3_fetch(tp3_ctx* ctx, tp3_acc* out_per_batch, uint64_t n_batches);
  * FastAccumulator, multi_threading.rs:130-190, makes the same trade). */
 int  tp3_simulate_merged(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches,
                          uint32_t last_batch_len, tp3_acc* out_merged);
+/* Both at once: one accumulator per batch in the caller's host array (copied while the kernel runs when the range
+ * is long) AND the left fold of those accumulators in batch order, done by the same launch on the device -- the host does
+ * not need to fold (sequential.rs:24-36, multi_threading.rs:107-126).  On one device *out_merged equals
+ * tp3_fold_batches(out_per_batch) bit for bit; with several devices see tp3_simulate_merged. */
+int  tp3_simulate_batches_merged(tp3_ctx* ctx, uint64_t first_batch, uint64_t n_batches, uint32_t last_batch_len,
+                                 tp3_acc* out_per_batch, tp3_acc* out_merged);
 /* Asynchronous form for multi-GPU runs (single-device contexts): the merged accumulator is left in
  * the caller's DEVICE buffer as 13 doubles {selected_events, spm2[5], vars[5], sigma, variance}
  * (the count is exact as a double below 2^53), i.e. the operand of one ncclReduce(sum) over the

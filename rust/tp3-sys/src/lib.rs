@@ -108,6 +108,8 @@ extern "C" {
     pub fn tp3_fetch(ctx: *mut tp3_ctx, out_per_batch: *mut tp3_acc, n_batches: u64) -> c_int;
     pub fn tp3_simulate_merged(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
                                out_merged: *mut tp3_acc) -> c_int;
+    pub fn tp3_simulate_batches_merged(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
+                                       out_per_batch: *mut tp3_acc, out_merged: *mut tp3_acc) -> c_int;
     pub fn tp3_simulate_merged_device(ctx: *mut tp3_ctx, first_batch: u64, n_batches: u64, last_batch_len: u32,
                                       device_out13: *mut f64) -> c_int;
     pub fn tp3_fe_tile_device(ctx: *mut tp3_ctx, first_round: u64, n_rounds: u64, max_events: u64, device_out13: *mut f64,

@@ -59,6 +59,28 @@ pub fn simulate_run_merged(inputs: &KernelInputs, n_gpus: i32) -> Result<BatchSu
     Ok(out)
 }
 
+/// Per-batch sums in batch order AND their ordered fold from the same launch (tp3_simulate_batches_merged): nothing left to fold
+/// on the host (sequential.rs:24-36).
+pub fn simulate_all_batches_merged(inputs: &KernelInputs, n_gpus: i32) -> Result<(Vec<BatchSums>, BatchSums), String> {
+    let params = kernel_params(inputs);
+    let batch = TP3_EVENT_BATCH_SIZE as usize;
+    let n_batches = (inputs.num_events + batch - 1) / batch;       // multi_threading.rs:25
+    let last_len = inputs.num_events - (n_batches - 1) * batch;    // multi_threading.rs:47
+    let mut ctx = std::ptr::null_mut();
+    let mut out = vec![BatchSums::default(); n_batches];
+    let mut merged = BatchSums::default();
+    unsafe {
+        if tp3_create(&params, n_gpus, std::ptr::null(), &mut ctx) != TP3_OK {
+            return Err(CStr::from_ptr(tp3_last_error(std::ptr::null())).to_string_lossy().into_owned());
+        }
+        let rc = tp3_simulate_batches_merged(ctx, 0, n_batches as u64, last_len as u32, out.as_mut_ptr(), &mut merged);
+        let err = if rc != TP3_OK { Some(CStr::from_ptr(tp3_last_error(ctx)).to_string_lossy().into_owned()) } else { None };
+        tp3_destroy(ctx);
+        if let Some(e) = err { return Err(e); }
+    }
+    Ok((out, merged))
+}
+
 /// Simulates every batch of the run on `n_gpus` devices and returns the per-batch sums in batch order.
 pub fn simulate_all_batches(inputs: &KernelInputs, n_gpus: i32) -> Result<Vec<BatchSums>, String> {
     let params = kernel_params(inputs);

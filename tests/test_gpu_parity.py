@@ -379,6 +379,23 @@ def test_streamed_per_batch_copy(sims, tp3):
         for i in range(len(small)):
             assert bytes(small[i]) == bytes(arr[lo - base + i]), (lo, i)
     assert bytes(sim.simulate_merged(n, n, 4321)) == bytes(tp3.fold(b))
+    # tp3_simulate_batches_merged: the same streamed accumulators AND their ordered fold from the same launch
+    both, merged = sim.simulate_batches_merged(n, n, 4321)
+    assert bytes(both) == bytes(b)
+    assert bytes(merged) == bytes(tp3.fold(b))
+
+
+@pytest.mark.parametrize("features", ["", "f32", "standard-random", "faster-evgen", "multi-threading,faster-threading"])
+def test_batches_and_merged_in_one_call(sims, tp3, features):
+    """tp3_simulate_batches_merged on a short range (no streaming): per-batch accumulators as tp3_simulate_batches gives them,
+    merged accumulator = their left fold in batch order, bit for bit, for every generator and seeding."""
+    sim = sims(features)
+    want = sim.simulate_batches(4, 23, 4321)
+    both, merged = sim.simulate_batches_merged(4, 23, 4321)
+    assert bytes(both) == bytes(want)
+    assert bytes(merged) == bytes(tp3.fold(want, sim.cfg.flags))
+    with pytest.raises(tp3.Tp3Error):
+        sim.simulate_batches_merged(0, 0)
 
 
 def test_bad_arguments_are_reported(sims, tp3):

@@ -47,10 +47,17 @@ __device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
 // Fast-path math: hand-written FP64 (fastmath.cuh). The f32 fast path goes straight to the SFU
 // approximations (MUFU.LG2 / SIN / COS / RCP / RSQ, 2-3 ulp): the stated f32 bounds are three
 // orders of magnitude looser than that, and the f32 literal kernel keeps the IEEE libdevice functions.
+// (The .ftz forms are ONE MUFU instruction each; without the modifier the compiler wraps every call in a rescaling of
+// subnormal arguments -- FSETP, FMUL by 2^24, FSEL, the MUFU, an FMUL back -- that no argument here can need: the reciprocals
+// are taken of E + Z > MIN_POSITIVE, of norms and of m + E, the logarithm of e + MIN_POSITIVE, the square roots of x + 1e-30.
+// For normal arguments and results both forms return the same bits.)
+__device__ __forceinline__ float mufu_rcp_f(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rsqrt_f(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2_f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ double rcp_t(double x) { return fast_rcp(x); }
-__device__ __forceinline__ float rcp_t(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float rcp_t(float x) { return mufu_rcp_f(x); }
 __device__ __forceinline__ double neg_log_t(double x, const FastMath sm) { return fast_neg_log(x, sm); }
-__device__ __forceinline__ float neg_log_t(float x, const FastMath) { return -__logf(x); }
+__device__ __forceinline__ float neg_log_t(float x, const FastMath) { return -(mufu_lg2_f(x) * 0.693147182f); }  // __logf, one MUFU
 // The azimuth uniform arrives pre-scaled by an exact power of two: 256 u in f64 (table + rotation), 4 u in f32
 // (quarter turns for the SFU path).
 template <class F> struct PhiScale;
@@ -68,10 +75,10 @@ __device__ __forceinline__ void sincos_scaled_t(float t, const FastMath, float* 
     *c = __int_as_float(__float_as_int(c0) ^ (int)((unsigned)((q + 1) & 2) << 30));
 }
 __device__ __forceinline__ double sqrt_pos_t(double x) { return fast_sqrt(x); }
-__device__ __forceinline__ float sqrt_pos_t(float x) { return x * rsqrtf(x + 1e-30f); }
+__device__ __forceinline__ float sqrt_pos_t(float x) { return x * mufu_rsqrt_f(x + 1e-30f); }
 __device__ __forceinline__ void sqrt_rsqrt_t(double x, double* s, double* rs) { fast_sqrt_rsqrt(x, *s, *rs); }
 __device__ __forceinline__ void sqrt_rsqrt_t(float x, float* s, float* rs) {
-    *rs = rsqrtf(x);
+    *rs = mufu_rsqrt_f(x);
     *s = x * *rs;
 }
 

@@ -667,6 +667,18 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
 // matrix elements in packed FP32 arithmetic.
 constexpr int kQueue2 = 128;  // < 64 pending + <= 64 new survivors
 
+// The uniforms of the two events of a lane, scaled TOGETHER (one packed multiply for two raw words; xoshiro: the azimuth's
+// factor 4 is part of the power of two).  Same bits as WarpRng<float, RNG>::uniform on each half: every step is either exact or
+// the same single rounding.
+template <int RNG> __device__ __forceinline__ f2 uniform_x2(uint32_t a, uint32_t b, bool phi);
+template <> __device__ __forceinline__ f2 uniform_x2<RNG_XOSHIRO>(uint32_t a, uint32_t b, bool phi) {
+    return f2((float)(a >> 8), (float)(b >> 8)) * f2(phi ? 1.0f / 4194304.0f : 1.0f / 16777216.0f);
+}
+template <> __device__ __forceinline__ f2 uniform_x2<RNG_RANF>(uint32_t a, uint32_t b, bool phi) {
+    const f2 u = f2((float)(int)a, (float)(int)b) * f2(1e-9f);
+    return phi ? u * f2(4.0f) : u;
+}
+
 template <int RNG>
 __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simulate_kernel_x2(const SimArgs a, const PhysParams<f2> P) {
     constexpr int kWarps = x2_warps(RNG);  // this kernel's CTA shape
@@ -744,7 +756,7 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
             RngTick<F, RNG> tick{rng, lane, more};
             f2 u[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) u[j] = f2(WarpRng<F, RNG>::uniform(w0[j], (j & 3) == 1, P.fc), WarpRng<F, RNG>::uniform(w1[j], (j & 3) == 1, P.fc));
+            for (int j = 0; j < 12; ++j) u[j] = uniform_x2<RNG>(w0[j], w1[j], (j & 3) == 1);
             f2 p[3][4];
             gen_event<f2, false, false>(u, P.e_total, fm, p, tick);
             const m2 ok = keep_event<f2, false, false>(p, P);
@@ -909,7 +921,7 @@ __global__ void __launch_bounds__(32) dump_kernel_x2(const SimArgs a, const Phys
         }
         f2 u[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) u[j] = f2(WarpRng<F, RNG>::uniform(w0[j], (j & 3) == 1, P.fc), WarpRng<F, RNG>::uniform(w1[j], (j & 3) == 1, P.fc));
+        for (int j = 0; j < 12; ++j) u[j] = uniform_x2<RNG>(w0[j], w1[j], (j & 3) == 1);
         f2 p[3][4];
         NoTick no_tick;
         gen_event<f2, false, false>(u, P.e_total, fm, p, no_tick);

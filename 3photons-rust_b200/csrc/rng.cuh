@@ -289,17 +289,28 @@ __device__ inline void ranf_seed_warp(uint32_t* y /*smem 55*/, uint32_t* tmp /*s
 }
 
 // --------------------------------------------------------------------------- xoshiro
+// One step of xoshiro (rand_xoshiro 0.6.0): s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = rotl(s3).  Written with every
+// new word as a three-input XOR of OLD words (one LOP3 each instead of a chain of two-input ones: 4 instead of 5 logic
+// instructions per 32-bit word and step, and no dependency between them).
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t xor3(uint64_t a, uint64_t b, uint64_t c) {
+    return (uint64_t)xor3((uint32_t)(a >> 32), (uint32_t)(b >> 32), (uint32_t)(c >> 32)) << 32 | xor3((uint32_t)a, (uint32_t)b, (uint32_t)c);
+}
+
 struct Xoshiro256Lane {
     uint64_t s0, s1, s2, s3;
     __device__ __forceinline__ uint64_t next() {
         const uint64_t res = s0 + s3;
         const uint64_t t = s1 << 17;
-        s2 ^= s0;
-        s3 ^= s1;
-        s1 ^= s2;
-        s0 ^= s3;
-        s2 ^= t;
-        s3 = (s3 << 45) | (s3 >> 19);
+        const uint64_t n1 = xor3(s1, s2, s0), n0 = xor3(s0, s3, s1), n2 = xor3(s2, s0, t), x3 = s3 ^ s1;
+        s0 = n0;
+        s1 = n1;
+        s2 = n2;
+        s3 = (x3 << 45) | (x3 >> 19);
         return res;
     }
     // s <- sum over set bits j of poly of (state advanced j steps); poly = 4 x u64
@@ -329,12 +340,11 @@ struct Xoshiro128Lane {
     __device__ __forceinline__ uint32_t next() {
         const uint32_t res = s0 + s3;
         const uint32_t t = s1 << 9;
-        s2 ^= s0;
-        s3 ^= s1;
-        s1 ^= s2;
-        s0 ^= s3;
-        s2 ^= t;
-        s3 = (s3 << 11) | (s3 >> 21);
+        const uint32_t n1 = xor3(s1, s2, s0), n0 = xor3(s0, s3, s1), n2 = xor3(s2, s0, t), x3 = s3 ^ s1;
+        s0 = n0;
+        s1 = n1;
+        s2 = n2;
+        s3 = __funnelshift_l(x3, x3, 11);
         return res;
     }
     __device__ void apply(const uint64_t* __restrict__ poly /*2 x u64*/) {

@@ -88,10 +88,16 @@ __device__ __forceinline__ void sqrt_rsqrt_t(f2 x, f2* s, f2* rs) {
     *s = f2(s0, s1);
     *rs = f2(r0, r1);
 }
-__device__ __forceinline__ void sincos_scaled_t(f2 t, const FastMath fm, f2* s, f2* c) {
+__device__ __forceinline__ void sincos_scaled_t(f2 t, const FastMath, f2* s, f2* c) {
+    // the quadrant split of both halves in packed arithmetic (see the scalar form in physics.cuh: same operations, same bits);
+    // the inline-PTX operators are opaque to the compiler, so (t + M) - M is not simplified
+    const f2 magic(kRintMagic);
+    const f2 tm = t + magic;
+    const f2 qf = tm - magic;
+    const f2 x = (t - qf) * f2(1.57079632679489661923f);
     float s0, c0, s1, c1;
-    sincos_scaled_t(t.lo(), fm, &s0, &c0);
-    sincos_scaled_t(t.hi(), fm, &s1, &c1);
+    sincos_quadrant(x.lo(), __float_as_int(tm.lo()), &s0, &c0);
+    sincos_quadrant(x.hi(), __float_as_int(tm.hi()), &s1, &c1);
     *s = f2(s0, s1);
     *c = f2(c0, c1);
 }

@@ -64,15 +64,23 @@ template <class F> struct PhiScale;
 template <> struct PhiScale<double> { static constexpr double value = 256.0; };
 template <> struct PhiScale<float> { static constexpr float value = 4.0f; };
 __device__ __forceinline__ void sincos_scaled_t(double t, const FastMath fm, double* s, double* c) { fast_sincos_256(t, fm, *s, *c); }
-__device__ __forceinline__ void sincos_scaled_t(float t, const FastMath, float* s, float* c) {
-    const float qf = rintf(t);
-    const int q = __float2int_rn(t);
-    const float x = (t - qf) * 1.57079632679489661923f;  // |x| <= pi/4: the SFU's most accurate range
+// sin, cos of t quarter turns, 0 <= t <= 4, on the SFU.  q = rint(t) comes from the float adder: t + 1.5 * 2^23 holds rint(t) (ties to
+// even, like rintf) in its low mantissa bits and (t + M) - M is that integer as a float -- two FADDs instead of FRND + F2I on the
+// XU pipe, which the 14 MUFU calls of an event already keep busy.  The remainder |x| <= pi/4 is the SFU's most accurate range.
+// (A/B, profiles/r02_f32_sincos_ab.txt: the full angle in ONE sin / cos call each is 7 % faster for the whole kernel and flips 5
+// instead of 1 of the 7 082 165 selected events of the golden run: not taken.)
+constexpr float kRintMagic = 12582912.0f;
+__device__ __forceinline__ void sincos_quadrant(float x, int q, float* s, float* c) {
     const float ps = __sinf(x), pc = __cosf(x);
     const bool swap = q & 1;
     const float s0 = swap ? pc : ps, c0 = swap ? ps : pc;
     *s = __int_as_float(__float_as_int(s0) ^ (int)((unsigned)(q & 2) << 30));
     *c = __int_as_float(__float_as_int(c0) ^ (int)((unsigned)((q + 1) & 2) << 30));
+}
+__device__ __forceinline__ void sincos_scaled_t(float t, const FastMath, float* s, float* c) {
+    const float tm = __fadd_rn(t, kRintMagic);
+    const float qf = __fadd_rn(tm, -kRintMagic);
+    sincos_quadrant((t - qf) * 1.57079632679489661923f, __float_as_int(tm), s, c);
 }
 __device__ __forceinline__ double sqrt_pos_t(double x) { return fast_sqrt(x); }
 __device__ __forceinline__ float sqrt_pos_t(float x) { return x * mufu_rsqrt_f(x + 1e-30f); }

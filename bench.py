@@ -123,19 +123,27 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 3.0:  # until nvidia-smi delivers (outside the timed region)
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """The timed region starts now: only samples taken from here on count (nvidia-smi itself needs ~0.5 s to deliver
+        its first sample, so the sampler is started before the warm-up steps)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
-        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        rows = [r for t, r in self.rows if t >= getattr(self, "t_mark", 0.0) and len(r) >= 7 and r[0].isdigit()]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(int(r[0]) for r in rows)
@@ -254,14 +262,15 @@ def main():
             sim.simulate_merged_device(lo, cnt, my_last, out13.data_ptr())
 
         # ---- device-resident timing ("value") ----
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(warmup):
             step_device()
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         launches0 = sim.launch_count
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        sampler.mark()
         ev0.record(stream)
         for _ in range(steps):
             step_device()

@@ -349,7 +349,7 @@ void build_xoshiro_tables(tp3_ctx* c) {
 // ---- faster-evgen: the scheduler's pre-advance of the master generator (evgen.rs:257-267) -------------
 // The reference's own method, kept on the host as the CROSS-CHECK of the GPU scans (fe_scan.cuh for RANF,
 // fe_scan_xo.cuh for xoshiro), which supply the start states in every run: this code is reached only with the test
-// hook TP3_FE_HOST_SCAN set.  It is what the reference's scheduler thread does between spawning batch tasks
+// option `fe_host_scan` set.  It is what the reference's scheduler thread does between spawning batch tasks
 // (multi_threading.rs:59-64); the accept / re-roll test is evaluated exactly as the reference does (no FMA, run's Float).
 template <class F> struct FeHostRanf {
     uint32_t* n;  // numbers[0..55]

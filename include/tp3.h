@@ -160,10 +160,17 @@ size_t tp3_kernel_arg_bytes(void);
  *   "fe_host_scan"     faster-evgen: batch start states from the reference's own method, the event-by-event
  *                      walk of the master generator on the host (evgen.rs:257-267), instead of the GPU scans:
  *                      the cross-check of those scans
+ *   "fe_legacy"        faster-evgen on the sequential RANF stream: 1 = the round-1 pipeline (scan over transition maps +
+ *                      batch kernel with private generators) instead of the stream pipeline (walk -> records -> physics)
+ *   "fe_pass_segments" stream pipeline: segments (= lanes of the walk) per pass (0 = one full wave of the device)
+ *   "fe_seg_rounds"    stream pipeline: RANF rounds per segment (0 = 64 .. 512 by run size)
+ *   "fe_warm"          stream pipeline: warm-up rounds before a segment (0 = 24); small values force the redo path
+ *   "fe_serial"        stream pipeline: 1 = passes one after the other (the walk of pass k + 1 not next to the physics of pass k)
  *   "fe_xo_seg_units"  faster-evgen + xoshiro scan: segment length in units of 2048 outputs (0 = by launch size)
  *   "fe_timing"        print the scan phases of every call to stderr */
 int  tp3_set_option(tp3_ctx* ctx, const char* name, int64_t value);
-/* "fe_xo_pass_b": how many times pass B of the last xoshiro faster-evgen scan ran. */
+/* "fe_xo_pass_b": how many times pass B of the last xoshiro faster-evgen scan ran; "fe_passes", "fe_redone": passes of the
+ * last stream-pipeline call and segments it had to redo. */
 int  tp3_get_stat(tp3_ctx* ctx, const char* name, int64_t* value);
 
 /* ---- per-event observables (the reference's empty hook) ---------------------------------------------

@@ -287,3 +287,15 @@ def test_engineering_format_matches_reference_goldens(tp3, valeurs_text, value, 
         text = tp3.FinalResults(fin, cfg).res_data()
         line = [l for l in text.splitlines() if l.startswith(" Section Efficace")][0]
         assert line.split(":")[1].strip() == want
+
+
+def test_every_option_is_documented_in_the_header():
+    """Every name tp3_set_option / tp3_get_stat accepts (api.cu) is described in include/tp3.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "3photons-rust_b200", "csrc", "api.cu")).read()
+    header = open(os.path.join(root, "include", "tp3.h")).read()
+    names = sorted(set(re.findall(r'k == "([a-z_0-9]+)"', src)))
+    assert len(names) >= 15, names
+    missing = [n for n in names if f'"{n}"' not in header]
+    assert not missing, missing

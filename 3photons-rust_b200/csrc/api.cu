@@ -179,6 +179,14 @@ template <class F> PhysParams<F> phys_params(const tp3_params& p) {
         q.he = (F)((S)0.5 * e);
     }
     q.fc = FastCoef TP3_FAST_COEF_INIT;
+    if (p.flags & TP3_STANDARD_RANDOM) {
+        // xoshiro256+: the stream integer is d = x >> 11 and the uniform d 2^-53 (rand 0.8.5 Standard): cos_theta = 2u - 1 =
+        // fma(d, 2^-52, -1), 256 u = d 2^-45, r r' = (d d') 2^-106 -- all exact rescalings, so gen_event_ints computes the
+        // reference's own values with one multiplication per uniform less
+        q.fc.u_scale2 = 0x1p-52;
+        q.fc.u_scale_sq = 0x1p-106;
+        q.fc.phi_scale = 0x1p-45;
+    }
     return q;
 }
 

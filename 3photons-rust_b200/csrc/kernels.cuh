@@ -565,10 +565,12 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
         if (more) rng.begin_next(lane);
         RngTick<F, RNG> tick{rng, lane, more};
         F p[3][4];  // lanes past the end compute on valid but unused draws
-        if constexpr (TP3_GEN_FROM_INTS && sizeof(F) == 8 && RNG == RNG_RANF && !LITERAL) {
+        if constexpr (TP3_GEN_FROM_INTS && sizeof(F) == 8 && !LITERAL) {
+            // straight from the stream integers (the scales are kernel parameters: 1e-9-based for RANF, powers of two for
+            // xoshiro256+, where (x >> 11) 2^-53 makes this form EXACTLY the reference's arithmetic with four multiplications less)
             double d[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) d[j] = (double)(int)w[j];
+            for (int j = 0; j < 12; ++j) d[j] = RNG == RNG_RANF ? (double)(int)w[j] : (double)((unsigned long long)w[j] >> 11);
             gen_event_ints<kSort>(d, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);
         } else {
             F u[12];
@@ -867,9 +869,9 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
         if (!d.momenta) continue;
         F p[3][4];
         NoTick no_tick;
-        if constexpr (TP3_GEN_FROM_INTS && sizeof(F) == 8 && RNG == RNG_RANF && !LITERAL) {  // as in simulate_kernel
+        if constexpr (TP3_GEN_FROM_INTS && sizeof(F) == 8 && !LITERAL) {  // as in simulate_kernel
             double d[12];
-            for (int j = 0; j < 12; ++j) d[j] = (double)(int)w[j];
+            for (int j = 0; j < 12; ++j) d[j] = RNG == RNG_RANF ? (double)(int)w[j] : (double)((unsigned long long)w[j] >> 11);
             gen_event_ints<SORT>(d, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);
         } else {
             F u[12];

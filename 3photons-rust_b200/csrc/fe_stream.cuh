@@ -348,7 +348,8 @@ template <> __device__ __forceinline__ void fe_event_from_record<double>(const u
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double c = fma((double)(int)w[k], fm.fc->u_scale2, -1.0);
-        const double e = fma((double)(int)w[3 + k] * (double)(int)w[6 + k], fm.fc->u_scale_sq, Num<double>::MIN_POSITIVE);
+        // (the product of the two integers is exact in 64 bits: one conversion rounds it as the multiplication of the two doubles would)
+        const double e = fma((double)((unsigned long long)w[3 + k] * (unsigned long long)w[6 + k]), fm.fc->u_scale_sq, Num<double>::MIN_POSITIVE);
         const double x = fma((double)(int)w[9 + 2 * k], fm.fc->u_scale2, -1.0), y = fma((double)(int)w[10 + 2 * k], fm.fc->u_scale2, -1.0);
         const double en = fast_neg_log(e, fm);
         // sin(theta) / |(x, y)| = sqrt(a) / sqrt(r2) = a / sqrt(a r2), a = 1 - c^2: ONE reciprocal square root instead of a

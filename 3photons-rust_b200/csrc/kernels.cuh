@@ -571,7 +571,11 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
             double d[12];
 #pragma unroll
             for (int j = 0; j < 12; ++j) d[j] = RNG == RNG_RANF ? (double)(int)w[j] : (double)((unsigned long long)w[j] >> 11);
-            gen_event_ints<kSort>(d, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);
+            double rr[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)  // RANF: n n' < 1e18 is exact in 64 bits: one IMAD.WIDE + one conversion instead of two + a DMUL
+                rr[k] = RNG == RNG_RANF ? (double)((unsigned long long)w[4 * k + 2] * (unsigned long long)w[4 * k + 3]) : d[4 * k + 2] * d[4 * k + 3];
+            gen_event_ints<kSort>(d, rr, P.e_total, FastMath{&sm.fm, &P.fc}, p, tick);
         } else {
             F u[12];
 #pragma unroll
@@ -872,7 +876,10 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
         if constexpr (TP3_GEN_FROM_INTS && sizeof(F) == 8 && !LITERAL) {  // as in simulate_kernel
             double d[12];
             for (int j = 0; j < 12; ++j) d[j] = RNG == RNG_RANF ? (double)(int)w[j] : (double)((unsigned long long)w[j] >> 11);
-            gen_event_ints<SORT>(d, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);
+            double rr[3];
+            for (int k = 0; k < 3; ++k)
+                rr[k] = RNG == RNG_RANF ? (double)((unsigned long long)w[4 * k + 2] * (unsigned long long)w[4 * k + 3]) : d[4 * k + 2] * d[4 * k + 3];
+            gen_event_ints<SORT>(d, rr, P.e_total, FastMath{&sm.fm, &P.fc}, p, no_tick);
         } else {
             F u[12];
             for (int j = 0; j < 12; ++j) u[j] = WarpRng<F, RNG>::uniform(w[j], !LITERAL && (j & 3) == 1, P.fc);

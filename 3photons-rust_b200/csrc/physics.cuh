@@ -222,9 +222,10 @@ __device__ __forceinline__ void raw_photon(const F* u, const FastMath fm, F q[4]
 // The same for the f64 RANF fast path, straight from the stream integers d_j = (double)n_j (ranf.rs:99 would first
 // scale each to u_j = 1e-9 d_j): cos_theta = 2e-9 d_0 - 1 in one FMA, 256 phi-turns = 256e-9 d_1, and
 // r r' = 1e-18 (d_2 d_3) with one multiplication less.  Each differs from the reference's expression by one rounding.
-__device__ __forceinline__ void raw_photon_ints(const double* d, const FastMath fm, double q[4]) {
+// (rr = d_2 d_3 rounded once: the caller forms it as the exact 64-bit integer product converted once where that fits)
+__device__ __forceinline__ void raw_photon_ints(const double* d, double rr, const FastMath fm, double q[4]) {
     const double c = fma(d[0], fm.fc->u_scale2, -1.0);
-    const double e = fma(d[2] * d[3], fm.fc->u_scale_sq, Num<double>::MIN_POSITIVE);
+    const double e = fma(rr, fm.fc->u_scale_sq, Num<double>::MIN_POSITIVE);
     double sphi, cphi;
     fast_sincos_256(d[1] * fm.fc->phi_scale, fm, sphi, cphi);
     const double st = fast_sqrt(fma(-c, c, 1.0));
@@ -236,13 +237,13 @@ __device__ __forceinline__ void raw_photon_ints(const double* d, const FastMath 
     q[3] = en;
 }
 template <bool SORT, class Tick>
-__device__ __forceinline__ void gen_event_ints(const double d[12], double e_total, const FastMath fm, double p[3][4], Tick& tick) {
+__device__ __forceinline__ void gen_event_ints(const double d[12], const double rr[3], double e_total, const FastMath fm, double p[3][4], Tick& tick) {
     double q[3][4];
-    raw_photon_ints(d, fm, q[0]);
+    raw_photon_ints(d, rr[0], fm, q[0]);
     tick.template at<1>();
-    raw_photon_ints(d + 4, fm, q[1]);
+    raw_photon_ints(d + 4, rr[1], fm, q[1]);
     tick.template at<2>();
-    raw_photon_ints(d + 8, fm, q[2]);
+    raw_photon_ints(d + 8, rr[2], fm, q[2]);
     tick.template at<3>();
     conformal_transform<double, SORT, false, Cons3<double, false>::value>(q, e_total, p);
 }

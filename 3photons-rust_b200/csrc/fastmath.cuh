@@ -57,9 +57,16 @@ __constant__ double kRotSin[3] = {TP3_ROT_SIN_COEFFS};
 __constant__ double kRotCos[3] = {TP3_ROT_COS_COEFFS};
 #endif
 
+#ifdef TP3_EXPERIMENT_SMALL_TABLES   /* timing experiment only (wrong results): how much would 20 resident warps per SM buy? */
+#define TP3_LOG_MASK 63
+#define TP3_SC_MASK 127
+#else
+#define TP3_LOG_MASK 127
+#define TP3_SC_MASK 255
+#endif
 struct FastMathSmem {
-    double2 log_tab[128];
-    double2 sincos_tab[256];  // {sin, cos}(2 pi k / 256)
+    double2 log_tab[TP3_LOG_MASK + 1];
+    double2 sincos_tab[TP3_SC_MASK + 1];  // {sin, cos}(2 pi k / 256)
 };
 // What the elementary functions need: the CTA's tables and the coefficients (a kernel parameter)
 struct FastMath {
@@ -68,8 +75,8 @@ struct FastMath {
 };
 
 __device__ __forceinline__ void fastmath_load(FastMathSmem* sm) {
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) sm->log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sm->sincos_tab[i] = make_double2(kSinCosTable[i][0], kSinCosTable[i][1]);
+    for (int i = threadIdx.x; i <= TP3_LOG_MASK; i += blockDim.x) sm->log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
+    for (int i = threadIdx.x; i <= TP3_SC_MASK; i += blockDim.x) sm->sincos_tab[i] = make_double2(kSinCosTable[i][0], kSinCosTable[i][1]);
 }
 
 __device__ __forceinline__ double mufu_rcp(double x) {
@@ -142,7 +149,7 @@ __device__ __forceinline__ double fast_neg_log(double x, const FastMath fm) {
     TP3_COEFF_ARRAYS
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int k = (hi >> 20) - 1023;
-    const double2 t = sm->log_tab[(hi >> 13) & 127];
+    const double2 t = sm->log_tab[(hi >> 13) & TP3_LOG_MASK];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, t.x, -1.0);
     double p = fma(r, kLog1p[4], kLog1p[3]);
@@ -160,7 +167,7 @@ __device__ __forceinline__ void fast_sincos_256(double t, const FastMath fm, dou
     const FastMathSmem* const sm = fm.sm;
     TP3_COEFF_ARRAYS
     const double kf = rint(t);
-    const int k = __double2int_rn(t) & 255;
+    const int k = __double2int_rn(t) & TP3_SC_MASK;
     const double2 sc = sm->sincos_tab[k];
     const double d = t - kf;
     const double d2 = d * d;

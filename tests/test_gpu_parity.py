@@ -852,10 +852,14 @@ def test_single_process_multi_device(tp3, valeurs_text, features):
     with tp3.Simulator(cfg, devices=[0, 1]) as two:
         got = two.simulate_batches(5, 37, 1234)
         got_merged = two.simulate_merged(5, 37, 1234)
+        both, both_merged = two.simulate_batches_merged(5, 37, 1234)
     assert bytes(got) == bytes(want)
     # two device partials folded on the host: same sums up to the association of one addition
     assert got_merged.selected_events == want_merged.selected_events
     assert_acc_close(got_merged, want_merged, 1e-14)
+    # per-batch accumulators and the merged one from the same launches
+    assert bytes(both) == bytes(want)
+    assert bytes(both_merged) == bytes(got_merged)
 
 
 def test_cli_binary(tp3, valeurs_text, tmp_path):

@@ -89,17 +89,27 @@ __device__ __forceinline__ void sqrt_rsqrt_t(f2 x, f2* s, f2* rs) {
     *rs = f2(r0, r1);
 }
 __device__ __forceinline__ void sincos_scaled_t(f2 t, const FastMath, f2* s, f2* c) {
-    // the quadrant split of both halves in packed arithmetic (see the scalar form in physics.cuh: same operations, same bits);
+    // the argument of both halves in packed arithmetic (see the scalar forms in physics.cuh: same operations, same bits);
     // the inline-PTX operators are opaque to the compiler, so (t + M) - M is not simplified
+    float s0, c0, s1, c1;
+#if TP3_F32_SINCOS_DIRECT
+    const f2 x = (f2(2.0f) - t) * f2(kHalfPiF);
+    s0 = mufu_sin_f(x.lo());
+    s1 = mufu_sin_f(x.hi());
+    c0 = mufu_cos_f(x.lo());
+    c1 = mufu_cos_f(x.hi());
+    *s = f2(s0, s1);
+    *c = -f2(c0, c1);
+#else
     const f2 magic(kRintMagic);
     const f2 tm = t + magic;
     const f2 qf = tm - magic;
-    const f2 x = (t - qf) * f2(1.57079632679489661923f);
-    float s0, c0, s1, c1;
+    const f2 x = (t - qf) * f2(kHalfPiF);
     sincos_quadrant(x.lo(), __float_as_int(tm.lo()), &s0, &c0);
     sincos_quadrant(x.hi(), __float_as_int(tm.hi()), &s1, &c1);
     *s = f2(s0, s1);
     *c = f2(c0, c1);
+#endif
 }
 
 // me_fast's photon-along-(-Z) case (spinor.rs:42-46), per half

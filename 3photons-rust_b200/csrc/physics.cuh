@@ -64,12 +64,21 @@ template <class F> struct PhiScale;
 template <> struct PhiScale<double> { static constexpr double value = 256.0; };
 template <> struct PhiScale<float> { static constexpr float value = 4.0f; };
 __device__ __forceinline__ void sincos_scaled_t(double t, const FastMath fm, double* s, double* c) { fast_sincos_256(t, fm, *s, *c); }
-// sin, cos of t quarter turns, 0 <= t <= 4, on the SFU.  q = rint(t) comes from the float adder: t + 1.5 * 2^23 holds rint(t) (ties to
-// even, like rintf) in its low mantissa bits and (t + M) - M is that integer as a float -- two FADDs instead of FRND + F2I on the
-// XU pipe, which the 14 MUFU calls of an event already keep busy.  The remainder |x| <= pi/4 is the SFU's most accurate range.
-// (A/B, profiles/r02_f32_sincos_ab.txt: the full angle in ONE sin / cos call each is 7 % faster for the whole kernel and flips 5
-// instead of 1 of the 7 082 165 selected events of the golden run: not taken.)
+// sin, cos of t quarter turns, 0 <= t <= 4, on the SFU.
+// Shipped form (TP3_F32_SINCOS_DIRECT = 1): the angle is reflected into x = pi - theta = (2 - t) pi/2, |x| <= pi -- the range on
+// which sin.approx / cos.approx have their documented absolute error (2^-21.4) -- and sin(theta) = sin(x), cos(theta) = -cos(x):
+// one subtraction, one multiplication and the two SFU calls; the sign folds into the consumer's operand modifier.
+// A/B form (= 0, shipped until session 47): quadrant split, q = rint(t) from the float adder (t + 1.5 * 2^23 holds rint(t) in its low
+// mantissa bits and (t + M) - M is that integer as a float), remainder |x| <= pi/4, swap and signs from q: 7 % more issue slots for
+// the whole kernel.  Both forms agree with the f32 oracle to the same per-event figures (profiles/r02_f32_sincos_ab.txt,
+// profiles/r02_f32_per_event.txt); over the 1e7 events of the golden run they decide 5 resp. 1 cuts differently from the reference.
+#ifndef TP3_F32_SINCOS_DIRECT
+#define TP3_F32_SINCOS_DIRECT 1
+#endif
 constexpr float kRintMagic = 12582912.0f;
+constexpr float kHalfPiF = 1.57079632679489661923f;
+__device__ __forceinline__ float mufu_sin_f(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_cos_f(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void sincos_quadrant(float x, int q, float* s, float* c) {
     const float ps = __sinf(x), pc = __cosf(x);
     const bool swap = q & 1;
@@ -78,9 +87,15 @@ __device__ __forceinline__ void sincos_quadrant(float x, int q, float* s, float*
     *c = __int_as_float(__float_as_int(c0) ^ (int)((unsigned)((q + 1) & 2) << 30));
 }
 __device__ __forceinline__ void sincos_scaled_t(float t, const FastMath, float* s, float* c) {
+#if TP3_F32_SINCOS_DIRECT
+    const float x = (2.0f - t) * kHalfPiF;
+    *s = mufu_sin_f(x);
+    *c = -mufu_cos_f(x);
+#else
     const float tm = __fadd_rn(t, kRintMagic);
     const float qf = __fadd_rn(tm, -kRintMagic);
-    sincos_quadrant((t - qf) * 1.57079632679489661923f, __float_as_int(tm), s, c);
+    sincos_quadrant((t - qf) * kHalfPiF, __float_as_int(tm), s, c);
+#endif
 }
 __device__ __forceinline__ double sqrt_pos_t(double x) { return fast_sqrt(x); }
 __device__ __forceinline__ float sqrt_pos_t(float x) { return x * mufu_rsqrt_f(x + 1e-30f); }

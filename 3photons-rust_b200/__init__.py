@@ -342,7 +342,11 @@ class Simulator:
             lib().tp3_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the module globals may already be gone
+            pass
 
     def __enter__(self):
         return self

@@ -207,7 +207,7 @@ template <class F, int RNG>
 __global__ void __launch_bounds__(kFeThreads, 512 / kFeThreads) faster_evgen_kernel(const FeArgs a, const PhysParams<F> P) {
     __shared__ FastMathSmem fm;
     __shared__ uint32_t ranf_state[RNG == RNG_RANF ? kFeRow * kFeThreads : 1];
-    fastmath_load(&fm);
+    fastmath_load<kFeThreads>(&fm);
     __syncthreads();
     const uint64_t unit = (uint64_t)blockIdx.x * kFeThreads + threadIdx.x;
     const bool split = a.split == 32;

@@ -74,9 +74,17 @@ struct FastMath {
     const FastCoef* fc;
 };
 
-__device__ __forceinline__ void fastmath_load(FastMathSmem* sm) {
-    for (int i = threadIdx.x; i <= TP3_LOG_MASK; i += blockDim.x) sm->log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
-    for (int i = threadIdx.x; i <= TP3_SC_MASK; i += blockDim.x) sm->sincos_tab[i] = make_double2(kSinCosTable[i][0], kSinCosTable[i][1]);
+// The tables live in GLOBAL memory (L2-resident, 6 KB) and are copied with coalesced 128-bit loads, all of a lane's loads in flight
+// at once.  (Until session 50 they were __constant__: every lane reads a different entry, and a constant-bank load with 32 different
+// addresses is served one address at a time -- 768 serialized accesses per CTA, which a one-warp CTA that lives for a single batch
+// or for one 2500-event part of the faster-evgen physics kernel pays at every start.)
+template <int THREADS> __device__ __forceinline__ void fastmath_load(FastMathSmem* sm) {
+#pragma unroll
+    for (int i = 0; i <= TP3_LOG_MASK; i += THREADS)
+        if (i + (int)threadIdx.x <= TP3_LOG_MASK) sm->log_tab[i + threadIdx.x] = __ldg(&kLogTable[i + threadIdx.x]);
+#pragma unroll
+    for (int i = 0; i <= TP3_SC_MASK; i += THREADS)
+        if (i + (int)threadIdx.x <= TP3_SC_MASK) sm->sincos_tab[i + threadIdx.x] = __ldg(&kSinCosTable[i + threadIdx.x]);
 }
 
 __device__ __forceinline__ double mufu_rcp(double x) {

@@ -415,7 +415,8 @@ template <class F, int HIST = 0> __global__ void __launch_bounds__(32, 16) fe_ph
     double* const hist_w = HIST ? a.hist_weights + (size_t)(blockIdx.x % kHistReplicas) * hist_n : nullptr;
     if (HIST)
         for (int i = lane; i < hist_n; i += 32) hist_c[i] = 0u;
-    for (int i = lane; i < 128; i += 32) sm.log_tab[i] = make_double2(kLogTable[i][0], kLogTable[i][1]);
+#pragma unroll
+    for (int i = 0; i < 128; i += 32) sm.log_tab[i + lane] = __ldg(&kLogTable[i + lane]);  // coalesced 128-bit loads from global memory (fastmath.cuh)
     __syncwarp();
     static_assert(offsetof(FastMathSmem, log_tab) == 0, "log_tab must lead FastMathSmem");
     const FastMath fm{reinterpret_cast<const FastMathSmem*>(sm.log_tab), &P.fc};  // only log_tab is read (fast_neg_log)

@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
     extern __shared__ __align__(16) unsigned char hist_raw[];
     using Word = typename RawWord<F, RNG>::type;
     const int warp = kWarps == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
-    fastmath_load(&sm.fm);
+    fastmath_load<kThreads>(&sm.fm);
     const int hist_n = HIST ? TP3_HIST_OBSERVABLES * (int)a.hist_bins : 0;
     uint32_t* const hist_c = reinterpret_cast<uint32_t*>(hist_raw);
     double* const hist_w = HIST ? a.hist_weights + (size_t)(blockIdx.x % kHistReplicas) * hist_n : nullptr;
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(kThreads) dump_kernel(const SimArgs a, const P
     __shared__ BlockSmem<F> sm;
     using Word = typename RawWord<F, RNG>::type;
     const int lane = threadIdx.x & 31;
-    fastmath_load(&sm.fm);
+    fastmath_load<kThreads>(&sm.fm);
     __syncthreads();
     if (threadIdx.x >= 32) return;  // one warp = one batch; the dump is for a single batch
     WarpRng<F, RNG> rng;
@@ -1035,7 +1035,7 @@ template <class F> __global__ void __launch_bounds__(kMergeThreads) merge_kernel
 // Parity hook for the hand-written FP64 functions (fastmath.cuh): out[i] = f_which(in[i]).
 __global__ void fastmath_probe_kernel(int which, uint32_t n, const double* __restrict__ in, double* __restrict__ out, const FastCoef fc) {
     __shared__ FastMathSmem fms;
-    fastmath_load(&fms);
+    fastmath_load<256>(&fms);  // (launched with 256 threads per CTA, api.cu)
     const FastMath fm{&fms, &fc};
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

@@ -108,6 +108,9 @@ struct tp3_ctx {
     int64_t opt_grid_warps = 0;      // warps in the grid (0 = what the device holds at once)
     int64_t opt_batch_parts = 1;     // parts per batch (1, 2, 5, 10; 0 = as many of those as still fit one wave of warps): small runs
                                      //    then fill the device; the per-batch sums depend on it in their last bits (tp3.h)
+    int64_t opt_taper_units = 0;     // dynamic schedule: units per taper stage (-1 = no taper, 0 = one wave)
+    int64_t opt_tail_singles = 0;    // dynamic schedule: single-batch units at the end of the launch (0 = auto)
+    int64_t opt_align_units = 1;     // dynamic schedule: the big units end on a multiple of 4 x SMs units
     int64_t opt_ramp_units = 0;      // dynamic schedule: ramp units of 1, 2, .., 8 batches at the head of the launch (A/B only)
     int64_t opt_sched_dynamic = 1;   // 1 (default): one unit per warp, dispatched by the hardware in unit order; 0: static balanced schedule (kernels.cuh)
     int64_t opt_f32_scalar = 0;      // f32: one event per lane instead of the packed two-events-per-lane kernel
@@ -199,6 +202,9 @@ struct Sched {
     int64_t dynamic;       // 1: one unit per warp, dispatched by the hardware (kernels.cuh)
     SimArgs* filled;       // out (may be null): the schedule the launcher chose
     int64_t ramp_units;    // 0 = none
+    int64_t taper_units;   // -1 = none, 0 = auto (one wave per stage), > 0: units per taper stage
+    int64_t tail_singles;  // 0 = auto, > 0: single-batch units at the end of the launch (at least)
+    bool align_units;      // the big units end on a multiple of 4 x SMs units (see fill_schedule)
 };
 
 // Fill the schedule fields of `a` for a kernel that runs `warps`-warp CTAs, `ctas_per_sm` of them per SM.
@@ -215,9 +221,40 @@ cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& s
         uint64_t ramp = sc.ramp_units > 0 ? (uint64_t)sc.ramp_units / 8 * 8 : 0;
         if (ramp / 8 * 36 > a.n_batches) ramp = 0;
         const uint64_t ramp_batches = ramp / 8 * 36;
-        const uint64_t singles = std::min<uint64_t>(a.n_batches - ramp_batches, 4 * W);
-        const uint64_t big = unit > 1 ? (a.n_batches - ramp_batches - singles) / unit : 0;
-        const uint64_t units = ramp + big + (a.n_batches - ramp_batches - big * unit);
+        // Tail (profiles/r02_tail_scan.txt, r02_unit_trace.txt).  The warps leave the big units at different times -- the starts of
+        // 2368 consecutive units are spread over 4 of the 5 ms a big unit takes -- and what follows has to absorb that spread and
+        // end with single batches, so that the device drains within one batch time.  With room for it: half a wave of half units,
+        // half a wave of quarter units, then two waves of single batches (3 W units for 5 W batches; four waves of single batches,
+        // the first version, are 4 W units for 4 W batches and measured 0.06-0.15 ms slower at the 125 000 batches one GPU gets of
+        // the 1e10-event run on eight).  Short launches: single batches for the last four waves.
+        const uint64_t left = a.n_batches - ramp_batches;
+        uint64_t taper = 0, singles = std::min<uint64_t>(left, 4 * W);
+        if (unit >= 4 && unit % 4 == 0 && sc.taper_units >= 0) {
+            const uint64_t t = sc.taper_units > 0 ? (uint64_t)sc.taper_units : W / 2;
+            const uint64_t s1 = sc.tail_singles > 0 ? (uint64_t)sc.tail_singles : 2 * W;
+            const uint64_t need = t * (unit / 2 + unit / 4) + s1;
+            if (left >= 2 * need) {
+                taper = t;
+                singles = s1;
+            }
+        } else if (sc.tail_singles > 0) {
+            singles = std::min<uint64_t>(left, (uint64_t)sc.tail_singles);
+        }
+        const uint64_t taper_batches = taper * (unit / 2 + unit / 4);
+        uint64_t big = unit > 1 ? (left - taper_batches - singles) / unit : 0;
+        // ALIGNMENT (profiles/r02_unit_trace.txt).  The four one-warp CTAs that share a sub-partition start a launch together,
+        // the scheduler serves them strictly in order, and from then on they stay 1.2 ms apart: in steady state 4 x SMs consecutive
+        // units -- one per sub-partition of the device -- start within 0.3 ms of each other, four such bands per 5 ms wave.  If the
+        // big units end inside a band, half of an SM's sub-partitions hold a big unit more than the others, nothing evens that
+        // out (a new CTA goes where a slot frees), and the launch takes 0.1-0.2 ms longer: the run time as a function of
+        // the launch size alternates with a period of 4 x SMs big units (profiles/r02_tail_scan.txt).  So the big units end on a
+        // band boundary and the batches this frees (< 4 x SMs units' worth) run as single batches.
+        if (warps == 1 && sc.align_units && ramp == 0) {
+            const uint64_t M = 4ull * (uint64_t)sc.sm_count;
+            if (big >= 2 * M) big -= big % M;
+        }
+        const uint64_t units = ramp + big + 2 * taper + (left - taper_batches - big * unit);
+        a.taper = (uint32_t)taper;
         a.dynamic = 1 + (uint32_t)ramp;
         a.unit_batches = (uint32_t)unit;
         a.full_rounds = (uint32_t)big;
@@ -1013,6 +1050,9 @@ int ensure_out(tp3_ctx* c, DeviceSlot& s, uint64_t n) {
     return TP3_OK;
 }
 
+#ifdef TP3_TRACE_UNITS
+unsigned long long* g_trace = nullptr;  // diagnostic build only: device buffer [units][3], set by tp3_debug_set_trace
+#endif
 SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_t last_len) {
     SimArgs a;
     std::memset(&a, 0, sizeof a);
@@ -1022,6 +1062,9 @@ SimArgs make_args(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
     a.batch_events = TP3_EVENT_BATCH_SIZE;
     a.batch_parts = 1;
     a.jump_seeding = (c->params.flags & TP3_FASTER_THREADING) ? 1u : 0u;
+#ifdef TP3_TRACE_UNITS
+    a.trace = g_trace;
+#endif
     a.ranf_table = s.d_ranf_table;
     a.xo_batch_states = s.d_xo_states;
     a.xo_lane_polys = s.d_xo_lane_polys;
@@ -1157,7 +1200,8 @@ int enqueue_range(tp3_ctx* c, DeviceSlot& s, uint64_t first, uint64_t n, uint32_
         a.hist_counts = s.d_hist_counts;
         a.hist_weights = s.d_hist_weights;
         const Sched sc{s.sm_count, c->opt_unit_batches, c->opt_grid_warps,
-                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic, &s.last_args, c->opt_ramp_units};
+                       !(c->params.flags & (TP3_STANDARD_RANDOM | TP3_FASTER_THREADING)), c->opt_sched_dynamic, &s.last_args, c->opt_ramp_units,
+                       c->opt_taper_units, c->opt_tail_singles, c->opt_align_units != 0};
         // Small runs (the default 1e7 events are 1000 batches on 2368 warp slots): cut every batch into equal parts, one warp
         // each, and add the parts of a batch in part order afterwards.  Only where a part's start is a plain stream position
         // (sequential RANF stream), and only on request: the sums of a batch then depend on the number of parts in their last
@@ -1243,6 +1287,9 @@ void split(uint64_t n, size_t G, size_t g, uint64_t& off, uint64_t& cnt) {
 }  // namespace
 
 extern "C" {
+#ifdef TP3_TRACE_UNITS
+void tp3_debug_set_trace(void* device_ptr) { g_trace = static_cast<unsigned long long*>(device_ptr); }
+#endif
 
 int tp3_abi_version(void) { return TP3_ABI_VERSION; }
 
@@ -1501,7 +1548,7 @@ static int simulate_batches_streamed(tp3_ctx* c, DeviceSlot& s, uint64_t first, 
     auto batches_of = [&](uint64_t units) -> uint64_t {  // batches covered by units [0, units) of the dynamic schedule (kernels.cuh)
         if (units == 0) return 0;
         uint64_t lo, hi;
-        unit_range_dynamic(a.dynamic - 1, a.full_rounds, a.unit_batches, units - 1, lo, hi);
+        unit_range_dynamic(a.dynamic - 1, a.full_rounds, a.unit_batches, a.taper, units - 1, lo, hi);
         return std::min<uint64_t>(n, hi);
     };
     uint64_t copied = 0;
@@ -1682,6 +1729,9 @@ int tp3_set_option(tp3_ctx* c, const char* name, int64_t value) {
     else if (k == "grid_warps" && value >= 0 && value <= (1 << 20)) c->opt_grid_warps = value;
     else if (k == "sched_dynamic") c->opt_sched_dynamic = value != 0;
     else if (k == "ramp_units" && value >= 0 && value <= (1 << 20)) c->opt_ramp_units = value;
+    else if (k == "taper_units" && value >= -1 && value <= (1 << 20)) c->opt_taper_units = value;
+    else if (k == "tail_singles" && value >= 0 && value <= (1 << 22)) c->opt_tail_singles = value;
+    else if (k == "align_units") c->opt_align_units = value != 0;
     else if (k == "batch_parts" && (value == 0 || value == 1 || value == 2 || value == 5 || value == 10)) c->opt_batch_parts = value;
     else if (k == "f32_scalar") c->opt_f32_scalar = value != 0;
     else if (k == "fe_split" && (value == 0 || value == 1 || value == 32)) c->opt_fe_split = value;

@@ -93,6 +93,9 @@ struct SimArgs {
                                //    of 1, 2, .., 8, 1, 2, .. batches (an A/B option: unequal first units to take the first wave out of
                                //    step at once; it does not pay), then `full_rounds` units of unit_batches batches, then single
                                //    batches (the last waves are short, so the tail is < 1 batch)
+    uint32_t taper;            // dynamic schedule: between the big units and the single batches, `taper` units of unit_batches / 2 and
+                               //    `taper` units of unit_batches / 4 batches: the warps leave the big units at different times, and
+                               //    every stage absorbs the spread of the one before it
     uint32_t epoch;            // value that marks a unit of THIS launch as done in unit_done
     uint32_t* unit_done;       // [(full_rounds + 1) * W], or null: no in-kernel fold
     struct FoldState* fold;    // running accumulator of the ordered fold, or null
@@ -106,6 +109,9 @@ struct SimArgs {
     uint32_t hist_bins;
     unsigned long long* hist_counts;   // [TP3_HIST_OBSERVABLES][hist_bins]
     double* hist_weights;              // [kHistReplicas][TP3_HIST_OBSERVABLES][hist_bins]
+#ifdef TP3_TRACE_UNITS                 /* diagnostic build only (scripts/unit_trace.py): when and where every unit ran */
+    unsigned long long* trace;         // [units][3]: globaltimer at the unit's start and end, smid | warpid << 16 | batches << 32
+#endif
 };
 
 // Ordered fold of a launch (one per device slot, reset by the host before the launch).
@@ -387,25 +393,39 @@ __device__ __forceinline__ int batch_len(const SimArgs& a, uint64_t slot) {
 // (dynamic schedule: the first argument has its top bit set and carries the number of ramp units, a multiple of 8, in its
 // other bits; `full_rounds` is the number of big units; the rest are single batches)
 constexpr uint32_t kSchedDynamic = 0x80000000u;
-__host__ __device__ __forceinline__ void unit_range_dynamic(uint64_t ramp, uint64_t big, uint64_t unit_batches, uint64_t u, uint64_t& lo,
-                                                            uint64_t& hi) {
+__host__ __device__ __forceinline__ void unit_range_dynamic(uint64_t ramp, uint64_t big, uint64_t unit_batches, uint64_t taper, uint64_t u,
+                                                            uint64_t& lo, uint64_t& hi) {
     const uint64_t ramp_batches = (ramp >> 3) * 36;  // 1 + 2 + .. + 8 per group of eight ramp units
     if (u < ramp) {
         const uint64_t j = u & 7;
         lo = (u >> 3) * 36 + j * (j + 1) / 2;
         hi = lo + j + 1;
-    } else if (u < ramp + big) {
-        lo = ramp_batches + (u - ramp) * unit_batches;
-        hi = lo + unit_batches;
-    } else {
-        lo = ramp_batches + big * unit_batches + (u - ramp - big);
-        hi = lo + 1;
+        return;
     }
+    u -= ramp;
+    uint64_t base = ramp_batches, size = unit_batches;
+    if (u >= big) {  // taper: units of unit_batches / 2, then of unit_batches / 4, then single batches
+        u -= big;
+        base += big * size;
+        size >>= 1;
+        if (u >= taper) {
+            u -= taper;
+            base += taper * size;
+            size >>= 1;
+            if (u >= taper) {
+                u -= taper;
+                base += taper * size;
+                size = 1;
+            }
+        }
+    }
+    lo = base + u * size;
+    hi = lo + size;
 }
-__device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint64_t n_batches, uint64_t u,
-                                           uint64_t& lo, uint64_t& hi) {
+__device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint32_t taper, uint64_t n_batches,
+                                           uint64_t u, uint64_t& lo, uint64_t& hi) {
     if (n_warps & kSchedDynamic) {
-        unit_range_dynamic(n_warps & ~kSchedDynamic, full_rounds, unit_batches, u, lo, hi);
+        unit_range_dynamic(n_warps & ~kSchedDynamic, full_rounds, unit_batches, taper, u, lo, hi);
         return;
     }
     const uint64_t W = n_warps, full = (uint64_t)full_rounds * W;
@@ -419,13 +439,15 @@ __device__ __forceinline__ void unit_range(uint32_t n_warps, uint32_t full_round
     }
 }
 __device__ __forceinline__ void unit_range(const SimArgs& a, uint64_t u, uint64_t& lo, uint64_t& hi) {
-    unit_range(a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.n_batches, u, lo, hi);
+    unit_range(a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.taper, a.n_batches, u, lo, hi);
 }
 // Number of units of a launch.
-__device__ __forceinline__ uint64_t unit_count(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint64_t n_batches) {
+__device__ __forceinline__ uint64_t unit_count(uint32_t n_warps, uint32_t full_rounds, uint32_t unit_batches, uint32_t taper,
+                                               uint64_t n_batches) {
     if (n_warps & kSchedDynamic) {
         const uint64_t ramp = n_warps & ~kSchedDynamic;
-        return ramp + full_rounds + (n_batches - (ramp >> 3) * 36 - (uint64_t)full_rounds * unit_batches);
+        const uint64_t taper_batches = (uint64_t)taper * ((unit_batches >> 1) + (unit_batches >> 2));
+        return ramp + full_rounds + 2ull * taper + (n_batches - (ramp >> 3) * 36 - (uint64_t)full_rounds * unit_batches - taper_batches);
     }
     return ((uint64_t)full_rounds + 1) * n_warps;
 }
@@ -442,8 +464,9 @@ __device__ __forceinline__ void fence_sc() { asm volatile("fence.sc.gpu;" ::: "m
 // (The schedule is passed by value: a reference to the kernel's parameter block would force a local-memory copy of it.)
 template <class F>
 __device__ __noinline__ void fold_publish(FoldState* fs, uint32_t* unit_done, const tp3_acc* out, uint32_t n_warps, uint32_t full_rounds,
-                                          uint32_t unit_batches, uint32_t epoch, uint64_t n_batches, uint64_t u, int lane) {
-    const uint64_t n_units = unit_count(n_warps, full_rounds, unit_batches, n_batches);
+                                          uint32_t unit_batches, uint32_t taper, uint32_t epoch, uint64_t n_batches, uint64_t u,
+                                          int lane) {
+    const uint64_t n_units = unit_count(n_warps, full_rounds, unit_batches, taper, n_batches);
     __syncwarp();
     if (lane == 0) {
         __threadfence();  // this unit's accumulators (written by lane 0) before the flag
@@ -475,8 +498,8 @@ __device__ __noinline__ void fold_publish(FoldState* fs, uint32_t* unit_done, co
             const unsigned m = not_ready ? (unsigned)__ffs(not_ready) - 1u : 32u;  // leading run of ready units
             if (m == 0) break;
             uint64_t lo, hi, lo2;
-            unit_range(n_warps, full_rounds, unit_batches, n_batches, nu, lo, hi);
-            unit_range(n_warps, full_rounds, unit_batches, n_batches, nu + m - 1, lo2, hi);  // units are consecutive batch ranges
+            unit_range(n_warps, full_rounds, unit_batches, taper, n_batches, nu, lo, hi);
+            unit_range(n_warps, full_rounds, unit_batches, taper, n_batches, nu + m - 1, lo2, hi);  // units are consecutive batch ranges
             const unsigned long long* src = reinterpret_cast<const unsigned long long*>(out) + word;
             for (uint64_t b = lo; b < hi; b += 16) {  // 16 loads in flight, then the dependent chain of additions
                 unsigned long long v[16];
@@ -540,6 +563,17 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
     uint64_t unit_lo, unit_hi;
     unit_range(a, unit, unit_lo, unit_hi);
     if (unit_lo >= a.n_batches) break;  // (warps past the last unit of a dynamic grid rounded up to whole CTAs)
+#ifdef TP3_TRACE_UNITS
+    if (a.trace && lane == 0) {
+        unsigned long long t;
+        unsigned smid, wid_hw;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid_hw));
+        a.trace[3 * unit] = t;
+        a.trace[3 * unit + 2] = smid | (wid_hw << 16) | (unsigned long long)(unit_hi - unit_lo) << 32;
+    }
+#endif
   for (uint64_t slot = unit_lo; slot < unit_hi; ++slot) {
     const int n_ev = batch_len(a, slot);
     if (slot == unit_lo || !rng.next_batch(a, n_ev, lane)) rng.init(a, &sm.w[warp], a.first_batch + slot, slot, n_ev, lane);
@@ -656,7 +690,14 @@ __global__ void __launch_bounds__(32 * sim_warps(LITERAL, HIST), sim_min_ctas(LI
     }
     __syncwarp();
   }
-    if (a.fold) fold_publish<F>(a.fold, a.unit_done, a.out, a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+#ifdef TP3_TRACE_UNITS
+    if (a.trace && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[3 * unit + 1] = t;
+    }
+#endif
+    if (a.fold) fold_publish<F>(a.fold, a.unit_done, a.out, a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.taper, a.epoch, a.n_batches, unit, lane);
   }
     if (HIST) {  // CTA histograms -> device histograms
         __syncthreads();
@@ -842,7 +883,7 @@ __global__ void __launch_bounds__(32 * x2_warps(RNG), 20 / x2_warps(RNG)) simula
         }
         __syncwarp();
     }
-    if (a.fold) fold_publish<float>(a.fold, a.unit_done, a.out, a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.epoch, a.n_batches, unit, lane);
+    if (a.fold) fold_publish<float>(a.fold, a.unit_done, a.out, a.dynamic ? ((a.dynamic - 1) | kSchedDynamic) : a.n_warps, a.full_rounds, a.unit_batches, a.taper, a.epoch, a.n_batches, unit, lane);
   }
 }
 

@@ -149,6 +149,11 @@ size_t tp3_kernel_arg_bytes(void);
  *   "grid_warps"       warps in the grid (0 = as many as the device holds at once)
  *   "sched_dynamic"    1 (default): one unit per warp, dispatched by the hardware; 0: static balanced schedule
  *   "ramp_units"       dynamic schedule: that many units of 1, 2, .., 8 batches at the head of the launch (0 = none, the default)
+ *   "taper_units"      dynamic schedule: units per taper stage (half units, then quarter units) between the big units and the
+ *                      single batches at the end of a launch (0 = half a wave each, the default; -1 = no taper stages)
+ *   "tail_singles"     dynamic schedule: single-batch units at the end of the launch (0 = by launch size, the default)
+ *   "align_units"      dynamic schedule: 1 (default): the number of big units is rounded down to a multiple of 4 x SMs, so that every
+ *                      sub-partition of the device leaves the big units in the same state; 0: as the sizes fall
  *   "batch_parts"      sequential RANF stream, default event generator: every batch is cut into that many equal parts (1 = whole
  *                      batches, the default; 2, 5, 10; 0 = the largest of those for which the launch still fits one
  *                      wave of resident warps), one warp each, and the parts of a batch are added in part order: a small run

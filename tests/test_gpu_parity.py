@@ -210,14 +210,16 @@ def test_batches_match_oracle_f64(sims, oracle, valeurs_text, features, kernel):
         assert_acc_close(accs[b], want, REL_F64, what=f"batch {b}")
 
 
-@pytest.mark.parametrize("unit,grid,dynamic,ramp", [(2, 2, 0, 0), (3, 1, 0, 0), (5, 0, 0, 0), (16, 0, 0, 0), (2, 3, 0, 0), (2, 0, 1, 0),
-                                                    (3, 1, 1, 0), (8, 0, 1, 0), (3, 1, 1, 8), (8, 2, 1, 8)])
-def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, dynamic, ramp):
+@pytest.mark.parametrize("unit,grid,dynamic,ramp,taper,singles", [
+    (2, 2, 0, 0, 0, 0), (3, 1, 0, 0, 0, 0), (5, 0, 0, 0, 0, 0), (16, 0, 0, 0, 0, 0), (2, 3, 0, 0, 0, 0), (2, 0, 1, 0, 0, 0),
+    (3, 1, 1, 0, 0, 0), (8, 0, 1, 0, 0, 0), (3, 1, 1, 8, 0, 0), (8, 2, 1, 8, 0, 0),
+    (8, 0, 1, 0, 2, 3), (8, 2, 1, 0, 1, 5), (4, 1, 1, 0, 3, 2), (8, 1, 1, 8, 1, 1), (8, 0, 1, 0, -1, 0), (8, 0, 1, 0, -1, 6)])
+def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, dynamic, ramp, taper, singles):
     """A warp that handles several consecutive batches (a scheduling unit) continues the sequential RANF stream instead
     of jumping again; the per-batch accumulators must not depend on how the launch is cut into units, rounds and warps,
     nor on the schedule (static: grids of 1, 2 and 3 warps give several full rounds plus the evenly split last round;
-    dynamic: [ramp units of 1, 2, .., 8 batches,] big units, then single batches; a 1-warp resident set makes every batch
-    of this launch a tail batch) --
+    dynamic: [ramp units of 1, 2, .., 8 batches,] big units, [taper: `taper` half units and `taper` quarter units,] then single
+    batches; a 1-warp resident set makes every batch of this launch a tail batch) --
     bit for bit -- and must match the oracle.  The in-kernel ordered fold equals the host fold for every shape."""
     nb = 43 if dynamic else 11
     cfg = tp3.Configuration.parse(valeurs_text)
@@ -226,6 +228,7 @@ def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, 
         ref = sim.simulate_batches(3, nb, 7777)
     with tp3.Simulator(cfg) as sim:
         sim.set_option("unit_batches", unit).set_option("grid_warps", grid).set_option("sched_dynamic", dynamic).set_option("ramp_units", ramp)
+        sim.set_option("taper_units", taper).set_option("tail_singles", singles)
         got = sim.simulate_batches(3, nb, 7777)
         merged = sim.simulate_merged(3, nb, 7777)
     assert bytes(got) == bytes(ref)
@@ -238,6 +241,29 @@ def test_stream_continues_across_batches(tp3, oracle, valeurs_text, unit, grid, 
         want.variance *= scale * scale
         assert got[b].selected_events == want.selected_events
         assert_acc_close(got[b], want, REL_F64, what=f"batch {3 + b}")
+
+
+@pytest.mark.parametrize("features", ["", "f32"])
+def test_launch_shape_of_a_long_launch_is_bit_neutral(tp3, valeurs_text, features):
+    """The tail of the dynamic schedule at a size where all of it is active (30 011 batches: big units rounded down to a multiple
+    of 4 x SMs, half a wave of half units, half a wave of quarter units, two waves of single batches, a ragged last batch): the
+    per-batch accumulators and the in-kernel ordered fold are the same bits with the taper and the alignment switched off, and
+    with a static schedule."""
+    cfg = tp3.Configuration.parse(valeurs_text, features)
+    nb, last = 30011, 4321
+    with tp3.Simulator(cfg) as sim:
+        ref = sim.simulate_batches(5, nb, last)
+        ref_merged = sim.simulate_merged(5, nb, last)
+    assert bytes(ref_merged) == bytes(tp3.fold(ref, cfg.flags))
+    for opts in ({"taper_units": -1, "align_units": 0}, {"align_units": 0}, {"taper_units": 777, "tail_singles": 1000},
+                 {"sched_dynamic": 0}):
+        with tp3.Simulator(cfg) as sim:
+            for k, v in opts.items():
+                sim.set_option(k, v)
+            got = sim.simulate_batches(5, nb, last)
+            merged = sim.simulate_merged(5, nb, last)
+        assert bytes(got) == bytes(ref), opts
+        assert bytes(merged) == bytes(ref_merged), opts
 
 
 @pytest.mark.parametrize("features", ["", "f32", "no-photon-sorting"])

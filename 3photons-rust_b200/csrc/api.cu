@@ -208,13 +208,19 @@ struct Sched {
 };
 
 // Fill the schedule fields of `a` for a kernel that runs `warps`-warp CTAs, `ctas_per_sm` of them per SM.
-cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& sc) {
+cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& sc, uint64_t max_unit = 8) {
     if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
     uint64_t W = (uint64_t)sc.sm_count * ctas_per_sm * warps;  // what the device holds at once
     if (sc.grid_warps > 0) W = ((uint64_t)sc.grid_warps + warps - 1) / warps * warps;
     if (sc.dynamic) {
         // Units in batch order, one warp each: big units of `unit` batches, then single batches for the last ~4 waves.
-        uint64_t unit = sc.stream_continues ? 8 : 1;
+        // Big units: the largest power of two <= max_unit that keeps a big unit shorter than half of what the launch takes (fixed
+        // units of 8 made a launch of 12 000 batches take 4.3 instead of 3.4 ms).  max_unit is 16 for the f64 kernel -- every unit pays
+        // one jump-ahead and one CTA turnover, 10-20 us: 0.15 % at 1e6 batches -- and 8 for the f32 kernels, whose launches from
+        // 125 000 batches up came out 0.2-0.3 ms LONGER with units of 16 (profiles/r02_tail_scan.txt).
+        uint64_t unit = 1;
+        if (sc.stream_continues)
+            while (unit < max_unit && 2 * unit * 2 * W <= a.n_batches) unit *= 2;
         if (sc.unit_batches > 0) unit = (uint64_t)sc.unit_batches;
         // ramp: the first wave's warps start together; unequal first units (1, 2, .., 8 batches) take them out of step at once
         // (measured: it does not pay, profiles/r02_schedule_ab.txt: the first wave drifts apart quickly enough on its own; off by default)
@@ -287,7 +293,7 @@ cudaError_t launch_sim(SimArgs a, const tp3_params& p, cudaStream_t st, const Sc
     constexpr int warps = sim_warps(LITERAL, false);
     auto kernel = simulate_kernel<F, RNG, SORT, LITERAL>;
     static const int occ = ctas_per_sm(kernel, 32 * warps, 0);
-    if (cudaError_t e = fill_schedule(a, warps, occ, sc)) return e;
+    if (cudaError_t e = fill_schedule(a, warps, occ, sc, sizeof(F) == 8 && !LITERAL ? 16 : 8)) return e;
     kernel<<<a.n_warps / warps, 32 * warps, 0, st>>>(a, phys_params<F>(p));
     return cudaGetLastError();
 }

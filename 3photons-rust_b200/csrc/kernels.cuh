@@ -12,9 +12,11 @@
 // Scheduling (multi_threading.rs:46-70 hands out batches to its workers one by one).  The launch's batches are cut into UNITS
 // of consecutive batches, in batch order; the sequential RANF stream is re-positioned once per unit and simply continues
 // inside it.  Two schedules (profiles/r02_schedule_ab.txt):
-//   * dynamic (shipped): one warp per unit, dispatched by the hardware in unit order.  Units of 8 batches first, then
-//     single batches for the last ~4 waves, so that the device drains within one batch time whatever the launch size
-//     (round 1 used 1-8 equal batches per CTA: 8.8 waves and a 3 % tail at 125 000 batches per GPU).
+//   * dynamic (shipped): one warp per unit, dispatched by the hardware in unit order.  Big units first (16 batches for the f64
+//     kernel, 8 for f32, fewer in short launches), their number a multiple of 4 x SMs; then half a wave of half units, half a wave
+//     of quarter units and two waves of single batches, so that the device drains within one batch time whatever the launch
+//     size (api.cu: fill_schedule; DESIGN.md section 4e has the trace of every unit this was designed from; round 1 used 1-8
+//     equal batches per CTA: 8.8 waves and a 3 % tail at 125 000 batches per GPU).
 //   * static: exactly as many warps as the device holds, each walking the same number of units (+- one batch).  No tail
 //     at all, but 11 % SLOWER: warps that start together stay in step, so their integer phases (stream generation)
 //     and FP64 phases collide instead of overlapping; warps that start at staggered times do not.

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device time of the default fused kernel (in-kernel fold) as a function of the launch size around the 8-GPU share of the
 1e10-event run: T(n) against the straight line through the 1e6-batch rate shows what the launch shape costs at each n.
-usage: tail_probe.py [features] [option=value ...] [--short]"""
+usage: tail_probe.py [features] [option=value ...] [--short | n=size,size,...]"""
 import os
 import sys
 
@@ -13,7 +13,8 @@ import __graft_entry__ as entry  # noqa: E402
 pkg = entry.package()
 features = sys.argv[1] if len(sys.argv) > 1 else ""
 short = "--short" in sys.argv
-opts = [a.split("=") for a in sys.argv[2:] if a != "--short"]
+sizes = [int(float(x)) for a in sys.argv[2:] if a.startswith("n=") for x in a[2:].split(",")]
+opts = [a.split("=") for a in sys.argv[2:] if a != "--short" and not a.startswith("n=")]
 text = open(os.path.join(ROOT, "tests", "golden", "valeurs")).read()
 st = torch.cuda.current_stream()
 out13 = torch.zeros(13, dtype=torch.float64, device="cuda")
@@ -42,6 +43,6 @@ def timed(n, K):
 
 ref = timed(1000000, 4) / 1000000
 print(f"# features {features!r} options {opts}: {ref * 1e3:.4f} us per batch at 1e6 batches", flush=True)
-for n in ([120768, 123136, 125000, 125504, 250000, 500000] if short else list(range(104192, 142081, 2368)) + [125000, 250000, 500000]):
+for n in sizes if sizes else ([120768, 123136, 125000, 125504, 250000, 500000] if short else list(range(104192, 142081, 2368)) + [125000, 250000, 500000]):
     t = timed(n, 10)
     print(f"n = {n:7d}  T = {t:8.3f} ms   T - n * rate = {t - n * ref:6.3f} ms   efficiency {n * ref / t:.4f}", flush=True)

@@ -213,7 +213,7 @@ cudaError_t fill_schedule(SimArgs& a, int warps, int ctas_per_sm, const Sched& s
     uint64_t W = (uint64_t)sc.sm_count * ctas_per_sm * warps;  // what the device holds at once
     if (sc.grid_warps > 0) W = ((uint64_t)sc.grid_warps + warps - 1) / warps * warps;
     if (sc.dynamic) {
-        // Units in batch order, one warp each: big units of `unit` batches, then single batches for the last ~4 waves.
+        // Units in batch order, one warp each: big units of `unit` batches, then the tail described below.
         // Big units: the largest power of two <= max_unit that keeps a big unit shorter than half of what the launch takes (fixed
         // units of 8 made a launch of 12 000 batches take 4.3 instead of 3.4 ms).  max_unit is 16 for the f64 kernel -- every unit pays
         // one jump-ahead and one CTA turnover, 10-20 us: 0.15 % at 1e6 batches -- and 8 for the f32 kernels, whose launches from

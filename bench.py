@@ -196,7 +196,7 @@ def run_reference(args, rank):
 # FP64 work the shipped fast f64 kernel EXECUTES per generated event (SASS-counted from the committed ncu capture:
 # DFMA = 2 flops, DMUL / DADD = 1), and the ncu FP64-pipe active fraction of the bench's own launch.
 EXECUTED = {"source": "profiles/r02_bench_kernel_1e10_events.txt (ncu --set full of this launch: 1e6 batches, in-kernel fold on)",
-            "dfma": 161.2, "dmul": 104.6, "dadd": 54.0, "pipe_active": 0.679, "traffic": 3663360 + 58386432}
+            "dfma": 161.2, "dmul": 104.6, "dadd": 54.0, "pipe_active": 0.682, "traffic": 3760896 + 60777984}
 
 
 def main():

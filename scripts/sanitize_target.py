@@ -21,6 +21,13 @@ def run(features, kernel=0, opts=(), hist=0, n=(0, 3, 5000), dump=True):
         print(features or "default", kernel, dict(opts), [a.selected_events for a in accs], m.selected_events, extra, flush=True)
 
 
+# --schedule: only the launch shapes of the dynamic schedule added in sessions 52-64 (taper stages, big units of 16, f32 packed kernel)
+if "--schedule" in sys.argv:
+    run("", opts=(("unit_batches", 8), ("taper_units", 2), ("tail_singles", 3)), n=(2, 43, 777), dump=False)
+    run("", opts=(("unit_batches", 16), ("taper_units", 1), ("tail_singles", 2), ("grid_warps", 2)), n=(0, 47, 10000), dump=False)
+    run("f32", opts=(("unit_batches", 4), ("taper_units", 3), ("tail_singles", 2)), n=(1, 31, 1234), dump=False)
+    run("", opts=(("taper_units", -1), ("align_units", 0)), n=(0, 9, 5000), dump=False)
+    sys.exit(0)
 # every generator / precision / seeding through the fused kernels, in-kernel ordered fold included
 for features, kernel in [("", 0), ("", 1), ("standard-random", 0), ("f32", 0), ("standard-random,f32", 0), ("multi-threading,faster-threading", 0)]:
     run(features, kernel)
